@@ -1,0 +1,315 @@
+"""Bridge from a circuit compiled by the reference (`cirkit.pipeline.compile`) to a plan.
+
+This module is the only place that touches the reference package, and it imports it lazily:
+everything else in `cirkit_b200` runs without `cirkit` installed (e.g. from a stored plan).
+
+* :func:`plan_from_torch` walks `TorchCircuit.address_book`
+  (`cirkit/backend/torch/graph/modules.py:168-187`) and every layer's `config` / `params`
+  (`layers/base.py:54-75`) and lowers them to a :class:`~cirkit_b200.plan.CircuitPlan`.
+* :func:`accelerate` swaps the executor of an existing `TorchCircuit` in place: the object keeps
+  its class hierarchy, layers, address book, `state_dict` keys and -- crucially -- the very same
+  `nn.Parameter` leaves (`TorchTensorParameter._ptensor`, `parameters/nodes.py:193-201`), so
+  optimisers, checkpoints and pointer-shared integrate/multiply circuits keep working; only
+  `forward` / `evaluate` are re-routed to the CUDA runtime.
+* :func:`register_backend` makes `PipelineContext(backend="b200", ...)` work by extending the
+  reference's backend switch (`cirkit/pipeline.py:348-356`, `backend/compiler.py:11`).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+import torch
+from torch import nn
+
+from .plan import CircuitPlan, LeafSpec, ParamSpec, StepSpec
+
+
+class UnsupportedCircuitError(NotImplementedError):
+    """The circuit holds a layer or parameterisation the CUDA runtime has no kernel for."""
+
+
+@dataclass
+class LoweredCircuit:
+    plan: CircuitPlan
+    leaves: list[nn.Parameter]  # the reference's own leaf tensors, in plan.leaves order
+    externals: dict[tuple[int, str], Any] = field(default_factory=dict)  # (step, name) -> TorchParameter
+
+
+# --------------------------------------------------------------------------- parameters
+def _lower_param(p, leaf_ids: dict[int, int], leaves: list, leaf_specs: list[LeafSpec],
+                 names: dict[int, str]) -> ParamSpec | None:
+    """Recognise `leaf [-> pointer slice] -> unary op chain` parameter graphs.
+
+    Returns None when the graph is anything else (kron/matmul/einsum nodes produced by
+    multiply/integrate or by the SumCollapse rule) -- the caller then keeps it *external*:
+    the host evaluates the reference's own `TorchParameter` with PyTorch and feeds the result
+    to the kernels (such graphs run once per step on small tensors).
+    """
+    from cirkit.backend.torch.parameters import nodes as N
+
+    op_names = {
+        N.TorchSoftmaxParameter: "softmax",
+        N.TorchLogSoftmaxParameter: "log_softmax",
+        N.TorchScaledSigmoidParameter: "scaled_sigmoid",
+        N.TorchSigmoidParameter: "sigmoid",
+        N.TorchExpParameter: "exp",
+        N.TorchLogParameter: "log",
+        N.TorchSquareParameter: "square",
+        N.TorchSoftplusParameter: "softplus",
+        N.TorchClampParameter: "clamp",
+        N.TorchMixingWeightParameter: "mixing",
+    }
+    entries = list(p.address_book)
+    mods = [e.module for e in entries[:-1]]
+    if not mods:
+        return None
+    head = mods[0]
+    fold_idx = None
+    if isinstance(head, N.TorchPointerParameter):
+        fold_idx = None if head._fold_idx is None else head._fold_idx.cpu().numpy().astype(np.int64)
+        head = head.deref()
+    if not isinstance(head, N.TorchTensorParameter) or head._ptensor is None:
+        return None
+    ops: list[tuple[str, dict[str, Any]]] = []
+    for i, e in enumerate(entries[1:-1], start=1):
+        m = e.module
+        if type(m) not in op_names:
+            return None
+        # must consume exactly the previous node, un-permuted
+        if e.in_module_ids != [[i - 1]] or len(e.in_fold_idx) != 1:
+            return None
+        fi = e.in_fold_idx[0]
+        if isinstance(fi, torch.Tensor):
+            if fi.tolist() != list(range(mods[i - 1].num_folds)):
+                return None
+        elif fi != ():
+            return None
+        attrs: dict[str, Any] = {}
+        if hasattr(m, "dim"):
+            attrs["dim"] = int(m.dim)
+        if isinstance(m, (N.TorchScaledSigmoidParameter, N.TorchClampParameter)):
+            attrs["vmin"] = None if m.vmin is None else float(m.vmin)
+            attrs["vmax"] = None if m.vmax is None else float(m.vmax)
+        ops.append((op_names[type(m)], attrs))
+    last = entries[-1]
+    if last.in_module_ids != [[len(mods) - 1]]:
+        return None
+    if last.in_fold_idx[0].tolist() != list(range(mods[-1].num_folds)):
+        return None
+    key = id(head._ptensor)
+    if key not in leaf_ids:
+        leaf_ids[key] = len(leaves)
+        leaves.append(head._ptensor)
+        leaf_specs.append(
+            LeafSpec(tuple(head._ptensor.shape), "normal", bool(head._ptensor.requires_grad),
+                     names.get(key, ""))
+        )
+    return ParamSpec(leaf_ids[key], ops, (p.num_folds, *p.shape), fold_idx)
+
+
+# --------------------------------------------------------------------------- layers
+def plan_from_torch(tc, *, allow_external_params: bool = True) -> LoweredCircuit:
+    """Lower a compiled `TorchCircuit` to a plan (see module docstring)."""
+    from cirkit.backend.torch.layers.inner import (
+        TorchHadamardLayer,
+        TorchKroneckerLayer,
+        TorchSumLayer,
+    )
+    from cirkit.backend.torch.layers.input import (
+        TorchCategoricalLayer,
+        TorchConstantValueLayer,
+        TorchEmbeddingLayer,
+        TorchGaussianLayer,
+    )
+    from cirkit.backend.torch.layers.optimized import TorchCPTLayer, TorchTuckerLayer
+    from cirkit.backend.torch.semiring import LSESumSemiring
+
+    names = {id(t): n for n, t in tc.named_parameters()}
+    leaf_ids: dict[int, int] = {}
+    leaves: list[nn.Parameter] = []
+    leaf_specs: list[LeafSpec] = []
+    externals: dict[tuple[int, str], Any] = {}
+    steps: list[StepSpec] = []
+    entries = list(tc.address_book)
+    num_folds: list[int] = []
+
+    def resolve(in_ids: list[int], idx, F: int, H: int) -> tuple[np.ndarray, np.ndarray]:
+        sizes = [num_folds[i] for i in in_ids]
+        total = sum(sizes)
+        if isinstance(idx, torch.Tensor):
+            flat = idx.cpu().numpy().astype(np.int64).reshape(-1)
+        else:  # unsqueeze shortcuts, graph/folding.py:235-241
+            flat = np.arange(total, dtype=np.int64)
+        bounds = np.cumsum([0] + sizes)
+        which = np.searchsorted(bounds, flat, side="right") - 1
+        step = np.asarray(in_ids, dtype=np.int64)[which]
+        fold = flat - bounds[which]
+        return step.reshape(F, H).astype(np.int32), fold.reshape(F, H).astype(np.int32)
+
+    for sid, e in enumerate(entries[:-1]):
+        m = e.module
+        if m.semiring is not LSESumSemiring:
+            raise UnsupportedCircuitError(
+                f"semiring {m.semiring.__name__} has no CUDA path yet (lse-sum only)"
+            )
+        F = m.num_folds
+        params: dict[str, ParamSpec] = {}
+        for name, p in m.params.items():
+            spec = _lower_param(p, leaf_ids, leaves, leaf_specs, names)
+            if spec is None:
+                if not allow_external_params:
+                    raise UnsupportedCircuitError(f"step {sid}: parameter graph of {name!r}")
+                spec = ParamSpec(-1, [], (p.num_folds, *p.shape), None)
+                externals[(sid, name)] = p
+            params[name] = spec
+        kind: str
+        config: dict[str, Any] = {}
+        scope_idx = None
+        in_step = in_fold = None
+        if isinstance(m, TorchCategoricalLayer):
+            kind = "categorical"
+            config["num_categories"] = int(m.num_categories)
+        elif isinstance(m, TorchEmbeddingLayer):
+            kind = "embedding"
+            config["num_states"] = int(m.num_states)
+        elif isinstance(m, TorchGaussianLayer):
+            kind = "gaussian"
+        elif isinstance(m, TorchConstantValueLayer):
+            kind = "constant"
+            config["log_space"] = bool(m.log_space)
+        elif isinstance(m, TorchCPTLayer):
+            kind = "cpt"
+        elif isinstance(m, TorchTuckerLayer):
+            kind = "tucker"
+        elif isinstance(m, TorchSumLayer):
+            kind = "sum"
+            w = params["weight"]
+            if w.leaf >= 0 and w.ops and w.ops[-1][0] == "mixing":
+                kind = "mixing"
+                params["weight"] = ParamSpec(
+                    w.leaf, w.ops[:-1], (F, m.num_output_units, m.arity), w.fold_idx
+                )
+        elif isinstance(m, TorchHadamardLayer):
+            kind = "hadamard"
+        elif isinstance(m, TorchKroneckerLayer):
+            kind = "kronecker"
+        else:
+            raise UnsupportedCircuitError(f"step {sid}: no CUDA kernel for {type(m).__name__}")
+        if kind in ("categorical", "embedding", "gaussian"):
+            if m.num_variables != 1:
+                raise UnsupportedCircuitError(f"step {sid}: multivariate input layer")
+            scope_idx = m.scope_idx.cpu().numpy().astype(np.int32).reshape(F)
+            arity, k_in = 1, 1
+        elif kind == "constant":
+            arity, k_in = 1, 0
+        else:
+            arity, k_in = int(m.arity), int(m.num_input_units)
+            in_step, in_fold = resolve(e.in_module_ids[0], e.in_fold_idx[0], F, arity)
+        steps.append(
+            StepSpec(kind, F, arity, k_in, int(m.num_output_units), params, in_step, in_fold,
+                     scope_idx, config)
+        )
+        num_folds.append(F)
+
+    last = entries[-1]
+    out_step, out_fold = resolve(last.in_module_ids[0], last.in_fold_idx[0], -1, 1)
+    scope = tuple(sorted(tc.scope))
+    plan = CircuitPlan(
+        steps=steps,
+        leaves=leaf_specs,
+        out_step=out_step.reshape(-1),
+        out_fold=out_fold.reshape(-1),
+        num_variables=(max(scope) + 1) if scope else 0,
+        scope=scope,
+        semiring="lse-sum",
+    )
+    plan.validate()
+    return LoweredCircuit(plan, leaves, externals)
+
+
+# --------------------------------------------------------------------------- executor swap
+def accelerate(tc, *, strict: bool = False):
+    """Re-route `tc(x)` to the CUDA runtime, in place; returns `tc`.
+
+    The circuit object, its parameters and its `state_dict` are untouched.  When the circuit
+    holds something the runtime cannot lower, `strict=False` leaves it on the reference path
+    (and records why in `tc._b200_reason`); `strict=True` raises UnsupportedCircuitError.
+    """
+    from .runtime import PlanRuntime
+
+    try:
+        lowered = plan_from_torch(tc)
+    except UnsupportedCircuitError as exc:
+        if strict:
+            raise
+        tc._b200_reason = str(exc)
+        return tc
+
+    base = type(tc)
+    runtime = PlanRuntime(lowered.plan)
+
+    def _tensors(self):
+        ext = {k: p() for k, p in lowered.externals.items()}
+        return lowered.leaves, ext
+
+    class B200Circuit(base):  # type: ignore[misc, valid-type]
+        """`TorchCircuit` whose layer loop runs as sm_100a kernels (cirkit_b200)."""
+
+        def forward(self, x=None):  # circuits.py:242-261
+            if self._scope and x is None:
+                raise ValueError(
+                    f"Expected some input 'x', as the circuit has scope '{self._scope}'"
+                )
+            leaves, ext = _tensors(self)
+            y = runtime.evaluate(x, leaves, ext)  # (B, O, K)
+            if not self._scope:
+                y = y.squeeze(dim=0)
+            return y
+
+        def evaluate(self, x=None, module_fn=None):  # graph/modules.py:303-335
+            if module_fn is not None:
+                return super().evaluate(x, module_fn)
+            leaves, ext = _tensors(self)
+            return runtime.evaluate(x, leaves, ext).transpose(0, 1)
+
+        def integrate_query(self, x, mask):
+            leaves, ext = _tensors(self)
+            return runtime.evaluate(x, leaves, ext, integrate_mask=mask)
+
+    B200Circuit.__name__ = f"B200{base.__name__}"
+    tc.__class__ = B200Circuit
+    tc._b200_runtime = runtime
+    tc._b200_lowered = lowered
+    return tc
+
+
+def register_backend() -> None:
+    """Teach the reference's pipeline the backend name ``"b200"``.
+
+    `PipelineContext(backend="b200", semiring=..., fold=..., optimize=...)` then compiles with
+    the reference's own torch front-end (rules, optimiser, folding: SURVEY §2 rows 11-15) and
+    hands every compiled circuit to :func:`accelerate`.
+    """
+    import cirkit.backend.compiler as BC
+    import cirkit.pipeline as P
+    from cirkit.backend.torch.compiler import TorchCompiler
+
+    if "b200" in BC.SUPPORTED_BACKENDS:
+        return
+
+    class B200Compiler(TorchCompiler):
+        def compile_pipeline(self, sc):  # backend/torch/compiler.py:140-151
+            return accelerate(super().compile_pipeline(sc))
+
+    BC.SUPPORTED_BACKENDS.append("b200")
+    prev = P.retrieve_compiler
+
+    def retrieve_compiler(backend: str, **backend_kwargs):
+        if backend == "b200":
+            return B200Compiler(**backend_kwargs)
+        return prev(backend, **backend_kwargs)
+
+    P.retrieve_compiler = retrieve_compiler

@@ -1,0 +1,259 @@
+"""Generate the golden fixtures under tests/golden/ from the REAL reference.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [--only NAME ...]
+
+For every case the reference's own torch backend (CPU, float64, `PipelineContext(backend="torch",
+semiring="lse-sum", fold=..., optimize=...)`) is compiled and evaluated; the compiled circuit is
+lowered to a `CircuitPlan` (cirkit_b200.adapter) and stored with the reference's outputs and
+autograd gradients.  Two kinds of files are written:
+
+* ``<name>.npz`` "full" fixtures (small circuits): plan, leaf values, inputs, reference outputs
+  ``y`` and the gradient of ``-mean(y)`` w.r.t. every leaf, plus optional integrate-query masks
+  and their outputs.  The two known-answer circuits of the reference's test-suite
+  (`tests/symbolic/test_utils.py:293-503`) also carry the hand-computed numbers.
+* ``<name>.npz`` "seeded" fixtures (benchmark-size circuits): plan + the seed the leaves are drawn
+  from (`cirkit_b200.plan.seeded_leaves`), inputs, reference outputs, and per-leaf gradient
+  summaries (sum, abs-sum and a strided probe), so the 10^7..10^8 parameters never hit the repo.
+"""
+
+from __future__ import annotations
+
+import argparse
+import itertools
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, "/root/reference")  # `cirkit` and the reference's `tests` package
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from cirkit.pipeline import PipelineContext  # noqa: E402
+from cirkit.backend.torch.queries import IntegrateQuery  # noqa: E402
+from cirkit.templates import data_modalities, utils  # noqa: E402
+import cirkit.symbolic.functional as SF  # noqa: E402
+from cirkit.symbolic.circuit import Circuit  # noqa: E402
+from cirkit.symbolic.layers import CategoricalLayer, EmbeddingLayer, GaussianLayer, SumLayer, HadamardLayer  # noqa: E402
+from cirkit.symbolic.parameters import Parameter, TensorParameter, SoftmaxParameter  # noqa: E402
+from cirkit.symbolic.initializers import NormalInitializer, UniformInitializer  # noqa: E402
+from cirkit.utils.scope import Scope  # noqa: E402
+
+from cirkit_b200.adapter import plan_from_torch  # noqa: E402
+from cirkit_b200.plan import seeded_leaves  # noqa: E402
+
+PROBE = 64  # gradient entries kept per leaf in seeded fixtures
+
+
+def compile_ref(sc, fold=True, optimize=True):
+    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=fold, optimize=optimize)
+    return ctx, ctx.compile(sc)
+
+
+def plan_array(plan) -> np.ndarray:
+    return np.frombuffer(plan.to_bytes(), dtype=np.uint8)
+
+
+def ref_forward_backward(tc, leaves, x):
+    for p in leaves:
+        p.grad = None
+    with torch.enable_grad():
+        y = tc(x)
+        (-y.mean()).backward()
+    return y.detach(), [
+        (torch.zeros_like(p) if p.grad is None else p.grad.detach().clone()) for p in leaves
+    ]
+
+
+def write_full(name, tc, x, *, masks=None, extra=None):
+    low = plan_from_torch(tc, allow_external_params=False)
+    y, grads = ref_forward_backward(tc, low.leaves, x)
+    out = {"plan": plan_array(low.plan), "x": x.numpy(), "y": y.numpy()}
+    for i, (p, g) in enumerate(zip(low.leaves, grads)):
+        out[f"leaf_{i}"] = p.detach().numpy()
+        out[f"grad_{i}"] = g.numpy()
+    if masks is not None:
+        q = IntegrateQuery(tc)
+        with torch.no_grad():
+            out["mask"] = masks.numpy()
+            out["y_mask"] = q(x, integrate_vars=masks).numpy()
+    meta = {"kind": "full", "steps": [s.kind for s in low.plan.steps]}
+    meta.update(extra or {})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(f"{name}: steps={meta['steps']} B={x.shape[0]} y[0]={y.reshape(-1)[0].item():.6f}")
+
+
+def write_seeded(name, tc, x, seed, extra=None):
+    low = plan_from_torch(tc, allow_external_params=False)
+    vals = seeded_leaves(low.plan, seed)
+    with torch.no_grad():
+        for p, v in zip(low.leaves, vals):
+            p.copy_(v.to(p.dtype))
+    y, grads = ref_forward_backward(tc, low.leaves, x)
+    out = {"plan": plan_array(low.plan), "x": x.numpy(), "y": y.numpy()}
+    for i, g in enumerate(grads):
+        flat = g.reshape(-1)
+        stride = max(1, flat.numel() // PROBE)
+        idx = torch.arange(0, flat.numel(), stride)[:PROBE]
+        out[f"gsum_{i}"] = np.array([flat.sum().item(), flat.abs().sum().item(), flat.abs().max().item()])
+        out[f"gidx_{i}"] = idx.numpy()
+        out[f"gval_{i}"] = flat[idx].numpy()
+    meta = {"kind": "seeded", "seed": seed, "steps": [s.kind for s in low.plan.steps]}
+    meta.update(extra or {})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(f"{name}: steps={len(meta['steps'])} B={x.shape[0]} y[0]={y.reshape(-1)[0].item():.6f} "
+          f"A={low.plan.activation_units()} P={low.plan.parameter_elements()}")
+
+
+# --------------------------------------------------------------------------- cases
+def image_circuit(shape, rg, spl, K, input_layer="categorical", **kw):
+    return data_modalities.image_data(
+        shape, region_graph=rg, input_layer=input_layer, num_input_units=K,
+        sum_product_layer=spl, num_sum_units=K,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"),
+        **kw,
+    )
+
+
+def case_ka_categorical():
+    """Hand-computed 5-variable circuit, reference tests/symbolic/test_utils.py:293-417."""
+    from tests.symbolic.test_utils import build_monotonic_structured_categorical_cpt_pc
+
+    sc, gt, gt_z = build_monotonic_structured_categorical_cpt_pc(return_ground_truth=True)
+    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True)
+    tc = ctx.compile(sc)
+    int_tc = ctx.compile(SF.integrate(sc))
+    worlds = torch.tensor(list(itertools.product([0, 1], repeat=5)))
+    mask = torch.zeros(32, 5, dtype=torch.bool)
+    mask[:, 4] = True
+    extra = {
+        "evi": {"".join(map(str, k)): v for k, v in gt["evi"].items()},
+        "mar": {"10110": 16.845},
+        "Z": gt_z,
+        "source": "tests/symbolic/test_utils.py:411-417",
+    }
+    write_full("ka_categorical_cpt", tc, worlds, masks=mask, extra=extra)
+    with torch.no_grad():
+        z = int_tc()
+    low = plan_from_torch(int_tc, allow_external_params=False)
+    out = {"plan": plan_array(low.plan), "y": z.numpy()}
+    for i, p in enumerate(low.leaves):
+        out[f"leaf_{i}"] = p.detach().numpy()
+    out["meta"] = np.frombuffer(json.dumps({"kind": "constant", "Z": gt_z}).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ka_categorical_cpt_Z.npz"), **out)
+    print("ka_categorical_cpt_Z: logZ", z.item(), "exp", z.exp().item())
+
+
+def case_ka_gaussian():
+    """Hand-computed bivariate Gaussian circuit, tests/symbolic/test_utils.py:420-503."""
+    from tests.symbolic.test_utils import build_monotonic_bivariate_gaussian_hadamard_dense_pc
+
+    sc, gt, gt_z = build_monotonic_bivariate_gaussian_hadamard_dense_pc(return_ground_truth=True)
+    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True)
+    tc = ctx.compile(sc)
+    x = torch.tensor([[0.3, 1.2], [0.3, 1.2], [-1.0, 0.25], [2.0, -3.0]])
+    mask = torch.tensor([[False, False], [False, True], [True, False], [True, True]])
+    extra = {
+        "evi": {"0": 3.744904862456293},
+        "mar": {"1": 23.528960785605985},
+        "Z": gt_z,
+        "source": "tests/symbolic/test_utils.py:497-503",
+    }
+    write_full("ka_gaussian", tc, x, masks=mask, extra=extra)
+
+
+def case_random_small():
+    B = 24
+    torch.manual_seed(42)
+    x8 = torch.randint(0, 256, (B, 64))
+    m8 = torch.rand(B, 64) < 0.3
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-tree-2", "cp", 4))
+    write_full("qt8_cp_k4", tc, x8, masks=m8)
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-graph", "cp", 4))
+    write_full("qg8_cp_k4", tc, x8)
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-tree-2", "tucker", 4))
+    write_full("qt8_tucker_k4", tc, x8)
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-tree-2", "tucker", 3), optimize=False)
+    write_full("qt8_kronecker_k3_unopt", tc, x8)
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-tree-4", "cp-t", 5))
+    write_full("qt8x4_cpt_k5", tc, x8)
+    _, tc = compile_ref(image_circuit((1, 6, 6), "poon-domingos", "cp", 3), optimize=False)
+    write_full("pd6_cp_k3_unopt", tc, torch.randint(0, 256, (B, 36)))
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-graph", "cp", 4, use_mixing_weights=False))
+    write_full("qg8_cp_k4_densemix", tc, x8)
+    _, tc = compile_ref(image_circuit((1, 8, 8), "quad-tree-2", "cp", 6, input_layer="embedding"))
+    # embedding weights must be positive for the log-space path: re-draw them uniform
+    low = plan_from_torch(tc)
+    with torch.no_grad():
+        for p, s in zip(low.leaves, low.plan.leaves):
+            if len(s.shape) == 3 and s.shape[-1] == 256:
+                p.uniform_(0.05, 1.0)
+    write_full("qt8_cp_k6_embedding", tc, x8)
+    # Gaussian leaves over a random binary tree (tabular route)
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=12, input_layers={"name": "gaussian", "args": {}},
+        num_input_units=5, sum_product_layer="cp", num_sum_units=5,
+    )
+    _, tc = compile_ref(sc)
+    xg = torch.randn(B, 12)
+    write_full("rbt12_gaussian_k5", tc, xg, masks=torch.rand(B, 12) < 0.4)
+    # 1-D Gaussian mixture, 8 components (BASELINE.json configs[0])
+    g = GaussianLayer(Scope((0,)), 8)
+    s = SumLayer(8, 1, 1, weight_factory=lambda shape: Parameter.from_unary(
+        SoftmaxParameter(shape), TensorParameter(*shape, initializer=NormalInitializer())))
+    sc = Circuit([g, s], in_layers={s: [g]}, outputs=[s])
+    _, tc = compile_ref(sc)
+    write_full("gmm1d_k8", tc, torch.randn(64, 1))
+    # categorical layers parameterised by unnormalised logits (integrate -> logsumexp)
+    ins = [CategoricalLayer(Scope((v,)), 3, num_categories=5,
+                            logits_factory=lambda shape: Parameter.from_input(
+                                TensorParameter(*shape, initializer=NormalInitializer())))
+           for v in range(4)]
+    h1, h2 = HadamardLayer(3, 2), HadamardLayer(3, 2)
+    wf = lambda shape: Parameter.from_unary(
+        SoftmaxParameter(shape), TensorParameter(*shape, initializer=NormalInitializer()))
+    s1, s2 = SumLayer(3, 3, 1, weight_factory=wf), SumLayer(3, 3, 1, weight_factory=wf)
+    h3 = HadamardLayer(3, 2)
+    s3 = SumLayer(3, 1, 1, weight_factory=wf)
+    sc = Circuit(ins + [h1, h2, s1, s2, h3, s3],
+                 in_layers={h1: ins[:2], h2: ins[2:], s1: [h1], s2: [h2], h3: [s1, s2], s3: [h3]},
+                 outputs=[s3])
+    _, tc = compile_ref(sc)
+    write_full("cat_logits_k3", tc, torch.randint(0, 5, (B, 4)))
+
+
+def case_bench():
+    torch.manual_seed(42)
+    x = torch.randint(0, 256, (8, 784))
+    _, tc = compile_ref(image_circuit((1, 28, 28), "quad-tree-2", "cp", 32))
+    write_seeded("qt28_cp_k32", tc, x, seed=1234, extra={"units": 32, "config": 1})
+    _, tc = compile_ref(image_circuit((1, 28, 28), "quad-tree-2", "cp", 64))
+    write_seeded("qt28_cp_k64", tc, x, seed=1234, extra={"units": 64, "config": "north-star"})
+    _, tc = compile_ref(image_circuit((1, 28, 28), "quad-tree-2", "tucker", 64))
+    write_seeded("qt28_tucker_k64", tc, x[:4], seed=1234, extra={"units": 64, "config": 2})
+
+
+CASES = {
+    "ka_categorical": case_ka_categorical,
+    "ka_gaussian": case_ka_gaussian,
+    "random_small": case_random_small,
+    "bench": case_bench,
+}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(42)
+    np.random.seed(42)
+    for name, fn in CASES.items():
+        if args.only is None or name in args.only:
+            fn()

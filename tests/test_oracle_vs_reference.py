@@ -1,0 +1,140 @@
+"""Pin the oracle (and the adapter's lowering) against the LIVE reference.
+
+Runs only where the reference checkout exists (the build container); on the GPU box the same
+guarantee travels as tests/golden/*.npz.
+"""
+import itertools
+
+import pytest
+import torch
+
+from oracle import OracleCircuit
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(autouse=True)
+def _fp64():
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(42)
+    yield
+    torch.set_default_dtype(prev)
+
+
+def _image(reference, shape, rg, spl, K, **kw):
+    from cirkit.templates import data_modalities, utils
+
+    return data_modalities.image_data(
+        shape, region_graph=rg, input_layer=kw.pop("input_layer", "categorical"),
+        num_input_units=K, sum_product_layer=spl, num_sum_units=K,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"), **kw)
+
+
+def _compare(tc, x):
+    from cirkit_b200.adapter import plan_from_torch
+
+    low = plan_from_torch(tc)
+    oc = OracleCircuit(low.plan, dtype=torch.float64)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, low.leaves):
+            p.copy_(v)
+    for p in low.leaves:
+        p.grad = None
+    ext = {k: p() for k, p in low.externals.items()}
+    y_ref = tc(x)
+    y = oc(x, externals={k: v.detach() for k, v in ext.items()})
+    assert y.shape == y_ref.shape
+    torch.testing.assert_close(y, y_ref, rtol=1e-10, atol=1e-12)
+    if not low.externals:
+        (-y_ref.mean()).backward()
+        (-y.mean()).backward()
+        for a, b in zip(oc.leaves, low.leaves):
+            ga = torch.zeros_like(a) if a.grad is None else a.grad
+            gb = torch.zeros_like(b) if b.grad is None else b.grad
+            torch.testing.assert_close(ga, gb, rtol=1e-9, atol=1e-14)
+    return low
+
+
+@pytest.mark.parametrize(
+    "rg,spl,fold,optimize",
+    [(rg, spl, f, o)
+     for rg, spl in [("quad-tree-2", "cp"), ("quad-graph", "cp"), ("quad-tree-2", "tucker"),
+                     ("quad-tree-4", "cp-t"), ("poon-domingos", "cp"), ("random-binary-tree", "cp")]
+     for f, o in [(True, True), (True, False), (False, False)]],
+)
+def test_image_circuits(reference, rg, spl, fold, optimize):
+    from cirkit.pipeline import PipelineContext
+
+    sc = _image(reference, (1, 4, 4) if not fold else (1, 6, 6), rg, spl, 3)
+    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=fold, optimize=optimize)
+    tc = ctx.compile(sc)
+    D = 16 if not fold else 36
+    with torch.enable_grad():
+        _compare(tc, torch.randint(0, 256, (5, D)))
+
+
+def test_known_answer_circuits(reference):
+    """The reference's own ground truths (tests/symbolic/test_utils.py:293-503) through the
+    adapter + oracle, for every fold/optimize combination the reference tests
+    (tests/backend/torch/test_compile_circuit.py:76-114)."""
+    import cirkit.symbolic.functional as SF
+    from cirkit.backend.torch.compiler import TorchCompiler
+    from cirkit_b200.adapter import plan_from_torch
+    from tests.symbolic.test_utils import (
+        build_monotonic_bivariate_gaussian_hadamard_dense_pc,
+        build_monotonic_structured_categorical_cpt_pc,
+    )
+
+    for fold, optimize in itertools.product([False, True], [False, True]):
+        compiler = TorchCompiler(fold=fold, optimize=optimize, semiring="lse-sum")
+        sc, gt, gt_z = build_monotonic_structured_categorical_cpt_pc(return_ground_truth=True)
+        tc = compiler.compile(sc)
+        int_tc = compiler.compile(SF.integrate(sc))
+        worlds = torch.tensor(list(itertools.product([0, 1], repeat=5)))
+        low = plan_from_torch(tc)
+        oc = OracleCircuit(low.plan, dtype=torch.float64)
+        with torch.no_grad():
+            for p, v in zip(oc.leaves, low.leaves):
+                p.copy_(v)
+            y = oc(worlds).reshape(-1)
+            for xs, val in gt["evi"].items():
+                idx = int("".join(map(str, xs)), base=2)
+                assert abs(y[idx].exp().item() - val) < 1e-9
+            assert abs(torch.logsumexp(y, 0).exp().item() - gt_z) < 1e-8
+            lowz = plan_from_torch(int_tc)
+            oz = OracleCircuit(lowz.plan, dtype=torch.float64)
+            for p, v in zip(oz.leaves, lowz.leaves):
+                p.copy_(v)
+            z = oz(externals={k: p() for k, p in lowz.externals.items()})
+            torch.testing.assert_close(z, int_tc(), rtol=1e-10, atol=1e-12)
+            assert abs(z.exp().item() - gt_z) < 1e-8
+
+    compiler = TorchCompiler(fold=True, optimize=True, semiring="lse-sum")
+    sc, gt, gt_z = build_monotonic_bivariate_gaussian_hadamard_dense_pc(return_ground_truth=True)
+    tc = compiler.compile(sc)
+    with torch.enable_grad():
+        _compare(tc, torch.tensor([[0.3, 1.2], [1.0, -2.0]]))
+
+
+def test_integrate_query(reference):
+    from cirkit.backend.torch.queries import IntegrateQuery
+    from cirkit.pipeline import PipelineContext
+    from cirkit_b200.adapter import plan_from_torch
+
+    sc = _image(reference, (1, 4, 4), "quad-graph", "cp", 3)
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    low = plan_from_torch(tc)
+    oc = OracleCircuit(low.plan, dtype=torch.float64)
+    x = torch.randint(0, 256, (7, 16))
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, low.leaves):
+            p.copy_(v)
+        for mask in (torch.rand(7, 16) < 0.5, torch.rand(1, 16) < 0.5,
+                     torch.ones(7, 16, dtype=torch.bool), torch.zeros(7, 16, dtype=torch.bool)):
+            ref = IntegrateQuery(tc)(x, integrate_vars=mask)
+            got = oc(x, integrate_mask=mask)
+            torch.testing.assert_close(got, ref, rtol=1e-10, atol=1e-12)
+        # all variables integrated out of a normalised circuit: log Z = 0
+        got = oc(x, integrate_mask=torch.ones(1, 16, dtype=torch.bool))
+    assert abs(got[0].item()) < 1e-9
