@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: forward + backward log-likelihood of a compiled circuit.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on host cores
+
+A *step* is `ll = circuit(x); (-ll.mean()).backward()` on one batch of synthetic evidence
+(`notebooks/learning-a-circuit.ipynb` loop body without the optimiser).  Workload:
+QuadTree 28x28, Categorical-256 inputs, CP layers, K=64 (BASELINE.json metric), per-GPU batch 2048
+by default.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "samples/sec (fwd+bwd log-lik) QuadTree 28x28 K=64"
+UNIT = "samples/s"
+WORKLOADS = {
+    "qt28_cp_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=64",
+    "qt28_cp_k32": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=32",
+    "qt28_tucker_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, Tucker, K=64",
+}
+
+
+def load_plan(name):
+    from helpers import Golden
+
+    return Golden(name)
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8: "hw_slowdown",
+            0x40: "hw_thermal_slowdown",
+            0x20: "sw_thermal_slowdown",
+            0x4: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's algorithm on the host cores (oracle port: same PyTorch op sequence as
+    cirkit/backend/torch, see oracle/reference_eval.py).  Bounded sample of the same workload."""
+    from oracle import OracleCircuit
+    from cirkit_b200.plan import seeded_leaves
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = load_plan(args.workload)
+    oc = OracleCircuit(g.plan, dtype=torch.float32)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, seeded_leaves(g.plan, 1234)):
+            p.copy_(v)
+    B = args.cpu_batch
+    gen = torch.Generator().manual_seed(0)
+    xs = [torch.randint(0, 256, (B, g.plan.num_variables), generator=gen) for _ in range(2)]
+
+    def step(i):
+        for p in oc.leaves:
+            p.grad = None
+        ll = oc(xs[i % len(xs)])
+        (-ll.mean()).backward()
+        return ll
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "batch": B, "device": "cpu",
+                   "leaves": "seeded N(0,1), seed 1234"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {B} (same circuit, fp32, torch CPU ops)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(g, batch, steps=3, warmup=1):
+    from oracle import OracleCircuit
+    from cirkit_b200.plan import seeded_leaves
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oc = OracleCircuit(g.plan, dtype=torch.float32)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, seeded_leaves(g.plan, 1234)):
+            p.copy_(v)
+    x = torch.randint(0, 256, (batch, g.plan.num_variables), generator=torch.Generator().manual_seed(0))
+    ts = []
+    for i in range(warmup + steps):
+        for p in oc.leaves:
+            p.grad = None
+        t0 = time.perf_counter()
+        ll = oc(x)
+        (-ll.mean()).backward()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return {"value": batch / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"median of {steps} steps of batch {batch} (same circuit, fp32, torch CPU ops, "
+                      f"{cores} threads)"}
+
+
+# ------------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    from cirkit_b200 import B200Circuit
+    from cirkit_b200.runtime import profile_steps
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = load_plan(args.workload)
+    plan = g.plan
+    cc = B200Circuit(plan, seed=1234).to(dev)
+    leaves = list(cc.leaves)
+    B, D = args.batch, plan.num_variables
+    gen = torch.Generator().manual_seed(1000 + rank)
+    n_batches = 4
+    host_x = [torch.randint(0, 256, (B, D), generator=gen, dtype=torch.int64).pin_memory()
+              for _ in range(n_batches)]
+    dev_x = [h.to(dev) for h in host_x]
+    flat_grads = None
+    launches = 0
+
+    def sync_grads():
+        # data-parallel replicas: gradients of the mean log-likelihood are averaged over ranks
+        if world > 1 and not args.no_grad_allreduce:
+            for p in leaves:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+
+    ll_all = torch.empty(world * B, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(x):
+        nonlocal launches
+        for p in leaves:
+            p.grad = None
+        ll = cc(x)
+        n = cc.runtime.last_launches
+        loss = -ll.mean()
+        loss.backward()
+        launches = n + cc.runtime.last_launches
+        if world > 1:
+            # the one collective of the data path: all-gather of the root log-densities
+            dist.all_gather_into_tensor(ll_all, ll.detach().reshape(-1))
+            sync_grads()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(dev_x[i % n_batches])
+    # ---- device-resident inputs: `value`
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dev_x[i % n_batches])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host evidence in, loss out, every step
+    stage = torch.empty((B, D), dtype=torch.int64, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    for i in range(2):
+        stage.copy_(host_x[i % n_batches], non_blocking=True)
+        loss_host.copy_(step(stage).detach(), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        stage.copy_(host_x[i % n_batches], non_blocking=True)
+        loss_host.copy_(step(stage).detach(), non_blocking=True)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(ms2.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0, live, CUDA events around each step's launches)
+    prof = profile_steps(cc.runtime, dev_x[0], leaves, iters=5)
+    peak, peak_src = peaks()
+    best = None
+    for r in prof:
+        for d in ("fwd", "bwd"):
+            t = r.get(f"{d}_ms")
+            if t is None:
+                continue
+            if best is None or t > best[0]:
+                best = (t, r, d)
+    t, r, d = best
+    nbytes = r[f"{d}_bytes"]
+    achieved = nbytes / (t * 1e-3) / 1e9
+    step_ms_sum = sum(q.get("fwd_ms", 0) + q.get("bwd_ms", 0) for q in prof)
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None,
+        "kernel": f"step {r['step']} {r['kind']} {d} (F={r.get('F')})",
+        "kernel_ms": t, "kernel_share_of_step": t / step_ms_sum, "peak_source": peak_src,
+        "algorithmic_bytes": nbytes,
+        "whole_step": {
+            "algorithmic_bytes": plan.algorithmic_bytes(B),
+            "achieved_gbs": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9,
+            "frac": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9 / peak,
+        },
+    }
+    if args.profile_out:
+        with open(args.profile_out, "w") as fh:
+            json.dump(prof, fh, indent=1)
+    base = cpu_baseline(g, args.cpu_batch) if world == 1 and not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
+            "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
+            "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, avg)"),
+            "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
+            "leaves": "seeded N(0,1), seed 1234",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": float(ms2.item()) / args.steps},
+        "gpu_launches": launches * args.steps,
+        "roofline": roofline,
+    }
+    if base is not None:
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qt28_cp_k64", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=2048, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-grad-allreduce", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)  # bounded sample: --cpu-batch samples per step
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

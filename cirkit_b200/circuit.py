@@ -1,0 +1,89 @@
+"""Stand-alone compiled-circuit module backed by the CUDA runtime.
+
+`B200Circuit` mirrors the surface of the reference's `TorchCircuit`
+(cirkit/backend/torch/circuits.py:122-278) for a circuit given as a :class:`CircuitPlan`:
+`cc(x)` with `x: (B, D)` returns `(B, O, K)` log-values (or `(O, K)` when the scope is empty),
+raises `ValueError` when `x` is missing or not 2-D, is differentiable w.r.t. `cc.parameters()`,
+and exposes `scope`, `num_variables`, `layers`, `reset_parameters()`, `state_dict()`.
+When the reference package is installed, `cirkit_b200.accelerate(tc)` is the drop-in route
+instead (it keeps the reference object and its parameters); this class is what runs from a
+stored plan, e.g. on a box without the reference.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor, nn
+
+from .plan import CircuitPlan, StepSpec, init_leaf_
+from .runtime import PlanRuntime
+
+
+@dataclass(frozen=True)
+class LayerInfo:
+    """Read-only view of one folded layer (the attributes `TorchLayer` exposes,
+    cirkit/backend/torch/layers/base.py:13-119)."""
+
+    kind: str
+    num_folds: int
+    arity: int
+    num_input_units: int
+    num_output_units: int
+    config: dict
+
+    @classmethod
+    def from_step(cls, s: StepSpec) -> "LayerInfo":
+        return cls(s.kind, s.num_folds, s.arity, s.num_input_units, s.num_output_units, dict(s.config))
+
+
+class B200Circuit(nn.Module):
+    def __init__(self, plan: CircuitPlan, *, seed: int | None = None):
+        super().__init__()
+        self.plan = plan
+        self.runtime = PlanRuntime(plan)
+        self.leaves = nn.ParameterList(
+            [nn.Parameter(torch.empty(l.shape, dtype=torch.float32), requires_grad=l.requires_grad)
+             for l in plan.leaves]
+        )
+        if seed is not None:
+            from .plan import seeded_leaves
+
+            with torch.no_grad():
+                for p, v in zip(self.leaves, seeded_leaves(plan, seed)):
+                    p.copy_(v)
+        else:
+            self.reset_parameters()
+
+    # -- TorchCircuit surface -------------------------------------------------------------
+    @property
+    def scope(self) -> tuple[int, ...]:
+        return self.plan.scope
+
+    @property
+    def num_variables(self) -> int:
+        return len(self.plan.scope)
+
+    @property
+    def layers(self) -> list[LayerInfo]:
+        return [LayerInfo.from_step(s) for s in self.plan.steps]
+
+    @property
+    def is_folded(self) -> bool:
+        return True
+
+    def reset_parameters(self) -> None:
+        for t, spec in zip(self.leaves, self.plan.leaves):
+            init_leaf_(t.data, spec)
+
+    def forward(self, x: Tensor | None = None) -> Tensor:
+        if self.plan.scope and x is None:
+            raise ValueError(f"Expected some input 'x', as the circuit has scope '{self.plan.scope}'")
+        y = self.runtime.evaluate(x, list(self.leaves))  # (B, O, K)
+        if not self.plan.scope:
+            y = y.squeeze(dim=0)
+        return y
+
+    def integrate_query(self, x: Tensor, mask: Tensor) -> Tensor:
+        return self.runtime.evaluate(x, list(self.leaves), integrate_mask=mask)

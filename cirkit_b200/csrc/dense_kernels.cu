@@ -1,0 +1,597 @@
+// The fused sum-product block:  gather -> (Hadamard | concat) -> max -> exp -> K x K product
+// against the fold's weights -> log -> + max, and its backward.  FP32 SIMT version.
+//
+// Reference path replaced (per folded layer, >= 6 HBM round trips of the (F,B,K) tensor):
+//   circuits.py:42-47 (cat + index gather)  ->  layers/optimized.py:171-178 / inner.py:266-273
+//   ->  semiring.py:382-408 (amax, clamp, sub, exp, einsum "fbi,foi->fbo", log, add).
+// Here a CTA owns one fold and a tile of samples: the fold's (Ko,Kred) weight slice is staged in
+// shared memory once, every warp turns SW samples into exp-shifted rows in shared memory and then
+// runs a register-tiled matrix-vector product against the staged weights, so an activation row
+// is read from HBM once and written once.
+#include "common.cuh"
+
+namespace ckb {
+
+struct DenseArgs {
+  const float* W;          // (F, Ko, Kred)
+  const int64_t* in_rows;  // (F*H) per-sample offsets, or nullptr: rows are x_base + f*B*Ki (H==1)
+  const float* arena;      // base the in_rows offsets refer to (or x_base when in_rows == nullptr)
+  float* y;                // (F, B, Ko) output block (forward: written; backward: read)
+  int64_t B;
+  int H, Ki, Ko, Kred, concat;
+  // backward only
+  GradSrc gs;
+  float* gin;   // (F, gin_h, B, Ki)
+  float* dWp;   // [splits][F][Ko][Kred] or nullptr
+  int64_t chunk;
+};
+
+__device__ __forceinline__ const float* in_row(const DenseArgs& a, int f, int h) {
+  return a.in_rows ? a.arena + a.B * a.in_rows[f * a.H + h] : a.arena + (int64_t)f * a.B * a.Ki;
+}
+
+// Writes u (pre-activation, log space) for one sample into `dst[0..Kred)`, returns the row max.
+__device__ __forceinline__ float load_u(const DenseArgs& a, const float* const* rows, int64_t b,
+                                        int lane, float* dst) {
+  float m = -INFINITY;
+  if (!a.concat) {
+    for (int k = lane; k < a.Kred; k += 32) {
+      float u = 0.f;
+      for (int h = 0; h < a.H; ++h) u += rows[h][b * a.Ki + k];
+      dst[k] = u;
+      m = fmaxf(m, u);
+    }
+  } else {
+    for (int h = 0; h < a.H; ++h)
+      for (int k = lane; k < a.Ki; k += 32) {
+        const float u = rows[h][b * a.Ki + k];
+        dst[h * a.Ki + k] = u;
+        m = fmaxf(m, u);
+      }
+  }
+  return clamp_max(warp_max(m));
+}
+
+constexpr int kMaxH = 64;  // inputs per fold the small kernels keep row pointers for
+
+// ------------------------------------------------------------------------------------------
+// forward, Kred <= 128 and Ko <= 128 ("small" = the whole weight slice fits in shared memory)
+// ------------------------------------------------------------------------------------------
+template <int NO, int SW>
+__global__ void __launch_bounds__(256) dense_fwd_small(DenseArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KoP = 32 * NO + 1;
+  const int KredP = (a.Kred + 3) & ~3;
+  float* Wt = smem;                       // [KredP][KoP]  (transposed: lane o reads Wt[k][o])
+  float* e_all = Wt + KredP * KoP;        // [8][SW][KredP]
+  e_all = (float*)(((uintptr_t)e_all + 15) & ~(uintptr_t)15);
+  __shared__ const float* rows[kMaxH];
+  const int f = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < KredP * KoP; i += 256) Wt[i] = 0.f;
+  if (tid < a.H) rows[tid] = in_row(a, f, tid);
+  __syncthreads();
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  for (int i = tid; i < a.Ko * a.Kred; i += 256) {
+    const int o = i / a.Kred, k = i - o * a.Kred;
+    Wt[k * KoP + o] = Wf[i];
+  }
+  __syncthreads();
+
+  float* e_w = e_all + warp * SW * KredP;
+  for (int64_t b0 = ((int64_t)blockIdx.x * 8 + warp) * SW; b0 < a.B;
+       b0 += (int64_t)gridDim.x * 8 * SW) {
+    float m_reg[SW];
+#pragma unroll
+    for (int s = 0; s < SW; ++s) {
+      const int64_t b = b0 + s;
+      float* es = e_w + s * KredP;
+      float m = 0.f;
+      if (b < a.B) m = load_u(a, rows, b, lane, es);
+      __syncwarp();
+      for (int k = lane; k < KredP; k += 32) es[k] = (b < a.B && k < a.Kred) ? expf(es[k] - m) : 0.f;
+      m_reg[s] = m;
+    }
+    __syncwarp();
+    float acc[SW][NO];
+#pragma unroll
+    for (int s = 0; s < SW; ++s)
+#pragma unroll
+      for (int j = 0; j < NO; ++j) acc[s][j] = 0.f;
+    for (int k = 0; k < KredP; k += 4) {
+      float w[4][NO];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int j = 0; j < NO; ++j) w[kk][j] = Wt[(k + kk) * KoP + lane + 32 * j];
+#pragma unroll
+      for (int s = 0; s < SW; ++s) {
+        const float4 e4 = *reinterpret_cast<const float4*>(e_w + s * KredP + k);
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          acc[s][j] = fmaf(e4.x, w[0][j], acc[s][j]);
+          acc[s][j] = fmaf(e4.y, w[1][j], acc[s][j]);
+          acc[s][j] = fmaf(e4.z, w[2][j], acc[s][j]);
+          acc[s][j] = fmaf(e4.w, w[3][j], acc[s][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < SW; ++s) {
+      const int64_t b = b0 + s;
+      if (b < a.B) {
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          const int o = lane + 32 * j;
+          if (o < a.Ko) a.y[((int64_t)f * a.B + b) * a.Ko + o] = logf(acc[s][j]) + m_reg[s];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int NO, int SW>
+static int launch_dense_fwd_small(const DenseArgs& a, int F, Ctx& c) {
+  const int KredP = (a.Kred + 3) & ~3;
+  const size_t smem = ((size_t)KredP * (32 * NO + 1) + 8 * SW * KredP) * 4 + 16;
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_fwd_small<NO, SW>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid(max(1, ceil_div(a.B, 8 * SW)), F);
+  dense_fwd_small<NO, SW><<<grid, 256, smem, c.stream>>>(a);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward, any shape: one warp per (fold, sample), weights read through L1/L2.
+// ------------------------------------------------------------------------------------------
+__global__ void dense_fwd_generic(DenseArgs a, int e_stride) {
+  extern __shared__ __align__(16) float smem[];
+  const int f = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* e = smem + warp * e_stride;
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < a.B; b += (int64_t)gridDim.x * nwarps) {
+    float m = -INFINITY;
+    for (int h = 0; h < a.H; ++h) {
+      const float* r = in_row(a, f, h) + b * a.Ki;
+      for (int k = lane; k < a.Ki; k += 32) {
+        const int kk = a.concat ? h * a.Ki + k : k;
+        const float u = (a.concat || h == 0) ? r[k] : e[kk] + r[k];
+        e[kk] = u;
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < a.Kred; k += 32) m = fmaxf(m, e[k]);
+    m = clamp_max(warp_max(m));
+    for (int k = lane; k < a.Kred; k += 32) e[k] = expf(e[k] - m);
+    __syncwarp();
+    for (int o = lane; o < a.Ko; o += 32) {
+      const float* wr = Wf + (int64_t)o * a.Kred;
+      float s = 0.f;
+      for (int k = 0; k < a.Kred; ++k) s = fmaf(e[k], wr[k], s);
+      a.y[((int64_t)f * a.B + b) * a.Ko + o] = logf(s) + m;
+    }
+    __syncwarp();
+  }
+}
+
+static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
+  if (a.Kred <= 128 && a.Ko <= 128 && a.H <= kMaxH) {
+    const int kmax = max(a.Ko, 1);
+    if (kmax <= 32) return launch_dense_fwd_small<1, 16>(a, F, c);
+    if (kmax <= 64) return launch_dense_fwd_small<2, 16>(a, F, c);
+    return launch_dense_fwd_small<4, 8>(a, F, c);
+  }
+  const int e_stride = (a.Kred + 3) & ~3;
+  int nwarps = 8;
+  while ((size_t)nwarps * e_stride * 4 > 96 * 1024 && nwarps > 1) nwarps >>= 1;
+  const size_t smem = (size_t)nwarps * e_stride * 4;
+  if (smem > 200 * 1024) {
+    set_error("dense_fwd: reduction length %d too large", a.Kred);
+    return CKB_ERR_UNSUPPORTED;
+  }
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_fwd_generic,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
+  dense_fwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, small shapes.  With r[o] = g[o] / S[o] (S[o] = exp(y[o] - m), so the forward
+// product is not recomputed) and e = exp(u - m):
+//   d/du[i]   = e[i] * sum_o r[o] W[o,i]          (phase B, per warp)
+//   d/dW[o,i] = sum_b r[b,o] e[b,i]               (phase C, per CTA, registers across tiles)
+// ------------------------------------------------------------------------------------------
+template <int NI, int TT, int SW>
+__global__ void __launch_bounds__(256) dense_bwd_small(DenseArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KS = 32 * NI + 1;  // row stride of the staged weights
+  constexpr int AL = TT > 4 ? TT : 4;  // row strides keep float4 / TT-wide reads in bounds
+  const int LR = max(4, (a.Ko + AL - 1) / AL * AL);
+  const int LE = (a.Kred + AL - 1) / AL * AL;
+  float* Wn = smem;                  // [LR][KS]   (natural: lane i reads Wn[o][i])
+  float* r_all = Wn + LR * KS;       // [8*SW][LR]
+  r_all = (float*)(((uintptr_t)r_all + 15) & ~(uintptr_t)15);
+  float* e_all = r_all + 8 * SW * LR;  // [8*SW][LE]
+  __shared__ const float* rows[kMaxH];
+  const int f = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < LR * KS; i += 256) Wn[i] = 0.f;
+  if (tid < a.H) rows[tid] = in_row(a, f, tid);
+  __syncthreads();
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  for (int i = tid; i < a.Ko * a.Kred; i += 256) {
+    const int o = i / a.Kred, k = i - o * a.Kred;
+    Wn[o * KS + k] = Wf[i];
+  }
+  __syncthreads();
+
+  // phase C mapping: thread owns the (TT x TT) block of dW at (o0, i0)
+  const int n_ti = (a.Kred + TT - 1) / TT;
+  const int n_to = (a.Ko + TT - 1) / TT;
+  const int ti = tid % n_ti, to = tid / n_ti;
+  const bool c_active = a.dWp != nullptr && to < n_to;
+  const int o0 = to * TT, i0 = ti * TT;
+  float dw[TT][TT];
+#pragma unroll
+  for (int p = 0; p < TT; ++p)
+#pragma unroll
+    for (int q = 0; q < TT; ++q) dw[p][q] = 0.f;
+
+  float* r_w = r_all + warp * SW * LR;
+  float* e_w = e_all + warp * SW * LE;
+  const int64_t b_begin = (int64_t)blockIdx.x * a.chunk;
+  const int64_t b_end = min(a.B, b_begin + a.chunk);
+  for (int64_t t0 = b_begin; t0 < b_end; t0 += 8 * SW) {
+    const int64_t b0 = t0 + warp * SW;
+    // ---- phase A: e and r of this warp's samples
+#pragma unroll 1
+    for (int s = 0; s < SW; ++s) {
+      const int64_t b = b0 + s;
+      float* es = e_w + s * LE;
+      float* rs = r_w + s * LR;
+      const bool valid = b < b_end;
+      float m = 0.f;
+      if (valid) m = load_u(a, rows, b, lane, es);
+      __syncwarp();
+      for (int k = lane; k < LE; k += 32) es[k] = (valid && k < a.Kred) ? expf(es[k] - m) : 0.f;
+      for (int o = lane; o < LR; o += 32) {
+        float r = 0.f;
+        if (valid && o < a.Ko) {
+          const float g = pull_grad(a.gs, f, b, a.Ko, o);
+          r = (g == 0.f) ? 0.f : g * expf(m - a.y[((int64_t)f * a.B + b) * a.Ko + o]);
+        }
+        rs[o] = r;
+      }
+    }
+    __syncwarp();
+    // ---- phase B: t[i] = sum_o r[o] W[o,i];  du[i] = e[i] t[i]
+    {
+      float acc[SW][NI];
+#pragma unroll
+      for (int s = 0; s < SW; ++s)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[s][j] = 0.f;
+      for (int o = 0; o < LR; o += 4) {
+        float w[4][NI];
+#pragma unroll
+        for (int oo = 0; oo < 4; ++oo)
+#pragma unroll
+          for (int j = 0; j < NI; ++j) w[oo][j] = Wn[(o + oo) * KS + lane + 32 * j];
+#pragma unroll
+        for (int s = 0; s < SW; ++s) {
+          const float4 r4 = *reinterpret_cast<const float4*>(r_w + s * LR + o);
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            acc[s][j] = fmaf(r4.x, w[0][j], acc[s][j]);
+            acc[s][j] = fmaf(r4.y, w[1][j], acc[s][j]);
+            acc[s][j] = fmaf(r4.z, w[2][j], acc[s][j]);
+            acc[s][j] = fmaf(r4.w, w[3][j], acc[s][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SW; ++s) {
+        const int64_t b = b0 + s;
+        if (b < b_end) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            const int i = lane + 32 * j;
+            if (i < a.Kred) {
+              const float du = e_w[s * LE + i] * acc[s][j];
+              if (!a.concat) {
+                a.gin[((int64_t)f * a.B + b) * a.Ki + i] = du;
+              } else {
+                const int h = i / a.Ki;
+                a.gin[(((int64_t)f * a.H + h) * a.B + b) * a.Ki + (i - h * a.Ki)] = du;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase C: dW += r^T e over the 8*SW samples of the tile
+    if (c_active) {
+      const int n_s = (int)min64(8 * SW, b_end - t0);
+      for (int s = 0; s < n_s; ++s) {
+        float rv[TT], ev[TT];
+        const float* rp = r_all + s * LR + o0;
+        const float* ep = e_all + s * LE + i0;
+        if constexpr (TT >= 4) {
+#pragma unroll
+          for (int p = 0; p < TT; p += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rp + p);
+            const float4 e4 = *reinterpret_cast<const float4*>(ep + p);
+            rv[p] = r4.x; rv[p + 1] = r4.y; rv[p + 2] = r4.z; rv[p + 3] = r4.w;
+            ev[p] = e4.x; ev[p + 1] = e4.y; ev[p + 2] = e4.z; ev[p + 3] = e4.w;
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < TT; ++p) { rv[p] = rp[p]; ev[p] = ep[p]; }
+        }
+#pragma unroll
+        for (int p = 0; p < TT; ++p)
+#pragma unroll
+          for (int q = 0; q < TT; ++q) dw[p][q] = fmaf(rv[p], ev[q], dw[p][q]);
+      }
+    }
+    __syncthreads();
+  }
+  if (c_active) {
+    float* out = a.dWp + ((int64_t)blockIdx.x * gridDim.y + f) * a.Ko * a.Kred;
+#pragma unroll
+    for (int p = 0; p < TT; ++p)
+#pragma unroll
+      for (int q = 0; q < TT; ++q)
+        if (o0 + p < a.Ko && i0 + q < a.Kred) out[(int64_t)(o0 + p) * a.Kred + i0 + q] = dw[p][q];
+  }
+}
+
+static void dense_bwd_config(int F, int Ko, int Kred, int64_t B, int& SW, int& splits, int64_t& chunk) {
+  SW = max(Ko, Kred) <= 64 ? 16 : 8;
+  const int tile = 8 * SW;
+  const int64_t want = ceil_div(3 * kNumSMs, F);
+  splits = (int)max64(1, min64(want, ceil_div(B, tile)));
+  chunk = (int64_t)ceil_div(ceil_div(B, splits), tile) * tile;
+  splits = ceil_div(B, chunk);
+}
+
+static bool dense_small_ok(int H, int Ko, int Kred) { return Kred <= 128 && Ko <= 128 && H <= kMaxH; }
+
+template <int NI, int TT, int SW>
+static int launch_dense_bwd_small(const DenseArgs& a, int F, int splits, Ctx& c) {
+  constexpr int KS = 32 * NI + 1;
+  constexpr int AL = TT > 4 ? TT : 4;
+  const int LR = max(4, (a.Ko + AL - 1) / AL * AL);
+  const int LE = (a.Kred + AL - 1) / AL * AL;
+  const size_t smem = ((size_t)LR * KS + 8 * SW * (LR + LE)) * 4 + 16;
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_small<NI, TT, SW>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid(splits, F);
+  dense_bwd_small<NI, TT, SW><<<grid, 256, smem, c.stream>>>(a);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// backward, any shape: one warp per (fold, sample); dW through global atomics (slow path).
+__global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float* dW) {
+  extern __shared__ __align__(16) float smem[];
+  const int f = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* e = smem + warp * (e_stride + r_stride);
+  float* r = e + e_stride;
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < a.B; b += (int64_t)gridDim.x * nwarps) {
+    for (int h = 0; h < a.H; ++h) {
+      const float* xr = in_row(a, f, h) + b * a.Ki;
+      for (int k = lane; k < a.Ki; k += 32) {
+        const int kk = a.concat ? h * a.Ki + k : k;
+        e[kk] = (a.concat || h == 0) ? xr[k] : e[kk] + xr[k];
+      }
+    }
+    __syncwarp();
+    float m = -INFINITY;
+    for (int k = lane; k < a.Kred; k += 32) m = fmaxf(m, e[k]);
+    m = clamp_max(warp_max(m));
+    for (int k = lane; k < a.Kred; k += 32) e[k] = expf(e[k] - m);
+    for (int o = lane; o < a.Ko; o += 32) {
+      const float g = pull_grad(a.gs, f, b, a.Ko, o);
+      r[o] = (g == 0.f) ? 0.f : g * expf(m - a.y[((int64_t)f * a.B + b) * a.Ko + o]);
+    }
+    __syncwarp();
+    for (int i = lane; i < a.Kred; i += 32) {
+      float t = 0.f;
+      for (int o = 0; o < a.Ko; ++o) t = fmaf(r[o], Wf[(int64_t)o * a.Kred + i], t);
+      const float du = e[i] * t;
+      if (!a.concat) {
+        a.gin[((int64_t)f * a.B + b) * a.Ki + i] = du;
+      } else {
+        const int h = i / a.Ki;
+        a.gin[(((int64_t)f * a.H + h) * a.B + b) * a.Ki + (i - h * a.Ki)] = du;
+      }
+      if (dW)
+        for (int o = 0; o < a.Ko; ++o)
+          if (r[o] != 0.f) atomicAdd(&dW[((int64_t)f * a.Ko + o) * a.Kred + i], r[o] * e[i]);
+    }
+    __syncwarp();
+  }
+}
+
+static size_t run_dense_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
+  if (!dense_small_ok(H, Ko, Kred)) return 0;
+  int SW, splits;
+  int64_t chunk;
+  dense_bwd_config(F, Ko, Kred, B, SW, splits, chunk);
+  return splits > 1 ? (size_t)splits * F * Ko * Kred * 4 : 0;
+}
+
+static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
+  const size_t n = (size_t)F * a.Ko * a.Kred;
+  if (dense_small_ok(a.H, a.Ko, a.Kred)) {
+    int SW, splits;
+    int64_t chunk;
+    dense_bwd_config(F, a.Ko, a.Kred, a.B, SW, splits, chunk);
+    a.chunk = chunk;
+    a.dWp = dW;
+    if (dW && splits > 1) {
+      if (ws_bytes < splits * n * 4) {
+        set_error("dense_bwd: workspace too small (%zu < %zu)", ws_bytes, splits * n * 4);
+        return CKB_ERR_WORKSPACE;
+      }
+      a.dWp = (float*)ws;
+    }
+    const int kmax = max(a.Ko, a.Kred);
+    int rc;
+    if (kmax <= 32) rc = launch_dense_bwd_small<1, 2, 16>(a, F, splits, c);
+    else if (kmax <= 64) rc = launch_dense_bwd_small<2, 4, 16>(a, F, splits, c);
+    else rc = launch_dense_bwd_small<4, 8, 8>(a, F, splits, c);
+    if (rc != CKB_OK) return rc;
+    if (dW && splits > 1) return reduce_partials(a.dWp, dW, (int64_t)n, splits, c);
+    return CKB_OK;
+  }
+  const int e_stride = (a.Kred + 3) & ~3, r_stride = (a.Ko + 3) & ~3;
+  int nwarps = 8;
+  while ((size_t)nwarps * (e_stride + r_stride) * 4 > 96 * 1024 && nwarps > 1) nwarps >>= 1;
+  const size_t smem = (size_t)nwarps * (e_stride + r_stride) * 4;
+  if (smem > 200 * 1024) {
+    set_error("dense_bwd: reduction length %d too large", a.Kred);
+    return CKB_ERR_UNSUPPORTED;
+  }
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_generic,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  if (dW) CKB_CUDA_CHECK(cudaMemsetAsync(dW, 0, n * 4, c.stream));
+  dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
+  dense_bwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride, r_stride, dW);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// step entry points
+// ------------------------------------------------------------------------------------------
+static DenseArgs make_args(const ckb_step_desc_t& d, Ctx& c) {
+  DenseArgs a{};
+  a.W = c.tensors[d.slot[0]];
+  a.in_rows = d.in_rows;
+  a.arena = c.arena;
+  a.y = c.arena + c.B * d.out_off;
+  a.B = c.B;
+  a.H = d.arity;
+  a.Ki = d.k_in;
+  a.Ko = d.k_out;
+  a.concat = (d.flags & CKB_DENSE_CONCAT) ? 1 : 0;
+  a.Kred = a.concat ? d.arity * d.k_in : d.k_in;
+  return a;
+}
+
+int dense_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  return run_dense_fwd(make_args(d, c), d.num_folds, c);
+}
+
+size_t dense_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
+  const int concat = (d.flags & CKB_DENSE_CONCAT) ? 1 : 0;
+  return run_dense_bwd_ws(d.num_folds, d.arity, d.k_out, concat ? d.arity * d.k_in : d.k_in, B);
+}
+
+int dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  DenseArgs a = make_args(d, c);
+  a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  a.gin = c.garena + c.B * d.gin_off;
+  return run_dense_bwd(a, d.num_folds, c.grads[d.slot[0]], c, c.ws, c.ws_bytes);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tucker (layers/optimized.py:89-103), FP32 SIMT route for small K: the Kronecker product of the
+// two shifted inputs is formed in scratch and fed to the dense block with Kred = Ki^2 (per-input
+// shifts m1, m2 and a single shift over the K^2 sums agree: max_ij (x1_i + x2_j) = m1 + m2).
+// ------------------------------------------------------------------------------------------
+int kronecker_into(const ckb_step_desc_t& d, Ctx& c, float* dst);
+int kronecker_bwd_from(const ckb_step_desc_t& d, Ctx& c, const float* gsrc);
+
+size_t tucker_ws(const ckb_step_desc_t& d, int64_t B) {
+  const size_t kron = (size_t)d.num_folds * B * d.k_in * d.k_in * 4;
+  return 2 * kron + run_dense_bwd_ws(d.num_folds, 1, d.k_out, d.k_in * d.k_in, B) + 256;
+}
+
+static int tucker_check(const ckb_step_desc_t& d) {
+  if (d.arity != 2) {
+    set_error("tucker: arity %d has no kernel (2 only)", d.arity);
+    return CKB_ERR_UNSUPPORTED;
+  }
+  return CKB_OK;
+}
+
+static DenseArgs tucker_args(const ckb_step_desc_t& d, Ctx& c, float* kron) {
+  DenseArgs a{};
+  a.W = c.tensors[d.slot[0]];
+  a.in_rows = nullptr;
+  a.arena = kron;
+  a.y = c.arena + c.B * d.out_off;
+  a.B = c.B;
+  a.H = 1;
+  a.Ki = d.k_in * d.k_in;
+  a.Ko = d.k_out;
+  a.concat = 0;
+  a.Kred = a.Ki;
+  return a;
+}
+
+int tucker_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  if (int rc = tucker_check(d)) return rc;
+  const size_t kron_bytes = (size_t)d.num_folds * c.B * d.k_in * d.k_in * 4;
+  if (c.ws_bytes < kron_bytes) {
+    set_error("tucker_fwd: workspace too small");
+    return CKB_ERR_WORKSPACE;
+  }
+  float* kron = (float*)c.ws;
+  if (int rc = kronecker_into(d, c, kron)) return rc;
+  return run_dense_fwd(tucker_args(d, c, kron), d.num_folds, c);
+}
+
+int tucker_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  if (int rc = tucker_check(d)) return rc;
+  const size_t kron_bytes = ((size_t)d.num_folds * c.B * d.k_in * d.k_in * 4 + 255) & ~(size_t)255;
+  if (c.ws_bytes < 2 * kron_bytes) {
+    set_error("tucker_bwd: workspace too small");
+    return CKB_ERR_WORKSPACE;
+  }
+  float* kron = (float*)c.ws;
+  float* gkron = (float*)(c.ws + kron_bytes);
+  if (int rc = kronecker_into(d, c, kron)) return rc;
+  DenseArgs a = tucker_args(d, c, kron);
+  a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  a.gin = gkron;
+  if (int rc = run_dense_bwd(a, d.num_folds, c.grads[d.slot[0]], c, c.ws + 2 * kron_bytes,
+                             c.ws_bytes - 2 * kron_bytes))
+    return rc;
+  return kronecker_bwd_from(d, c, gkron);
+}
+
+}  // namespace ckb

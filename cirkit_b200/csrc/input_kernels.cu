@@ -1,0 +1,387 @@
+// Input-layer kernels: evidence transpose, table (Categorical / Embedding), Gaussian, constant.
+#include "common.cuh"
+
+namespace ckb {
+
+// ------------------------------------------------------------------------------------------
+// x (B, D) -> xT (D, B).  The reference re-gathers x for every input layer
+// (`x[..., scope_idx].permute(1, 0, 2)`, circuits.py:66); here it is transposed and narrowed
+// once so that every later read of "variable v of samples b..b+31" is one coalesced line.
+// ------------------------------------------------------------------------------------------
+template <typename T, typename O>
+__global__ void transpose_kernel(const T* __restrict__ x, int64_t B, int D, int64_t ld,
+                                 O* __restrict__ xT) {
+  __shared__ O tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int d0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int64_t b = b0 + j;
+    const int d = d0 + threadIdx.x;
+    if (b < B && d < D) tile[j][threadIdx.x] = (O)x[b * ld + d];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int d = d0 + j;
+    const int64_t b = b0 + threadIdx.x;
+    if (b < B && d < D) xT[(int64_t)d * B + b] = tile[threadIdx.x][j];
+  }
+}
+
+template <typename T, typename O>
+static int launch_transpose(const void* x, int64_t B, int D, int64_t ld, void* xT, cudaStream_t s) {
+  if (B == 0 || D == 0) return CKB_OK;
+  dim3 grid(ceil_div(B, 32), ceil_div(D, 32)), block(32, 8);
+  transpose_kernel<T, O><<<grid, block, 0, s>>>((const T*)x, B, D, ld, (O*)xT);
+  CKB_LAUNCH_CHECK();
+  return CKB_OK;
+}
+
+int transpose_input(const void* x, int dtype, int64_t B, int D, int64_t ld, void* xT, cudaStream_t s) {
+  switch (dtype) {
+    case CKB_U8: return launch_transpose<uint8_t, int32_t>(x, B, D, ld, xT, s);
+    case CKB_I16: return launch_transpose<int16_t, int32_t>(x, B, D, ld, xT, s);
+    case CKB_I32: return launch_transpose<int32_t, int32_t>(x, B, D, ld, xT, s);
+    case CKB_I64: return launch_transpose<int64_t, int32_t>(x, B, D, ld, xT, s);
+    case CKB_F32: return launch_transpose<float, float>(x, B, D, ld, xT, s);
+    case CKB_F64: return launch_transpose<double, float>(x, B, D, ld, xT, s);
+  }
+  set_error("ckb_transpose_input: unknown dtype %d", dtype);
+  return CKB_ERR_INVALID;
+}
+
+int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStream_t s) {
+  return launch_transpose<uint8_t, uint8_t>(m, rows, D, D, mT, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Table lookup: y[f,b,:] = T[f, x[b,var_f], :]  (T is the (F,V,K) log-table a parameter op
+// produced).  Pure gather: one sample reads K contiguous floats.
+// ------------------------------------------------------------------------------------------
+__global__ void table_fwd_kernel(const float* __restrict__ T, const int32_t* __restrict__ scope_var,
+                                 const void* __restrict__ xT, int x_is_float,
+                                 const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                                 const float* __restrict__ integ, float* __restrict__ y, int64_t B,
+                                 int K, int V) {
+  const int f = blockIdx.y;
+  const int var = scope_var[f];
+  const float* Tf = T + (int64_t)f * V * K;
+  float* yf = y + (int64_t)f * B * K;
+  const float* integ_f = integ ? integ + (int64_t)f * K : nullptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if ((K & 3) == 0) {
+    const int K4 = K >> 2;
+    const int64_t total = B * K4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+      const int64_t b = idx / K4;
+      const int k4 = (int)(idx - b * K4);
+      float4 val;
+      if (read_mask(maskT, mask_ld, var, b)) {
+        val = integ_f ? ((const float4*)integ_f)[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        int v = read_state(xT, x_is_float, (int64_t)var * B + b);
+        v = min(max(v, 0), V - 1);
+        val = ((const float4*)(Tf + (int64_t)v * K))[k4];
+      }
+      ((float4*)yf)[idx] = val;
+    }
+  } else {
+    const int64_t total = B * K;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+      const int64_t b = idx / K;
+      const int k = (int)(idx - b * K);
+      float val;
+      if (read_mask(maskT, mask_ld, var, b)) {
+        val = integ_f ? integ_f[k] : 0.f;
+      } else {
+        int v = read_state(xT, x_is_float, (int64_t)var * B + b);
+        v = min(max(v, 0), V - 1);
+        val = Tf[(int64_t)v * K + k];
+      }
+      yf[idx] = val;
+    }
+  }
+}
+
+int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  const int K = d.k_out;
+  const int64_t per_fold = (K % 4 == 0) ? c.B * (K / 4) : c.B * K;
+  const int bx = (int)min64(ceil_div(per_fold, 256), 4 * kNumSMs);
+  dim3 grid(max(bx, 1), d.num_folds);
+  table_fwd_kernel<<<grid, 256, 0, c.stream>>>(
+      c.tensors[d.slot[0]], d.scope_var, c.xT, c.x_is_float, c.maskT, c.mask_ld,
+      d.int_slot >= 0 ? c.tensors[d.int_slot] : nullptr, c.arena + c.B * d.out_off, c.B, K,
+      d.num_states);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// Backward of the lookup: dT[f,v,:] = sum over samples with x=v of g[f,b,:]  (the reference gets
+// this from autograd as an `index_put_`, 26 % of its CPU step -- SURVEY §3(b)).  One CTA owns a
+// (fold, unit tile, batch split) and accumulates into a shared-memory histogram.
+__global__ void table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var,
+                                 const void* __restrict__ xT, int x_is_float,
+                                 const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                                 float* __restrict__ out, int64_t B, int K, int V, int KT,
+                                 int64_t chunk) {
+  extern __shared__ float hist[];  // [V][KT]
+  const int f = blockIdx.y;
+  const int k0 = blockIdx.z * KT;
+  const int kt = min(KT, K - k0);
+  const int var = scope_var[f];
+  for (int i = threadIdx.x; i < V * KT; i += blockDim.x) hist[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t b_begin = (int64_t)blockIdx.x * chunk;
+  const int64_t b_end = min(B, b_begin + chunk);
+  for (int64_t b = b_begin + warp; b < b_end; b += nwarps) {
+    if (read_mask(maskT, mask_ld, var, b)) continue;
+    int v = read_state(xT, x_is_float, (int64_t)var * B + b);
+    v = min(max(v, 0), V - 1);
+    for (int kk = lane; kk < kt; kk += 32) {
+      const float g = pull_grad(gs, f, b, K, k0 + kk);
+      atomicAdd(&hist[v * KT + kk], g);
+    }
+  }
+  __syncthreads();
+  // out: [split][F][V][K]
+  float* o = out + ((int64_t)blockIdx.x * gridDim.y + f) * V * K;
+  for (int i = threadIdx.x; i < V * kt; i += blockDim.x) {
+    const int v = i / kt, kk = i - v * kt;
+    o[(int64_t)v * K + k0 + kk] = hist[v * KT + kk];
+  }
+}
+
+static void table_bwd_config(const ckb_step_desc_t& d, int64_t B, int& KT, int& splits, int64_t& chunk) {
+  KT = min(d.k_out, 64);
+  while ((size_t)d.num_states * KT * 4 > 96 * 1024 && KT > 1) KT = (KT + 1) / 2;
+  const int ktiles = ceil_div(d.k_out, KT);
+  const int64_t want = ceil_div(3 * kNumSMs, (int64_t)d.num_folds * ktiles);
+  splits = (int)max64(1, min64(want, ceil_div(B, 256)));
+  chunk = ceil_div(B, splits);
+  splits = ceil_div(B, chunk);
+}
+
+size_t table_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
+  int KT, splits;
+  int64_t chunk;
+  table_bwd_config(d, B, KT, splits, chunk);
+  return splits > 1 ? (size_t)splits * d.num_folds * d.num_states * d.k_out * 4 : 0;
+}
+
+int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  float* dT = c.grads[d.slot[0]];
+  if (dT == nullptr) return CKB_OK;
+  int KT, splits;
+  int64_t chunk;
+  table_bwd_config(d, c.B, KT, splits, chunk);
+  const size_t smem = (size_t)d.num_states * KT * 4;
+  if (smem > 200 * 1024) {
+    set_error("table_bwd: %d states do not fit the shared-memory histogram", d.num_states);
+    return CKB_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    attr_set = true;
+  }
+  const size_t n = (size_t)d.num_folds * d.num_states * d.k_out;
+  float* out = dT;
+  if (splits > 1) {
+    if (c.ws_bytes < (size_t)splits * n * 4) {
+      set_error("table_bwd: workspace too small");
+      return CKB_ERR_WORKSPACE;
+    }
+    out = (float*)c.ws;
+  }
+  GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  dim3 grid(splits, d.num_folds, ceil_div(d.k_out, KT));
+  table_bwd_kernel<<<grid, 256, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
+                                                  c.mask_ld, out, c.B, d.k_out, d.num_states, KT,
+                                                  chunk);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  if (splits > 1) return reduce_partials(out, dT, (int64_t)n, splits, c);
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gaussian log-density, layers/input.py:661-670 (torch.distributions.Normal.log_prob):
+//   y = -(x-mu)^2 / (2 sigma^2) - log(sigma) - log(sqrt(2 pi)) (+ log_partition)
+// ------------------------------------------------------------------------------------------
+__global__ void gaussian_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ stddev,
+                                    const float* __restrict__ logp, const int32_t* __restrict__ scope_var,
+                                    const void* __restrict__ xT, int x_is_float,
+                                    const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                                    float* __restrict__ y, int64_t B, int K) {
+  const int f = blockIdx.y;
+  const int var = scope_var[f];
+  float* yf = y + (int64_t)f * B * K;
+  const int64_t total = B * K;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / K;
+    const int k = (int)(idx - b * K);
+    const float lp = logp ? logp[(int64_t)f * K + k] : 0.f;
+    float val;
+    if (read_mask(maskT, mask_ld, var, b)) {
+      val = lp;  // integrate(): log-partition (0 when normalised), layers/input.py:672-678
+    } else {
+      const float x = read_value(xT, x_is_float, (int64_t)var * B + b);
+      const float mu = mean[(int64_t)f * K + k], sd = stddev[(int64_t)f * K + k];
+      const float dlt = x - mu;
+      val = -(dlt * dlt) / (2.f * sd * sd) - logf(sd) - 0.91893853320467274178f + lp;
+    }
+    yf[idx] = val;
+  }
+}
+
+int gaussian_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  const int K = d.k_out;
+  const int bx = (int)min64(ceil_div(c.B * K, 256), 4 * kNumSMs);
+  dim3 grid(max(bx, 1), d.num_folds);
+  gaussian_fwd_kernel<<<grid, 256, 0, c.stream>>>(
+      c.tensors[d.slot[0]], c.tensors[d.slot[1]], d.slot[2] >= 0 ? c.tensors[d.slot[2]] : nullptr,
+      d.scope_var, c.xT, c.x_is_float, c.maskT, c.mask_ld, c.arena + c.B * d.out_off, c.B, K);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// d/dmu = (x-mu)/sigma^2, d/dsigma = ((x-mu)^2 - sigma^2)/sigma^3, d/dlogp = 1; reduced over
+// the batch by one CTA per fold (threads: 32 units x 8 batch slices).
+__global__ void gaussian_bwd_kernel(GradSrc gs, const float* __restrict__ mean,
+                                    const float* __restrict__ stddev,
+                                    const int32_t* __restrict__ scope_var, const void* __restrict__ xT,
+                                    int x_is_float, const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                                    float* __restrict__ dmean, float* __restrict__ dstd,
+                                    float* __restrict__ dlogp, int64_t B, int K) {
+  __shared__ float red[3][8][33];
+  const int f = blockIdx.x;
+  const int var = scope_var[f];
+  const int lane = threadIdx.x, slice = threadIdx.y;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    float a_mu = 0.f, a_sd = 0.f, a_lp = 0.f;
+    if (k < K) {
+      const float mu = mean[(int64_t)f * K + k], sd = stddev[(int64_t)f * K + k];
+      const float inv_var = 1.f / (sd * sd);
+      for (int64_t b = slice; b < B; b += 8) {
+        const float g = pull_grad(gs, f, b, K, k);
+        a_lp += g;
+        if (!read_mask(maskT, mask_ld, var, b)) {
+          const float dlt = read_value(xT, x_is_float, (int64_t)var * B + b) - mu;
+          a_mu += g * dlt * inv_var;
+          a_sd += g * (dlt * dlt * inv_var - 1.f) / sd;
+        }
+      }
+    }
+    red[0][slice][lane] = a_mu;
+    red[1][slice][lane] = a_sd;
+    red[2][slice][lane] = a_lp;
+    __syncthreads();
+    if (slice == 0 && k < K) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0 += red[0][j][lane];
+        s1 += red[1][j][lane];
+        s2 += red[2][j][lane];
+      }
+      if (dmean) dmean[(int64_t)f * K + k] = s0;
+      if (dstd) dstd[(int64_t)f * K + k] = s1;
+      if (dlogp) dlogp[(int64_t)f * K + k] = s2;
+    }
+    __syncthreads();
+  }
+}
+
+int gaussian_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  float* dmean = c.grads[d.slot[0]];
+  float* dstd = c.grads[d.slot[1]];
+  float* dlogp = d.slot[2] >= 0 ? c.grads[d.slot[2]] : nullptr;
+  if (!dmean && !dstd && !dlogp) return CKB_OK;
+  GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  gaussian_bwd_kernel<<<d.num_folds, dim3(32, 8), 0, c.stream>>>(
+      gs, c.tensors[d.slot[0]], c.tensors[d.slot[1]], d.scope_var, c.xT, c.x_is_float, c.maskT,
+      c.mask_ld, dmean, dstd, dlogp, c.B, d.k_out);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Constant layer, layers/input.py:739-743: broadcast a (F,K) log-space value over the batch.
+// ------------------------------------------------------------------------------------------
+__global__ void constant_fwd_kernel(const float* __restrict__ value, float* __restrict__ y,
+                                    int64_t B, int K) {
+  const int f = blockIdx.y;
+  float* yf = y + (int64_t)f * B * K;
+  const int64_t total = B * K;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    yf[idx] = value[(int64_t)f * K + (int)(idx % K)];
+}
+
+int constant_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  const int bx = (int)min64(ceil_div(c.B * d.k_out, 256), 4 * kNumSMs);
+  dim3 grid(max(bx, 1), d.num_folds);
+  constant_fwd_kernel<<<grid, 256, 0, c.stream>>>(c.tensors[d.slot[0]], c.arena + c.B * d.out_off,
+                                                  c.B, d.k_out);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+__global__ void constant_bwd_kernel(GradSrc gs, float* __restrict__ dvalue, int64_t B, int K) {
+  __shared__ float red[8][33];
+  const int f = blockIdx.x;
+  const int lane = threadIdx.x, slice = threadIdx.y;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    float a = 0.f;
+    if (k < K)
+      for (int64_t b = slice; b < B; b += 8) a += pull_grad(gs, f, b, K, k);
+    red[slice][lane] = a;
+    __syncthreads();
+    if (slice == 0 && k < K) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += red[j][lane];
+      dvalue[(int64_t)f * K + k] = s;
+    }
+    __syncthreads();
+  }
+}
+
+int constant_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  float* dv = c.grads[d.slot[0]];
+  if (!dv) return CKB_OK;
+  GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  constant_bwd_kernel<<<d.num_folds, dim3(32, 8), 0, c.stream>>>(gs, dv, c.B, d.k_out);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                       int64_t n, int splits) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < splits; ++j) s += partial[(int64_t)j * n + i];
+    out[i] = s;
+  }
+}
+
+int reduce_partials(const float* partial, float* out, int64_t n, int splits, Ctx& c) {
+  const int bx = (int)min64(ceil_div(n, 256), 8 * kNumSMs);
+  reduce_partials_kernel<<<max(bx, 1), 256, 0, c.stream>>>(partial, out, n, splits);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+}  // namespace ckb

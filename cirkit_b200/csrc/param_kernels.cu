@@ -1,0 +1,267 @@
+// Parameter re-parameterisation ops (cirkit/backend/torch/parameters/nodes.py) and their backward.
+// The reference re-evaluates every layer's parameter graph on each forward
+// (parameters/parameter.py:180-188): softmax over all sum weights, softmax + log over all
+// Categorical tables.  These kernels do the same work in one pass per tensor and emit the layout
+// the layer kernels read ((F,V,K) log-tables).
+#include "common.cuh"
+
+namespace ckb {
+
+// ---- softmax over the last axis, one warp per row ------------------------------------------
+__global__ void softmax_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                   int64_t rows, int cols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+    const float* s = src + r * cols;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, s[c]);
+    m = warp_max(m);
+    float z = 0.f;
+    for (int c = lane; c < cols; c += 32) z += expf(s[c] - m);
+    z = warp_sum(z);
+    const float inv = 1.f / z;
+    for (int c = lane; c < cols; c += 32) dst[r * cols + c] = expf(s[c] - m) * inv;
+  }
+}
+
+// d theta = W * (dW - sum_j W_j dW_j)
+__global__ void softmax_bwd_kernel(const float* __restrict__ W, const float* __restrict__ dW,
+                                   float* __restrict__ dsrc, int64_t rows, int cols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+    const float* w = W + r * cols;
+    const float* g = dW + r * cols;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) dot = fmaf(w[c], g[c], dot);
+    dot = warp_sum(dot);
+    for (int c = lane; c < cols; c += 32) dsrc[r * cols + c] = w[c] * (g[c] - dot);
+  }
+}
+
+// ---- (F,K,V) -> (F,V,K) table builders; one CTA per (fold, unit tile of 32) -----------------
+// MODE 0: log_softmax over V, MODE 1: log, MODE 2: copy
+template <int MODE>
+__global__ void table_fwd_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int V) {
+  __shared__ float tile[32][33];
+  __shared__ float lse[32];
+  const int f = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const float* s = src + (int64_t)f * K * V;
+  float* d = dst + (int64_t)f * V * K;
+  if (MODE == 0) {
+    // warp ty handles rows k0 + ty, +8, ...: logsumexp over V
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk;
+      float m = -INFINITY, z = 0.f;
+      if (k < K) {
+        for (int v = tx; v < V; v += 32) m = fmaxf(m, s[(int64_t)k * V + v]);
+        m = warp_max(m);
+        for (int v = tx; v < V; v += 32) z += expf(s[(int64_t)k * V + v] - m);
+        z = warp_sum(z);
+      }
+      if (tx == 0) lse[kk] = (k < K) ? m + logf(z) : 0.f;
+    }
+    __syncthreads();
+  }
+  for (int v0 = 0; v0 < V; v0 += 32) {
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk, v = v0 + tx;
+      float val = 0.f;
+      if (k < K && v < V) {
+        val = s[(int64_t)k * V + v];
+        if (MODE == 0) val -= lse[kk];
+        if (MODE == 1) val = logf(val);
+      }
+      tile[kk][tx] = val;
+    }
+    __syncthreads();
+    for (int vv = ty; vv < 32; vv += 8) {
+      const int v = v0 + vv, k = k0 + tx;
+      if (v < V && k < K) d[(int64_t)v * K + k] = tile[tx][vv];
+    }
+    __syncthreads();
+  }
+}
+
+// backward: dsrc[f,k,v] from dT[f,v,k]
+//  MODE 0: dT[v,k] - exp(T[v,k]) * sum_v dT[v,k]     (T = log softmax)
+//  MODE 1: dT[v,k] / src[k,v]
+//  MODE 2: dT[v,k]
+template <int MODE>
+__global__ void table_bwd_t_kernel(const float* __restrict__ src, const float* __restrict__ T,
+                                   const float* __restrict__ dT, float* __restrict__ dsrc, int K, int V) {
+  __shared__ float tile[32][33];
+  __shared__ float tile2[32][33];
+  __shared__ float colsum[32];
+  const int f = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const float* t = T + (int64_t)f * V * K;
+  const float* g = dT + (int64_t)f * V * K;
+  float* d = dsrc + (int64_t)f * K * V;
+  if (MODE == 0) {
+    // sum over v of dT[v, k0+tx]; slices over ty
+    float a = 0.f;
+    const int k = k0 + tx;
+    if (k < K)
+      for (int v = ty; v < V; v += 8) a += g[(int64_t)v * K + k];
+    tile[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += tile[j][tx];
+      colsum[tx] = s;
+    }
+    __syncthreads();
+  }
+  for (int v0 = 0; v0 < V; v0 += 32) {
+    for (int vv = ty; vv < 32; vv += 8) {
+      const int v = v0 + vv, k = k0 + tx;
+      float gv = 0.f, tv = 0.f;
+      if (v < V && k < K) {
+        gv = g[(int64_t)v * K + k];
+        if (MODE == 0) tv = t[(int64_t)v * K + k];
+      }
+      tile[vv][tx] = gv;
+      if (MODE == 0) tile2[vv][tx] = tv;
+    }
+    __syncthreads();
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk, v = v0 + tx;
+      if (k < K && v < V) {
+        float val = tile[tx][kk];
+        if (MODE == 0) val -= expf(tile2[tx][kk]) * colsum[kk];
+        if (MODE == 1) val /= src[(int64_t)f * K * V + (int64_t)k * V + v];
+        d[(int64_t)k * V + v] = val;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- elementwise ------------------------------------------------------------------------------
+__global__ void scaled_sigmoid_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                          int64_t n, float a, float b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (1.f / (1.f + expf(-src[i]))) * (b - a) + a;
+}
+__global__ void scaled_sigmoid_bwd_kernel(const float* __restrict__ src, const float* __restrict__ g,
+                                          float* __restrict__ dsrc, int64_t n, float a, float b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = 1.f / (1.f + expf(-src[i]));
+    dsrc[i] = g[i] * (b - a) * s * (1.f - s);
+  }
+}
+__global__ void log_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = logf(src[i]);
+}
+__global__ void log_bwd_kernel(const float* __restrict__ src, const float* __restrict__ g,
+                               float* __restrict__ dsrc, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dsrc[i] = g[i] / src[i];
+}
+__global__ void lse_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows,
+                                int cols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < rows; r += (int64_t)gridDim.x * nwarps) {
+    const float* s = src + r * cols;
+    float m = -INFINITY, z = 0.f;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, s[c]);
+    m = warp_max(m);
+    for (int c = lane; c < cols; c += 32) z += expf(s[c] - m);
+    z = warp_sum(z);
+    if (lane == 0) dst[r] = m + logf(z);
+  }
+}
+
+static int grid1d(int64_t n, int per_block) {
+  return (int)max64(1, min64(ceil_div(n, per_block), 8 * kNumSMs));
+}
+
+int param_op_fwd(const ckb_param_op_t& op, Ctx& c) {
+  const float* src = c.tensors[op.src];
+  float* dst = c.tensors[op.dst];
+  const int64_t n = op.rows * op.cols * (op.aux > 0 ? op.aux : 1);
+  switch (op.kind) {
+    case CKB_POP_SOFTMAX:
+      softmax_fwd_kernel<<<grid1d(op.rows, 8), 256, 0, c.stream>>>(src, dst, op.rows, op.cols);
+      break;
+    case CKB_POP_LOG_SOFTMAX_T:
+      table_fwd_t_kernel<0><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, op.aux, op.cols);
+      break;
+    case CKB_POP_LOG_T:
+      table_fwd_t_kernel<1><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, op.aux, op.cols);
+      break;
+    case CKB_POP_COPY_T:
+      table_fwd_t_kernel<2><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, op.aux, op.cols);
+      break;
+    case CKB_POP_SCALED_SIGMOID:
+      scaled_sigmoid_fwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, dst, n, op.a, op.b);
+      break;
+    case CKB_POP_LOG:
+      log_fwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, dst, n);
+      break;
+    case CKB_POP_LSE_ROWS:
+      lse_rows_kernel<<<grid1d(op.rows, 8), 256, 0, c.stream>>>(src, dst, op.rows, op.cols);
+      break;
+    default:
+      set_error("unknown parameter op %d", op.kind);
+      return CKB_ERR_INVALID;
+  }
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+int param_op_bwd(const ckb_param_op_t& op, Ctx& c) {
+  float* dsrc = c.grads[op.src];
+  const float* g = c.grads[op.dst];
+  if (dsrc == nullptr || op.kind == CKB_POP_LSE_ROWS) return CKB_OK;
+  if (g == nullptr) {
+    set_error("parameter op %d: gradient of slot %d requested but slot %d has none", op.kind,
+              op.src, op.dst);
+    return CKB_ERR_INVALID;
+  }
+  const float* src = c.tensors[op.src];
+  const float* dst = c.tensors[op.dst];
+  const int64_t n = op.rows * op.cols * (op.aux > 0 ? op.aux : 1);
+  switch (op.kind) {
+    case CKB_POP_SOFTMAX:
+      softmax_bwd_kernel<<<grid1d(op.rows, 8), 256, 0, c.stream>>>(dst, g, dsrc, op.rows, op.cols);
+      break;
+    case CKB_POP_LOG_SOFTMAX_T:
+      table_bwd_t_kernel<0><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, g, dsrc, op.aux, op.cols);
+      break;
+    case CKB_POP_LOG_T:
+      table_bwd_t_kernel<1><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, g, dsrc, op.aux, op.cols);
+      break;
+    case CKB_POP_COPY_T:
+      table_bwd_t_kernel<2><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
+          src, dst, g, dsrc, op.aux, op.cols);
+      break;
+    case CKB_POP_SCALED_SIGMOID:
+      scaled_sigmoid_bwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, g, dsrc, n, op.a, op.b);
+      break;
+    case CKB_POP_LOG:
+      log_bwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, g, dsrc, n);
+      break;
+    default:
+      set_error("unknown parameter op %d", op.kind);
+      return CKB_ERR_INVALID;
+  }
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+}  // namespace ckb

@@ -1,0 +1,273 @@
+// Plan object and the C ABI (include/cirkit_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ckb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int transpose_input(const void* x, int dtype, int64_t B, int D, int64_t ld, void* xT, cudaStream_t s);
+int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStream_t s);
+
+}  // namespace ckb
+
+struct ckb_plan {
+  std::vector<ckb_step_desc_t> steps;
+  std::vector<ckb_param_op_t> ops;
+  int32_t n_slots = 0;
+  int64_t last_launches = 0;
+};
+
+using namespace ckb;
+
+static int check_step(const ckb_step_desc_t& d, int idx, int n_slots) {
+  auto slot_ok = [&](int s) { return s >= -1 && s < n_slots; };
+  if (d.num_folds <= 0 || d.k_out <= 0) {
+    set_error("step %d: non-positive folds/units", idx);
+    return CKB_ERR_INVALID;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (!slot_ok(d.slot[i])) {
+      set_error("step %d: parameter slot %d out of range", idx, d.slot[i]);
+      return CKB_ERR_INVALID;
+    }
+  if (!slot_ok(d.int_slot)) {
+    set_error("step %d: integrate slot out of range", idx);
+    return CKB_ERR_INVALID;
+  }
+  if (d.cons_ptr == nullptr || (d.cons_rows == nullptr && false)) {
+    set_error("step %d: missing consumer list", idx);
+    return CKB_ERR_INVALID;
+  }
+  switch (d.kind) {
+    case CKB_STEP_TABLE:
+      if (d.slot[0] < 0 || d.scope_var == nullptr || d.num_states <= 0) {
+        set_error("step %d: table layer needs a table, a scope and num_states", idx);
+        return CKB_ERR_INVALID;
+      }
+      break;
+    case CKB_STEP_GAUSSIAN:
+      if (d.slot[0] < 0 || d.slot[1] < 0 || d.scope_var == nullptr) {
+        set_error("step %d: gaussian layer needs mean, stddev and a scope", idx);
+        return CKB_ERR_INVALID;
+      }
+      break;
+    case CKB_STEP_CONSTANT:
+      if (d.slot[0] < 0) {
+        set_error("step %d: constant layer needs a value", idx);
+        return CKB_ERR_INVALID;
+      }
+      break;
+    case CKB_STEP_DENSE:
+    case CKB_STEP_MIXING:
+    case CKB_STEP_TUCKER:
+      if (d.slot[0] < 0) {
+        set_error("step %d: sum layer needs weights", idx);
+        return CKB_ERR_INVALID;
+      }
+      // fallthrough
+    case CKB_STEP_HADAMARD:
+    case CKB_STEP_KRONECKER:
+      if (d.in_rows == nullptr || d.arity <= 0 || d.k_in <= 0 || d.gin_off < 0) {
+        set_error("step %d: inner layer needs gather rows and a gradient block", idx);
+        return CKB_ERR_INVALID;
+      }
+      if ((d.kind == CKB_STEP_KRONECKER || d.kind == CKB_STEP_TUCKER) && d.arity != 2) {
+        set_error("step %d: kronecker/tucker kernels support arity 2 only (got %d)", idx, d.arity);
+        return CKB_ERR_UNSUPPORTED;
+      }
+      if (d.kind == CKB_STEP_MIXING && d.k_in != d.k_out) {
+        set_error("step %d: mixing layer with %d != %d units", idx, d.k_in, d.k_out);
+        return CKB_ERR_INVALID;
+      }
+      break;
+    default:
+      set_error("step %d: unknown kind %d", idx, d.kind);
+      return CKB_ERR_INVALID;
+  }
+  return CKB_OK;
+}
+
+extern "C" {
+
+int ckb_version(void) { return CKB_VERSION; }
+const char* ckb_last_error(void) { return g_error; }
+
+int ckb_plan_create(const ckb_step_desc_t* steps, int32_t n_steps, const ckb_param_op_t* ops,
+                    int32_t n_ops, int32_t n_slots, ckb_plan_t** out) {
+  if (out == nullptr || steps == nullptr || n_steps <= 0 || n_slots < 0 || (n_ops > 0 && !ops)) {
+    set_error("ckb_plan_create: bad arguments");
+    return CKB_ERR_INVALID;
+  }
+  for (int i = 0; i < n_steps; ++i)
+    if (int rc = check_step(steps[i], i, n_slots)) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const ckb_param_op_t& op = ops[i];
+    if (op.src < 0 || op.src >= n_slots || op.dst < 0 || op.dst >= n_slots || op.rows <= 0 ||
+        op.cols <= 0 || op.kind < 0 || op.kind > CKB_POP_LSE_ROWS) {
+      set_error("parameter op %d: bad descriptor", i);
+      return CKB_ERR_INVALID;
+    }
+  }
+  ckb_plan* p = new ckb_plan();
+  p->steps.assign(steps, steps + n_steps);
+  if (n_ops > 0) p->ops.assign(ops, ops + n_ops);
+  p->n_slots = n_slots;
+  *out = p;
+  return CKB_OK;
+}
+
+void ckb_plan_destroy(ckb_plan_t* plan) { delete plan; }
+
+size_t ckb_plan_workspace_bytes(const ckb_plan_t* plan, int64_t batch) {
+  size_t need = 256;
+  if (plan == nullptr || batch <= 0) return need;
+  for (const ckb_step_desc_t& d : plan->steps) {
+    size_t w = 0;
+    switch (d.kind) {
+      case CKB_STEP_TABLE: w = table_bwd_ws(d, batch); break;
+      case CKB_STEP_MIXING: w = mixing_bwd_ws(d, batch); break;
+      case CKB_STEP_DENSE: w = dense_bwd_ws(d, batch); break;
+      case CKB_STEP_TUCKER: w = tucker_ws(d, batch); break;
+      default: break;
+    }
+    need = std::max(need, w + 256);
+  }
+  return need;
+}
+
+int ckb_transpose_input(const void* x, int32_t dtype, int64_t batch, int32_t num_vars, int64_t ld,
+                        void* xT, void* stream) {
+  if (batch < 0 || num_vars < 0 || (batch > 0 && num_vars > 0 && (!x || !xT))) {
+    set_error("ckb_transpose_input: bad arguments");
+    return CKB_ERR_INVALID;
+  }
+  return transpose_input(x, dtype, batch, num_vars, ld, xT, (cudaStream_t)stream);
+}
+
+int ckb_transpose_mask(const uint8_t* mask, int64_t rows, int32_t num_vars, uint8_t* maskT,
+                       void* stream) {
+  if (rows <= 0 || num_vars <= 0 || !mask || !maskT) {
+    set_error("ckb_transpose_mask: bad arguments");
+    return CKB_ERR_INVALID;
+  }
+  return transpose_mask(mask, rows, num_vars, maskT, (cudaStream_t)stream);
+}
+
+static int make_ctx(ckb_plan_t* plan, int32_t s0, int32_t s1, int64_t batch, const void* xT,
+                    int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                    float* const* tensors, float* const* grads, float* arena, float* garena,
+                    void* ws, size_t ws_bytes, void* stream, Ctx& c) {
+  if (plan == nullptr || tensors == nullptr || arena == nullptr || batch <= 0 || s0 < 0 ||
+      s1 > (int)plan->steps.size() || s0 > s1) {
+    set_error("bad plan / range / batch arguments");
+    return CKB_ERR_INVALID;
+  }
+  if (maskT != nullptr && mask_rows != 1 && mask_rows != batch) {
+    set_error("mask must have 1 or batch rows (got %lld)", (long long)mask_rows);
+    return CKB_ERR_INVALID;
+  }
+  c.B = batch;
+  c.xT = xT;
+  c.x_is_float = x_is_float;
+  c.maskT = maskT;
+  c.mask_ld = mask_rows;
+  c.tensors = tensors;
+  c.grads = grads;
+  c.arena = arena;
+  c.garena = garena;
+  c.ws = (char*)ws;
+  c.ws_bytes = ws_bytes;
+  c.stream = (cudaStream_t)stream;
+  c.launches = 0;
+  for (int i = s0; i < s1; ++i) {
+    const int k = plan->steps[i].kind;
+    if ((k == CKB_STEP_TABLE || k == CKB_STEP_GAUSSIAN) && xT == nullptr) {
+      set_error("step %d reads the evidence but xT is NULL", i);
+      return CKB_ERR_INVALID;
+    }
+  }
+  return CKB_OK;
+}
+
+int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                     const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                     float* const* tensors, float* arena, void* workspace, size_t workspace_bytes,
+                     int32_t flags, void* stream) {
+  Ctx c;
+  if (int rc = make_ctx(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows,
+                        tensors, nullptr, arena, nullptr, workspace, workspace_bytes, stream, c))
+    return rc;
+  if (flags & CKB_RUN_PARAM_OPS)
+    for (const ckb_param_op_t& op : plan->ops)
+      if (int rc = param_op_fwd(op, c)) return rc;
+  for (int i = step_begin; i < step_end; ++i) {
+    const ckb_step_desc_t& d = plan->steps[i];
+    int rc = CKB_OK;
+    switch (d.kind) {
+      case CKB_STEP_TABLE: rc = table_fwd(d, c); break;
+      case CKB_STEP_GAUSSIAN: rc = gaussian_fwd(d, c); break;
+      case CKB_STEP_CONSTANT: rc = constant_fwd(d, c); break;
+      case CKB_STEP_DENSE: rc = dense_fwd(d, c); break;
+      case CKB_STEP_MIXING: rc = mixing_fwd(d, c); break;
+      case CKB_STEP_HADAMARD: rc = hadamard_fwd(d, c); break;
+      case CKB_STEP_KRONECKER: rc = kronecker_fwd(d, c); break;
+      case CKB_STEP_TUCKER: rc = tucker_fwd(d, c); break;
+    }
+    if (rc != CKB_OK) return rc;
+  }
+  plan->last_launches = c.launches;
+  return CKB_OK;
+}
+
+int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                      const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                      float* const* tensors, float* const* grads, const float* arena,
+                      float* garena, void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* stream) {
+  Ctx c;
+  if (grads == nullptr || garena == nullptr) {
+    set_error("ckb_plan_backward: grads / garena are NULL");
+    return CKB_ERR_INVALID;
+  }
+  if (int rc = make_ctx(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows,
+                        tensors, grads, const_cast<float*>(arena), garena, workspace,
+                        workspace_bytes, stream, c))
+    return rc;
+  for (int i = step_end - 1; i >= step_begin; --i) {
+    const ckb_step_desc_t& d = plan->steps[i];
+    int rc = CKB_OK;
+    switch (d.kind) {
+      case CKB_STEP_TABLE: rc = table_bwd(d, c); break;
+      case CKB_STEP_GAUSSIAN: rc = gaussian_bwd(d, c); break;
+      case CKB_STEP_CONSTANT: rc = constant_bwd(d, c); break;
+      case CKB_STEP_DENSE: rc = dense_bwd(d, c); break;
+      case CKB_STEP_MIXING: rc = mixing_bwd(d, c); break;
+      case CKB_STEP_HADAMARD: rc = hadamard_bwd(d, c); break;
+      case CKB_STEP_KRONECKER: rc = kronecker_bwd(d, c); break;
+      case CKB_STEP_TUCKER: rc = tucker_bwd(d, c); break;
+    }
+    if (rc != CKB_OK) return rc;
+  }
+  if (flags & CKB_RUN_PARAM_OPS)
+    for (auto it = plan->ops.rbegin(); it != plan->ops.rend(); ++it)
+      if (int rc = param_op_bwd(*it, c)) return rc;
+  plan->last_launches = c.launches;
+  return CKB_OK;
+}
+
+int64_t ckb_plan_last_launches(const ckb_plan_t* plan) { return plan ? plan->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,562 @@
+"""Device runtime: binds a :class:`CircuitPlan` to the CUDA library and to autograd.
+
+One `PlanRuntime` per circuit; per device it owns the index tables, the C plan handle, the
+effective-parameter buffers and a scratch workspace.  A forward pass is ONE call into the library
+(`ckb_plan_forward`: parameter ops + every folded layer), a backward pass is one more
+(`ckb_plan_backward`), wrapped in a single `torch.autograd.Function` whose differentiable inputs
+are the parameter tensors.  PyTorch is used for memory, streams and autograd plumbing only.
+
+What this replaces in the reference: `TorchDiAcyclicGraph.evaluate`
+(cirkit/backend/torch/graph/modules.py:303-335), `LayerAddressBook.lookup`
+(circuits.py:30-71), every `TorchLayer.forward` on the path and the autograd graph they record.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from .plan import CircuitPlan, ParamSpec, StepSpec, build_layout
+
+_DTYPES = {
+    torch.uint8: L.U8,
+    torch.int16: L.I16,
+    torch.int32: L.I32,
+    torch.int64: L.I64,
+    torch.float32: L.F32,
+    torch.float64: L.F64,
+}
+
+
+def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
+    """Host (PyTorch) evaluation of one re-parameterisation node, used only for the part of a
+    parameter chain that has no fused kernel (small tensors, once per step)."""
+    nd = t.ndim - 1
+    if op == "softmax":
+        return torch.softmax(t, dim=attrs.get("dim", nd - 1) + 1)
+    if op == "log_softmax":
+        return torch.log_softmax(t, dim=attrs.get("dim", nd - 1) + 1)
+    if op == "scaled_sigmoid":
+        return torch.sigmoid(t) * (attrs["vmax"] - attrs["vmin"]) + attrs["vmin"]
+    if op == "sigmoid":
+        return torch.sigmoid(t)
+    if op == "exp":
+        return torch.exp(t)
+    if op == "log":
+        return torch.log(t)
+    if op == "square":
+        return torch.square(t)
+    if op == "softplus":
+        return torch.nn.functional.softplus(t)
+    if op == "clamp":
+        return torch.clamp(t, min=attrs.get("vmin"), max=attrs.get("vmax"))
+    if op == "mixing":
+        d = torch.vmap(torch.vmap(torch.diag, in_dims=1))(t)
+        return d.permute(0, 2, 1, 3).flatten(start_dim=2)
+    raise ValueError(f"unknown parameter op {op!r}")
+
+
+@dataclass
+class _Binding:
+    """One layer parameter: source tensor -> host prefix ops -> optional fused op -> slot."""
+
+    sid: int
+    name: str
+    spec: ParamSpec
+    prefix: list
+    native: tuple | None  # (pop kind, rows, cols, aux, a, b)
+    src_shape: tuple
+    eff_shape: tuple
+    src_slot: int = -1
+    dst_slot: int = -1
+
+
+def _is_last_dim(op: tuple, name: str, shape: tuple) -> bool:
+    nd = len(shape) - 1
+    return op[0] == name and op[1].get("dim", nd - 1) in (nd - 1, -1)
+
+
+def _bind(sid: int, step: StepSpec, name: str, spec: ParamSpec) -> _Binding:
+    ops = list(spec.ops)
+    shape = tuple(spec.shape)
+    F = shape[0]
+    native = None
+    prefix = ops
+    eff_shape = shape
+    kind = step.kind
+    if kind == "categorical":
+        K, V = shape[1], shape[2]
+        eff_shape = (F, V, K)
+        if name == "probs":
+            if ops and _is_last_dim(ops[-1], "softmax", shape):
+                prefix, native = ops[:-1], (L.POP_LOG_SOFTMAX_T, F, V, K, 0.0, 0.0)
+            else:
+                native = (L.POP_LOG_T, F, V, K, 0.0, 0.0)
+        else:
+            if ops and _is_last_dim(ops[-1], "log_softmax", shape):
+                prefix, native = ops[:-1], (L.POP_LOG_SOFTMAX_T, F, V, K, 0.0, 0.0)
+            else:
+                native = (L.POP_COPY_T, F, V, K, 0.0, 0.0)
+    elif kind == "embedding":
+        K, V = shape[1], shape[2]
+        eff_shape = (F, V, K)
+        native = (L.POP_LOG_T, F, V, K, 0.0, 0.0)
+    elif kind == "gaussian":
+        if name == "stddev" and ops and ops[-1][0] == "scaled_sigmoid":
+            a = ops[-1][1]
+            prefix = ops[:-1]
+            native = (L.POP_SCALED_SIGMOID, int(np.prod(shape)), 1, 0, float(a["vmin"]), float(a["vmax"]))
+    elif kind == "constant":
+        if not step.config.get("log_space", False):
+            native = (L.POP_LOG, int(np.prod(shape)), 1, 0, 0.0, 0.0)
+    elif kind in ("sum", "cpt", "mixing", "tucker"):
+        if ops and _is_last_dim(ops[-1], "softmax", shape):
+            prefix = ops[:-1]
+            native = (L.POP_SOFTMAX, int(np.prod(shape[:-1])), shape[-1], 0, 0.0, 0.0)
+    return _Binding(sid, name, spec, prefix, native, shape, eff_shape)
+
+
+_KIND = {
+    "categorical": L.STEP_TABLE,
+    "embedding": L.STEP_TABLE,
+    "gaussian": L.STEP_GAUSSIAN,
+    "constant": L.STEP_CONSTANT,
+    "sum": L.STEP_DENSE,
+    "cpt": L.STEP_DENSE,
+    "mixing": L.STEP_MIXING,
+    "hadamard": L.STEP_HADAMARD,
+    "kronecker": L.STEP_KRONECKER,
+    "tucker": L.STEP_TUCKER,
+}
+_PARAM_ORDER = {
+    "categorical": ("probs|logits",),
+    "embedding": ("weight",),
+    "gaussian": ("mean", "stddev", "log_partition"),
+    "constant": ("value",),
+    "sum": ("weight",),
+    "cpt": ("weight",),
+    "mixing": ("weight",),
+    "tucker": ("weight",),
+    "hadamard": (),
+    "kronecker": (),
+}
+
+
+class _DeviceState:
+    """Everything that lives on one GPU for one plan."""
+
+    def __init__(self, rt: "PlanRuntime", device: torch.device):
+        self.device = device
+        lay, plan = rt.layout, rt.plan
+        lib = L.load()
+        self.keep: list[Tensor] = []  # index tables referenced by the C plan
+
+        def up(a: np.ndarray, dtype) -> int:
+            if a is None or a.size == 0:
+                t = torch.zeros(1, dtype=dtype, device=device)
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+            self.keep.append(t)
+            return t.data_ptr()
+
+        descs = (L.StepDesc * len(plan.steps))()
+        for sid, s in enumerate(plan.steps):
+            d = descs[sid]
+            d.kind = _KIND[s.kind]
+            d.num_folds, d.arity = s.num_folds, s.arity
+            d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
+            d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
+            d.num_states = int(s.config.get("num_categories", s.config.get("num_states", 0)))
+            d.gin_h = int(lay.gin_h[sid])
+            d.out_off = int(lay.out_off[sid])
+            d.gin_off = int(lay.gin_off[sid])
+            d.in_rows = up(lay.in_rows[sid], torch.int64) if lay.in_rows[sid] is not None else None
+            d.scope_var = up(s.scope_idx, torch.int32) if s.scope_idx is not None else None
+            d.cons_ptr = up(lay.cons_ptr[sid], torch.int32)
+            d.cons_rows = up(lay.cons_rows[sid], torch.int64)
+            slots = rt.step_slots[sid]
+            for i in range(4):
+                d.slot[i] = slots[i] if i < len(slots) else -1
+            d.int_slot = rt.int_slots.get(sid, -1)
+        ops = (L.ParamOp * max(1, len(rt.native_ops)))()
+        for i, (b, (kind, rows, cols, aux, a, bb)) in enumerate(rt.native_ops):
+            ops[i].kind, ops[i].src, ops[i].dst = kind, b.src_slot, b.dst_slot
+            ops[i].rows, ops[i].cols, ops[i].aux, ops[i].a, ops[i].b = rows, cols, aux, a, bb
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(
+                lib.ckb_plan_create(descs, len(plan.steps), ops, len(rt.native_ops), rt.n_slots,
+                                    C.byref(handle)),
+                "ckb_plan_create",
+            )
+        self.handle = handle
+        self.lib = lib
+        # effective parameters and their gradients (runtime-owned, persistent)
+        self.eff: dict[int, Tensor] = {}
+        self.eff_grad: dict[int, Tensor] = {}
+        for b in rt.bindings:
+            if b.native is not None:
+                self.eff[b.dst_slot] = torch.empty(b.eff_shape, dtype=torch.float32, device=device)
+        self.int_buf = {
+            sid: torch.zeros(plan.steps[sid].num_folds, plan.steps[sid].num_output_units,
+                             dtype=torch.float32, device=device)
+            for sid in rt.int_buf_sids
+        }
+        self.ws: Tensor | None = None
+
+    def workspace(self, batch: int) -> Tensor:
+        need = int(self.lib.ckb_plan_workspace_bytes(self.handle, batch))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.ws
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.lib.ckb_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class PlanRuntime:
+    def __init__(self, plan: CircuitPlan):
+        plan.validate()
+        if plan.semiring != "lse-sum":
+            raise NotImplementedError("only the 'lse-sum' semiring has a CUDA path")
+        self.plan = plan
+        self.layout = build_layout(plan)
+        self.bindings: list[_Binding] = []
+        self.step_slots: list[list[int]] = []
+        self.int_slots: dict[int, int] = {}
+        self.int_buf_sids: list[int] = []  # steps whose integrate values live in a runtime buffer
+        n = 0
+        for sid, s in enumerate(plan.steps):
+            slots = []
+            for pname in _PARAM_ORDER[s.kind]:
+                name = next((c for c in pname.split("|") if c in s.params), None)
+                if name is None:
+                    slots.append(-1)
+                    continue
+                b = _bind(sid, s, name, s.params[name])
+                b.src_slot = n
+                n += 1
+                if b.native is not None:
+                    b.dst_slot = n
+                    n += 1
+                else:
+                    b.dst_slot = b.src_slot
+                self.bindings.append(b)
+                slots.append(b.dst_slot)
+            self.step_slots.append(slots)
+            if s.kind == "categorical" and "logits" in s.params:
+                self.int_slots[sid] = n  # logsumexp(logits): what integrating the variable yields
+                self.int_buf_sids.append(sid)
+                n += 1
+            if s.kind == "gaussian" and "log_partition" in s.params:
+                self.int_slots[sid] = slots[2]
+        self.n_slots = n
+        self.native_ops = [(b, b.native) for b in self.bindings if b.native is not None]
+        self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
+        self._states: dict[torch.device, _DeviceState] = {}
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ device state
+    def state(self, device: torch.device) -> _DeviceState:
+        if device.type != "cuda":
+            raise RuntimeError(
+                "cirkit_b200 evaluates circuits with CUDA kernels only: parameters must live on a "
+                f"CUDA device (found {device}).  There is no CPU fallback."
+            )
+        device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        st = self._states.get(device)
+        if st is None:
+            st = self._states[device] = _DeviceState(self, device)
+        return st
+
+    # ------------------------------------------------------------------ parameters
+    def parameter_tensors(self, leaves: Sequence[Tensor], externals: dict | None) -> list[Tensor]:
+        out = []
+        for b in self.bindings:
+            if b.spec.leaf < 0:
+                if externals is None or (b.sid, b.name) not in externals:
+                    raise ValueError(f"missing external parameter for step {b.sid} {b.name!r}")
+                t = externals[(b.sid, b.name)]
+            else:
+                t = leaves[b.spec.leaf]
+                if b.spec.fold_idx is not None:
+                    idx = torch.as_tensor(b.spec.fold_idx, dtype=torch.int64, device=t.device)
+                    t = t.index_select(0, idx)
+            for op, attrs in b.prefix:
+                t = apply_param_op(t, op, attrs)
+            if t.dtype != torch.float32:
+                t = t.to(torch.float32)
+            if tuple(t.shape) != b.src_shape:
+                raise ValueError(
+                    f"step {b.sid} parameter {b.name!r}: expected shape {b.src_shape}, got {tuple(t.shape)}"
+                )
+            out.append(t.contiguous())
+        return out
+
+    # ------------------------------------------------------------------ evaluation
+    def evaluate(
+        self,
+        x: Tensor | None,
+        leaves: Sequence[Tensor],
+        externals: dict | None = None,
+        integrate_mask: Tensor | None = None,
+    ) -> Tensor:
+        """Returns the circuit output, shape (B, O, K) (B = 1 when the circuit reads no evidence)."""
+        if x is not None and x.ndim != 2:
+            raise ValueError(
+                "The input to the circuit should have shape (B, D), "
+                "where B is the batch size and D is the number of variables "
+                "the circuit is defined on"
+            )
+        if x is None and self.reads_evidence:
+            raise ValueError(
+                f"Expected some input 'x', as the circuit has scope '{self.plan.scope}'"
+            )
+        if x is not None and x.shape[1] < self.plan.num_variables:
+            raise IndexError(
+                f"the circuit reads variable {self.plan.num_variables - 1} but the input has "
+                f"{x.shape[1]} columns"
+            )
+        P = self.parameter_tensors(leaves, externals)
+        if not P:
+            raise ValueError("circuit without parameters")
+        st = self.state(P[0].device)
+        return _PlanFn.apply(self, st, x, integrate_mask, *P)
+
+
+class _PlanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rt: PlanRuntime, st: _DeviceState, x, mask, *P):
+        lib, dev = st.lib, st.device
+        lay, plan = rt.layout, rt.plan
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            xT = None
+            x_is_float = 0
+            B = 1
+            if x is not None:
+                B = int(x.shape[0])
+                if B == 0:
+                    raise ValueError("empty batch")
+                if x.dtype not in _DTYPES:
+                    x = x.to(torch.float32 if x.is_floating_point() else torch.int64)
+                xd = x.detach()
+                if xd.device != dev:
+                    xd = xd.to(dev, non_blocking=True)
+                if xd.stride(1) != 1:
+                    xd = xd.contiguous()
+                x_is_float = 1 if xd.is_floating_point() else 0
+                D = plan.num_variables
+                xT = torch.empty((max(D, 1), B), dtype=torch.float32 if x_is_float else torch.int32, device=dev)
+                if rt.reads_evidence:
+                    L.check(
+                        lib.ckb_transpose_input(xd.data_ptr(), _DTYPES[xd.dtype], B, D, xd.stride(0),
+                                                xT.data_ptr(), stream),
+                        "ckb_transpose_input",
+                    )
+            maskT, mask_rows = None, 0
+            if mask is not None:
+                m = mask.to(device=dev, dtype=torch.uint8).contiguous()
+                if m.ndim == 1:
+                    m = m.unsqueeze(0)
+                if m.shape[0] not in (1, B) or m.shape[1] < plan.num_variables:
+                    raise ValueError(f"integration mask of shape {tuple(mask.shape)} does not match x")
+                mask_rows = int(m.shape[0])
+                maskT = torch.empty((plan.num_variables, mask_rows), dtype=torch.uint8, device=dev)
+                L.check(
+                    lib.ckb_transpose_mask(m.data_ptr(), mask_rows, plan.num_variables, maskT.data_ptr(), stream)
+                    if m.shape[1] == plan.num_variables
+                    else lib.ckb_transpose_mask(m[:, : plan.num_variables].contiguous().data_ptr(), mask_rows,
+                                                plan.num_variables, maskT.data_ptr(), stream),
+                    "ckb_transpose_mask",
+                )
+                # values an integrated variable contributes for unnormalised categoricals
+                for sid, buf in st.int_buf.items():
+                    i = next(j for j, bb in enumerate(rt.bindings) if bb.sid == sid and bb.name == "logits")
+                    if rt.bindings[i].native[0] == L.POP_LOG_SOFTMAX_T:
+                        buf.zero_()  # normalised logits integrate to log 1
+                    else:
+                        buf.copy_(torch.logsumexp(P[i].detach(), dim=2))
+            tensors = (C.c_void_p * rt.n_slots)()
+            for b, p in zip(rt.bindings, P):
+                tensors[b.src_slot] = p.data_ptr()
+                if b.native is not None:
+                    tensors[b.dst_slot] = st.eff[b.dst_slot].data_ptr()
+            for sid, slot in rt.int_slots.items():
+                if sid in st.int_buf:
+                    tensors[slot] = st.int_buf[sid].data_ptr()
+            arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
+            ws = st.workspace(B)
+            L.check(
+                lib.ckb_plan_forward(
+                    st.handle, 0, len(plan.steps), B,
+                    xT.data_ptr() if xT is not None else None, x_is_float,
+                    maskT.data_ptr() if maskT is not None else None, mask_rows,
+                    tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
+                "ckb_plan_forward",
+            )
+            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle)) + (1 if xT is not None else 0)
+            K = plan.num_output_units
+            rows = lay.out_rows
+            if len(rows) == 1:
+                r = int(rows[0])
+                out = arena[B * r : B * r + B * K].view(B, 1, K).clone()
+            else:
+                out = torch.stack([arena[B * int(r) : B * int(r) + B * K].view(B, K) for r in rows], dim=1)
+        ctx.rt, ctx.st, ctx.B = rt, st, B
+        ctx.x_is_float, ctx.mask_rows = x_is_float, mask_rows
+        ctx.xT, ctx.maskT, ctx.arena = xT, maskT, arena
+        ctx.P = P
+        ctx.tensors = tensors
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        rt, st, B = ctx.rt, ctx.st, ctx.B
+        lib, dev = st.lib, st.device
+        lay, plan = rt.layout, rt.plan
+        need = ctx.needs_input_grad[4:]
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            garena = torch.empty(B * lay.garena_units, dtype=torch.float32, device=dev)
+            O, K = plan.num_outputs, plan.num_output_units
+            go = garena[B * lay.out_goff : B * lay.out_goff + O * B * K].view(O, B, K)
+            go.copy_(gout.to(torch.float32).transpose(0, 1))
+            grads = (C.c_void_p * rt.n_slots)()
+            outs: list[Tensor | None] = []
+            for b, p, nd in zip(rt.bindings, ctx.P, need):
+                if not nd:
+                    outs.append(None)
+                    continue
+                g = torch.empty_like(p)
+                outs.append(g)
+                grads[b.src_slot] = g.data_ptr()
+                if b.native is not None:
+                    eg = st.eff_grad.get(b.dst_slot)
+                    if eg is None:
+                        eg = st.eff_grad[b.dst_slot] = torch.empty_like(st.eff[b.dst_slot])
+                    grads[b.dst_slot] = eg.data_ptr()
+            ws = st.workspace(B)
+            L.check(
+                lib.ckb_plan_backward(
+                    st.handle, 0, len(plan.steps), B,
+                    ctx.xT.data_ptr() if ctx.xT is not None else None, ctx.x_is_float,
+                    ctx.maskT.data_ptr() if ctx.maskT is not None else None, ctx.mask_rows,
+                    ctx.tensors, grads, ctx.arena.data_ptr(), garena.data_ptr(),
+                    ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
+                "ckb_plan_backward",
+            )
+            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle))
+        ctx.arena = None
+        return (None, None, None, None, *outs)
+
+
+# ----------------------------------------------------------------------------- per-step timing
+def step_algorithmic_bytes(plan: CircuitPlan, sid: int, batch: int) -> tuple[int, int]:
+    """Algorithmic HBM bytes of the forward and of the backward launch of one step: every tensor
+    the step must read or write counted once, fp32 (see DESIGN.md "Kernels")."""
+    s = plan.steps[sid]
+    F, H, Ki, Ko, B = s.num_folds, s.arity, s.num_input_units, s.num_output_units, batch
+    out = F * B * Ko * 4
+    if s.is_input:
+        p = sum(int(np.prod(q.shape)) for q in s.params.values()) * 4
+        x = B * F * 4
+        return out + x + p, out + x + p  # fwd: table + x -> y ; bwd: g + x -> dT
+    inp = F * H * B * Ki * 4
+    p = sum(int(np.prod(q.shape)) for q in s.params.values()) * 4
+    hg = 1 if s.kind in ("cpt", "hadamard") else H
+    gin = F * hg * B * Ki * 4
+    fwd = inp + p + out
+    bwd = (inp + out if s.kind not in ("hadamard", "kronecker") else 0) + out + gin + 2 * p
+    return fwd, bwd
+
+
+def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: int = 3) -> list[dict]:
+    """Times every step's forward and backward launch group in isolation with CUDA events on the
+    launching stream (bench.py's roofline leg).  Returns one dict per step."""
+    P = rt.parameter_tensors(leaves, None)
+    st = rt.state(P[0].device)
+    lib, dev, plan, lay = st.lib, st.device, rt.plan, rt.layout
+    S = len(plan.steps)
+    with torch.cuda.device(dev), torch.no_grad():
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        B = int(x.shape[0])
+        xd = x.to(dev)
+        x_is_float = 1 if xd.is_floating_point() else 0
+        xT = torch.empty((plan.num_variables, B), dtype=torch.float32 if x_is_float else torch.int32, device=dev)
+        L.check(lib.ckb_transpose_input(xd.data_ptr(), _DTYPES[xd.dtype], B, plan.num_variables,
+                                        xd.stride(0), xT.data_ptr(), stream), "ckb_transpose_input")
+        tensors = (C.c_void_p * rt.n_slots)()
+        grads = (C.c_void_p * rt.n_slots)()
+        keep = []
+        for b, p in zip(rt.bindings, P):
+            tensors[b.src_slot] = p.data_ptr()
+            g = torch.empty_like(p)
+            keep.append(g)
+            grads[b.src_slot] = g.data_ptr()
+            if b.native is not None:
+                tensors[b.dst_slot] = st.eff[b.dst_slot].data_ptr()
+                eg = st.eff_grad.get(b.dst_slot)
+                if eg is None:
+                    eg = st.eff_grad[b.dst_slot] = torch.empty_like(st.eff[b.dst_slot])
+                grads[b.dst_slot] = eg.data_ptr()
+        arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
+        garena = torch.zeros(B * lay.garena_units, dtype=torch.float32, device=dev)
+        O, K = plan.num_outputs, plan.num_output_units
+        garena[B * lay.out_goff : B * lay.out_goff + O * B * K] = -1.0 / B
+        ws = st.workspace(B)
+
+        def fwd(s0, s1, flags):
+            L.check(lib.ckb_plan_forward(st.handle, s0, s1, B, xT.data_ptr(), x_is_float, None, 0,
+                                         tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                                         stream), "ckb_plan_forward")
+            return int(lib.ckb_plan_last_launches(st.handle))
+
+        def bwd(s0, s1, flags):
+            L.check(lib.ckb_plan_backward(st.handle, s0, s1, B, xT.data_ptr(), x_is_float, None, 0,
+                                          tensors, grads, arena.data_ptr(), garena.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), flags, stream), "ckb_plan_backward")
+            return int(lib.ckb_plan_last_launches(st.handle))
+
+        def timed(fn, *a):
+            best, n = [], 0
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                n = fn(*a)
+                e1.record()
+                e1.synchronize()
+                best.append(e0.elapsed_time(e1))
+            return float(np.mean(best)), n
+
+        fwd(0, S, L.RUN_PARAM_OPS)  # warm everything once
+        bwd(0, S, L.RUN_PARAM_OPS)
+        res = []
+        t, n = timed(fwd, 0, 0, L.RUN_PARAM_OPS)
+        res.append({"step": -1, "kind": "param_ops", "fwd_ms": t, "fwd_launches": n})
+        for sid in range(S):
+            t, n = timed(fwd, sid, sid + 1, 0)
+            fb, bb = step_algorithmic_bytes(plan, sid, B)
+            res.append({"step": sid, "kind": plan.steps[sid].kind, "F": plan.steps[sid].num_folds,
+                        "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb})
+        for sid in reversed(range(S)):
+            t, n = timed(bwd, sid, sid + 1, 0)
+            res[sid + 1]["bwd_ms"] = t
+            res[sid + 1]["bwd_launches"] = n
+        t, n = timed(bwd, 0, 0, L.RUN_PARAM_OPS)
+        res[0]["bwd_ms"] = t
+        res[0]["bwd_launches"] = n
+        pbytes = sum(int(np.prod(l.shape)) for l in plan.leaves) * 4
+        res[0]["fwd_bytes"] = 2 * pbytes
+        res[0]["bwd_bytes"] = 3 * pbytes
+    return res

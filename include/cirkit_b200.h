@@ -1,0 +1,162 @@
+/*
+ * cirkit_b200 -- C ABI of the B200-native (sm_100a) circuit evaluator.
+ *
+ * The reference (april-tools/cirkit) has no FFI of its own: its "backend" is the Python class
+ * TorchCircuit whose forward pass loops over folded layers and calls stock PyTorch ops
+ * (cirkit/backend/torch/circuits.py:242-278, graph/modules.py:303-335).  This header declares
+ * the entry points a native backend for that path binds instead; INTEGRATION.md shows the
+ * ctypes stub on the reference side.  Conventions:
+ *
+ *   - C linkage, plain pointers and sizes, no torch / C++ types in any signature;
+ *   - every function returns 0 on success and a negative ckb_status on failure; the message of
+ *     the last failure on the calling thread is available from ckb_last_error();
+ *   - no hidden device allocations: activations, gradients, parameters and scratch are
+ *     caller-provided device buffers (ckb_plan_workspace_bytes tells how much scratch);
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as void*),
+ *     nothing synchronises;
+ *   - no ownership transfer: the plan copies the small descriptors it is given and keeps the
+ *     DEVICE pointers found inside them (index tables), which must outlive the plan;
+ *   - thread-compatible: no mutable globals besides the thread-local error string.
+ *
+ * Memory model (see cirkit_b200/plan.py:PlanLayout).  All offsets are "per sample" float
+ * offsets: the block of step s lives at arena + batch * out_off[s] and is laid out
+ * (fold, batch, unit), so a plan is independent of the batch size.
+ */
+#ifndef CIRKIT_B200_H
+#define CIRKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CKB_VERSION 1
+
+typedef enum {
+  CKB_OK = 0,
+  CKB_ERR_INVALID = -1,     /* bad argument / inconsistent descriptor          */
+  CKB_ERR_UNSUPPORTED = -2, /* shape or layer kind without a kernel            */
+  CKB_ERR_CUDA = -3,        /* a CUDA runtime call or launch failed            */
+  CKB_ERR_WORKSPACE = -4    /* caller-provided workspace too small             */
+} ckb_status;
+
+/* Folded layer kinds.  Each restates one reference layer (file:line in cirkit/backend/torch): */
+typedef enum {
+  CKB_STEP_TABLE = 0,     /* Categorical layers/input.py:399-412 and Embedding :258-266:
+                             y[f,b,k] = T[f, x[b,var_f], k], T = log-table (F,V,K)              */
+  CKB_STEP_GAUSSIAN = 1,  /* layers/input.py:661-670                                            */
+  CKB_STEP_CONSTANT = 2,  /* layers/input.py:739-743 (value already mapped to log space)        */
+  CKB_STEP_DENSE = 3,     /* TorchSumLayer layers/inner.py:266-273 (flags=CKB_DENSE_CONCAT) and
+                             TorchCPTLayer layers/optimized.py:171-178 (flags=0), both through
+                             LSESumSemiring.apply_reduce semiring.py:382-408                    */
+  CKB_STEP_MIXING = 4,    /* TorchSumLayer fed by TorchMixingWeightParameter
+                             (parameters/nodes.py:847-862), computed on the (F,K,H) weights     */
+  CKB_STEP_HADAMARD = 5,  /* layers/inner.py:126-127                                            */
+  CKB_STEP_KRONECKER = 6, /* layers/inner.py:178-187 (arity 2)                                  */
+  CKB_STEP_TUCKER = 7     /* layers/optimized.py:89-103 (arity 2)                               */
+} ckb_step_kind;
+
+#define CKB_DENSE_CONCAT 1 /* reduce over the concatenation of the H inputs instead of their sum */
+
+typedef struct {
+  int32_t kind;       /* ckb_step_kind                                                        */
+  int32_t num_folds;  /* F                                                                    */
+  int32_t arity;      /* H                                                                    */
+  int32_t k_in;       /* Ki: units of every gathered input row                                */
+  int32_t k_out;      /* Ko                                                                   */
+  int32_t flags;
+  int32_t num_states; /* V (CKB_STEP_TABLE)                                                   */
+  int32_t gin_h;      /* input-gradient rows per fold: 1 (shared by all inputs) or H          */
+  int64_t out_off;    /* activation arena: per-sample float offset of the (F,B,Ko) block      */
+  int64_t gin_off;    /* gradient arena: per-sample float offset of the (F,gin_h,B,Ki) block  */
+  const int64_t* in_rows;   /* device (F*H): per-sample float offsets of the gathered rows    */
+  const int32_t* scope_var; /* device (F): variable read by every fold (input layers)         */
+  const int32_t* cons_ptr;  /* device (F+1): CSR over the gradient rows each output row sums  */
+  const int64_t* cons_rows; /* device (nnz): per-sample float offsets into the gradient arena */
+  int32_t slot[4];    /* tensor-table slots of the effective parameters, -1 = absent:
+                           TABLE: {T}   GAUSSIAN: {mean, stddev, log_partition}
+                           CONSTANT: {value}   DENSE/TUCKER: {W (F,Ko,Kred)}   MIXING: {w (F,K,H)} */
+  int32_t int_slot;   /* slot of the (F,Ko) values an integrated variable yields, -1 = zeros   */
+} ckb_step_desc_t;
+
+/* Parameter re-parameterisation ops, run before the layers (forward) and after them (backward).
+ * They restate cirkit/backend/torch/parameters/nodes.py and fuse the layout changes the
+ * kernels want (tables are stored (F,V,K) so a sample reads K contiguous floats). */
+typedef enum {
+  CKB_POP_SOFTMAX = 0,       /* nodes.py:764-772 over the last axis: (rows, cols)              */
+  CKB_POP_LOG_SOFTMAX_T = 1, /* log(softmax(src)) transposed: src (rows=F, aux=K, cols=V) -> (F,V,K) */
+  CKB_POP_LOG_T = 2,         /* log(src) transposed, same shapes                               */
+  CKB_POP_COPY_T = 3,        /* transpose only                                                 */
+  CKB_POP_SCALED_SIGMOID = 4,/* nodes.py:682-699: sigmoid(x)*(b-a)+a, elementwise              */
+  CKB_POP_LOG = 5,           /* elementwise log                                                */
+  CKB_POP_LSE_ROWS = 6       /* logsumexp over the last axis: (rows, cols) -> (rows); no backward */
+} ckb_param_op_kind;
+
+typedef struct {
+  int32_t kind; /* ckb_param_op_kind */
+  int32_t src;  /* tensor-table slot read  */
+  int32_t dst;  /* tensor-table slot written */
+  int32_t cols;
+  int64_t rows;
+  int32_t aux;
+  float a, b;
+} ckb_param_op_t;
+
+typedef struct ckb_plan ckb_plan_t;
+
+/* element types accepted by ckb_transpose_input */
+typedef enum { CKB_U8 = 0, CKB_I32 = 1, CKB_I64 = 2, CKB_F32 = 3, CKB_F64 = 4, CKB_I16 = 5 } ckb_dtype;
+
+int ckb_version(void);
+const char* ckb_last_error(void);
+
+/* Build a plan from n_steps step descriptors and n_ops parameter ops over a table of n_slots
+ * tensors.  Replaces: TorchCircuit.__init__ building its address book
+ * (circuits.py:73-119, graph/modules.py:262-265). */
+int ckb_plan_create(const ckb_step_desc_t* steps, int32_t n_steps, const ckb_param_op_t* ops,
+                    int32_t n_ops, int32_t n_slots, ckb_plan_t** out);
+void ckb_plan_destroy(ckb_plan_t* plan);
+
+/* Scratch bytes ckb_plan_forward / ckb_plan_backward need for a given batch size. */
+size_t ckb_plan_workspace_bytes(const ckb_plan_t* plan, int64_t batch);
+
+/* x (batch, num_vars) row-major with leading dimension ld (elements) -> xT (num_vars, batch):
+ * int32 for integer dtypes, float32 for floating dtypes.  Replaces the per-layer
+ * `x[..., scope_idx].permute(1, 0, 2)` gather of circuits.py:66. */
+int ckb_transpose_input(const void* x, int32_t dtype, int64_t batch, int32_t num_vars, int64_t ld,
+                        void* xT, void* stream);
+
+/* mask (rows, num_vars) bool bytes -> maskT (num_vars, rows) bytes (IntegrateQuery, queries.py:48-109) */
+int ckb_transpose_mask(const uint8_t* mask, int64_t rows, int32_t num_vars, uint8_t* maskT,
+                       void* stream);
+
+#define CKB_RUN_PARAM_OPS 1 /* forward: evaluate the parameter ops; backward: back-propagate them */
+
+/* One forward pass over steps [step_begin, step_end).  Replaces TorchDiAcyclicGraph.evaluate
+ * (graph/modules.py:303-335) + LayerAddressBook.lookup (circuits.py:30-71) + every layer's
+ * forward.  tensors: HOST array of n_slots device pointers.  maskT (num_vars, mask_rows) may be
+ * NULL; mask_rows is batch, or 1 when a single mask row is broadcast over the batch. */
+int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                     const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                     float* const* tensors, float* arena, void* workspace, size_t workspace_bytes,
+                     int32_t flags, void* stream);
+
+/* Reverse pass over the same steps.  Replaces autograd's walk over the reference's op graph
+ * (SURVEY §3(c)).  The caller has written d(loss)/d(output) into the output-gradient block of
+ * garena.  grads: HOST array of n_slots device pointers (NULL = gradient not wanted); every
+ * requested gradient is overwritten, not accumulated. */
+int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                      const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                      float* const* tensors, float* const* grads, const float* arena,
+                      float* garena, void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* stream);
+
+/* Number of kernels the last forward/backward call on this plan enqueued (bench bookkeeping). */
+int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIRKIT_B200_H */

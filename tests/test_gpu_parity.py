@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's outputs (golden fixtures,
+float64) and against the CPU oracle on the same seeded inputs.
+
+Stated tolerances (derived from the reference's own fp32-vs-fp64 gap):
+  forward    |ll - ll_ref64| <= 5e-7 * |ll_ref64| + 1e-5        (2.2e-3 at ll = -4357)
+  gradients  per parameter tensor  max|g - g_ref64| <= max(5e-7, 1e-4 * max|g_ref64|)
+"""
+import math
+
+import pytest
+import torch
+
+from helpers import Golden, golden_names, grad_tolerance
+
+pytestmark = pytest.mark.gpu
+
+FULL = golden_names("full")
+SEEDED = golden_names("seeded")
+FWD_RTOL, FWD_ATOL = 5e-7, 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _circuit(g: Golden, dev):
+    from cirkit_b200 import B200Circuit
+
+    cc = B200Circuit(g.plan)
+    with torch.no_grad():
+        for p, v in zip(cc.leaves, g.leaves(torch.float32)):
+            p.copy_(v)
+    return cc.to(dev)
+
+
+def _check_forward(y, y_ref):
+    y = y.detach().double().cpu()
+    assert y.shape == y_ref.shape
+    err = (y - y_ref).abs()
+    tol = FWD_RTOL * y_ref.abs() + FWD_ATOL
+    assert bool((err <= tol).all()), f"max err {err.max().item():.3e} (tol {tol.max().item():.3e})"
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_forward_backward_vs_reference(name, dev):
+    g = Golden(name)
+    cc = _circuit(g, dev)
+    y = cc(g.x().to(dev))
+    _check_forward(y, g.y())
+    (-y.mean()).backward()
+    for i, (p, gr) in enumerate(zip(cc.leaves, g.grads())):
+        got = torch.zeros_like(p) if p.grad is None else p.grad
+        err = (got.double().cpu() - gr).abs().max().item()
+        assert err <= grad_tolerance(gr), f"leaf {i}: grad err {err:.3e} > {grad_tolerance(gr):.3e}"
+
+
+@pytest.mark.parametrize("name", [n for n in FULL if Golden(n).mask()[0] is not None])
+def test_integrate_query_vs_reference(name, dev):
+    from cirkit_b200 import IntegrateQuery
+
+    g = Golden(name)
+    cc = _circuit(g, dev)
+    mask, y_mask = g.mask()
+    with torch.no_grad():
+        y = IntegrateQuery(cc)(g.x().to(dev), integrate_vars=mask.to(dev))
+    _check_forward(y, y_mask)
+
+
+def test_known_answers(dev):
+    """The reference's hand-computed values, tests/symbolic/test_utils.py:411-417 and :497-503."""
+    from cirkit_b200 import IntegrateQuery
+
+    g = Golden("ka_categorical_cpt")
+    cc = _circuit(g, dev)
+    with torch.no_grad():
+        y = cc(g.x().to(dev)).reshape(-1).double().cpu()
+        for bits, val in g.meta["evi"].items():
+            assert math.isclose(y[int(bits, 2)].exp().item(), val, rel_tol=2e-6)
+        assert math.isclose(torch.logsumexp(y, 0).exp().item(), 318.0, rel_tol=2e-6)
+        mask, _ = g.mask()
+        ym = IntegrateQuery(cc)(g.x().to(dev), integrate_vars=mask.to(dev)).reshape(-1).double().cpu()
+        assert math.isclose(ym[int("10110", 2)].exp().item(), 16.845, rel_tol=2e-6)
+    gz = Golden("ka_categorical_cpt_Z")
+    cz = _circuit(gz, dev)
+    with torch.no_grad():
+        z = cz()
+    assert z.shape == gz.y().shape
+    assert math.isclose(z.double().exp().item(), 318.0, rel_tol=2e-6)
+
+    g = Golden("ka_gaussian")
+    cc = _circuit(g, dev)
+    with torch.no_grad():
+        y = cc(g.x().to(dev)).reshape(-1).double().cpu()
+        assert math.isclose(y[0].exp().item(), 3.744904862456293, rel_tol=2e-6)
+        mask, _ = g.mask()
+        ym = IntegrateQuery(cc)(g.x().to(dev), integrate_vars=mask.to(dev)).reshape(-1).double().cpu()
+        assert math.isclose(ym[1].exp().item(), 23.528960785605985, rel_tol=2e-6)
+        assert math.isclose(ym[3].exp().item(), 44.0, rel_tol=2e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in SEEDED if "tucker" not in n])
+def test_benchmark_circuits_vs_reference(name, dev):
+    """Benchmark-size circuits (QuadTree 28x28, K=32/64): outputs and gradient summaries of the
+    real reference (float64) on leaves re-drawn from the fixture seed."""
+    g = Golden(name)
+    cc = _circuit(g, dev)
+    y = cc(g.x().to(dev))
+    _check_forward(y, g.y())
+    (-y.mean()).backward()
+    for i, p in enumerate(cc.leaves):
+        flat = p.grad.double().cpu().reshape(-1)
+        gsum, gabs, gmax = g.z[f"gsum_{i}"]
+        tol = max(5e-7, 1e-4 * gmax)
+        probe = torch.from_numpy(g.z[f"gval_{i}"])
+        idx = torch.from_numpy(g.z[f"gidx_{i}"])
+        assert (flat[idx] - probe).abs().max().item() <= tol, f"leaf {i} probe"
+        assert abs(flat.abs().sum().item() - gabs) <= 1e-3 * gabs + flat.numel() * 1e-9, f"leaf {i} abs-sum"
+
+
+@pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_tucker_k4", "rbt12_gaussian_k5"])
+def test_against_cpu_oracle_fp32(name, dev):
+    """Same seeded inputs, larger ragged batch than the fixture holds: CUDA vs the oracle."""
+    from oracle import OracleCircuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden(name)
+    cc = _circuit(g, dev)
+    oc = OracleCircuit(g.plan, dtype=torch.float64)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, g.leaves(torch.float64)):
+            p.copy_(v)
+    x = make_inputs(g.plan, 131, seed=7)
+    y = cc(x.to(dev))
+    yo = oc(x)
+    _check_forward(y, yo.detach())
+    w = torch.randn(131, 1, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    (y * w.to(dev, torch.float32)).sum().backward()
+    (yo * w).sum().backward()
+    for i, (p, q) in enumerate(zip(cc.leaves, oc.leaves)):
+        gr = torch.zeros_like(q) if q.grad is None else q.grad
+        got = torch.zeros_like(p) if p.grad is None else p.grad
+        err = (got.double().cpu() - gr).abs().max().item()
+        assert err <= grad_tolerance(gr) * 4, f"leaf {i}: {err:.3e}"
+
+
+@pytest.mark.parametrize("batch", [1, 2, 31, 128, 129, 300])
+def test_ragged_batches_and_input_dtypes(batch, dev):
+    g = Golden("qt8_cp_k4")
+    cc = _circuit(g, dev)
+    from oracle.reference_eval import make_inputs
+
+    x = make_inputs(g.plan, batch, seed=batch)
+    with torch.no_grad():
+        y64 = cc(x.to(dev))
+        for dt in (torch.uint8, torch.int32, torch.int16, torch.float32, torch.float64):
+            y = cc(x.to(dt).to(dev))
+            assert torch.equal(y, y64), f"dtype {dt}"
+        # host tensor and extra trailing columns are accepted like in the reference
+        y = cc(torch.cat([x, torch.zeros(batch, 3, dtype=x.dtype)], dim=1))
+        assert torch.equal(y, y64)
+        # row b of a batch does not depend on the other rows
+        y1 = cc(x[:1].to(dev))
+        assert torch.equal(y1[0], y64[0])
+
+
+def test_errors(dev):
+    g = Golden("qt8_cp_k4")
+    cc = _circuit(g, dev)
+    with pytest.raises(ValueError, match="Expected some input"):
+        cc()
+    with pytest.raises(ValueError, match="shape"):
+        cc(torch.zeros(5, dtype=torch.int64, device=dev))
+    with pytest.raises(IndexError):
+        cc(torch.zeros(5, 3, dtype=torch.int64, device=dev))
+    cpu = _circuit(g, torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cpu(g.x())
+
+
+def test_full_size_properties(dev):
+    """BASELINE north-star shape (QuadTree 28x28, K=64, B=2048): size-independent properties."""
+    from cirkit_b200 import IntegrateQuery
+
+    g = Golden("qt28_cp_k64")
+    cc = _circuit(g, dev)
+    B = 2048
+    x = torch.randint(0, 256, (B, 784), generator=torch.Generator().manual_seed(0))
+    x[:8] = g.x()
+    xd = x.to(dev)
+    y = cc(xd)
+    # (1) the fixture rows embedded in a big batch reproduce the reference values
+    _check_forward(y[:8], g.y())
+    # (2) run-to-run determinism of the forward pass
+    assert torch.equal(cc(xd), y)
+    # (3) a normalised circuit integrates to one: log Z = 0 with every variable marginalised
+    with torch.no_grad():
+        z = IntegrateQuery(cc)(xd[:64], integrate_vars=torch.ones(1, 784, dtype=torch.bool))
+    assert z.abs().max().item() < 1e-3
+    # (4) marginalising nothing is the plain forward pass
+    with torch.no_grad():
+        y0 = IntegrateQuery(cc)(xd[:64], integrate_vars=torch.zeros(1, 784, dtype=torch.bool))
+    assert torch.equal(y0, y[:64])
+    # (5) softmax re-parameterisation: every row of d(theta) sums to zero
+    (-y.mean()).backward()
+    for p in cc.leaves:
+        rows = p.grad.double().sum(dim=-1)
+        scale = p.grad.double().abs().sum(dim=-1).clamp_min(1e-30)
+        assert (rows.abs() / scale).max().item() < 1e-3
+    # (6) gradient of the mean log-likelihood is linear in the batch: two halves average
+    grads = [p.grad.clone() for p in cc.leaves]
+    for p in cc.leaves:
+        p.grad = None
+    (-cc(xd[: B // 2]).mean()).backward()
+    g1 = [p.grad.clone() for p in cc.leaves]
+    for p in cc.leaves:
+        p.grad = None
+    (-cc(xd[B // 2 :]).mean()).backward()
+    for ga, gb, p in zip(grads, g1, cc.leaves):
+        half = 0.5 * (gb.double() + p.grad.double())
+        tol = max(5e-7, 1e-4 * ga.abs().max().item())
+        assert (half - ga.double()).abs().max().item() <= tol
+
+
+def test_state_dict_roundtrip(dev):
+    """tests/backend/torch/test_serialization.py:17-32: save -> rebuild -> load -> same scores."""
+    from cirkit_b200 import B200Circuit
+
+    g = Golden("qg8_cp_k4")
+    cc = _circuit(g, dev)
+    sd = {k: v.cpu() for k, v in cc.state_dict().items()}
+    other = B200Circuit(g.plan).to(dev)
+    x = g.x().to(dev)
+    with torch.no_grad():
+        assert not torch.equal(other(x), cc(x))
+        other.load_state_dict(sd)
+        assert torch.equal(other(x), cc(x))

@@ -1,0 +1,53 @@
+"""Plan / layout host logic (no GPU)."""
+import numpy as np
+import pytest
+
+from cirkit_b200.plan import CircuitPlan, build_layout
+from helpers import Golden, golden_names
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_roundtrip_and_layout(name):
+    g = Golden(name)
+    plan = g.plan
+    again = CircuitPlan.load(plan.to_bytes())
+    assert [s.kind for s in again.steps] == [s.kind for s in plan.steps]
+    lay = build_layout(plan)
+    # activation blocks are disjoint, 4-float aligned and cover every step
+    ends = 0
+    for sid, s in enumerate(plan.steps):
+        assert lay.out_off[sid] % 4 == 0 and lay.out_off[sid] >= ends
+        ends = lay.out_off[sid] + s.num_folds * s.num_output_units
+    assert lay.arena_units >= ends
+    # every gathered row points at the start of a producer row
+    for sid, s in enumerate(plan.steps):
+        if s.is_input:
+            continue
+        rows = lay.in_rows[sid].reshape(s.num_folds, s.arity)
+        for f in range(s.num_folds):
+            for h in range(s.arity):
+                p, pf = int(s.in_step[f, h]), int(s.in_fold[f, h])
+                assert rows[f, h] == lay.out_off[p] + pf * plan.steps[p].num_output_units
+    # consumer lists are the transpose of the gathers (+ the circuit outputs)
+    total = sum(len(r) for r in lay.cons_rows)
+    edges = sum(s.num_folds * s.arity for s in plan.steps if not s.is_input)
+    assert total == edges + plan.num_outputs
+
+
+def test_survey_sizes():
+    """A and P of SURVEY §8 for the benchmark shapes."""
+    g = Golden("qt28_cp_k64").plan
+    assert (g.activation_units(), g.parameter_elements()) == (150401, 19259456)
+    assert g.algorithmic_bytes(2048) == 8 * 2048 * 784 + 20 * 150401 * 2048 + 28 * 19259456
+    g = Golden("qt28_cp_k32").plan
+    assert (g.activation_units(), g.parameter_elements()) == (75201, 8026144)
+    g = Golden("qt28_tucker_k64").plan
+    assert (g.activation_units(), g.parameter_elements()) == (100225, 217845760)
+
+
+def test_validate_rejects_bad_gathers():
+    g = Golden("qt8_cp_k4").plan
+    bad = CircuitPlan.load(g.to_bytes())
+    bad.steps[2].in_fold[0, 0] = 10_000
+    with pytest.raises(ValueError):
+        bad.validate()
