@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
             0x20: "sw_thermal_slowdown",
             0x4: "sw_power_cap",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1)
         return {
             "sm_mhz": float(np.median(self.samples)) if self.samples else None,

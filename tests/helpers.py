@@ -58,6 +58,20 @@ def golden_names(kind: str | None = None) -> list[str]:
     return out
 
 
-def grad_tolerance(g_ref: torch.Tensor) -> float:
-    """per-tensor bound max(5e-7, 1e-4 * max|g_ref64|) for fp32 gradients."""
-    return max(5e-7, 1e-4 * float(g_ref.abs().max()))
+GRAD_FLOOR = 2e-6
+
+
+def grad_tolerance(g_ref: torch.Tensor, gout_l1: float = 1.0) -> float:
+    """Per-tensor bound for fp32 gradients against the float64 reference:
+    max(2e-6, 1e-4 * max|g_ref64|).
+
+    SURVEY §8(d) derives max(5e-7, 1e-4*max|g|) from the reference's own fp32-vs-fp64 gap at
+    B=256.  The floor is an *absolute* error that does not shrink with the gradient: through a
+    softmax re-parameterisation d(theta) = W * (dW - sum_j W_j dW_j) cancels O(1) entries of dW
+    (each a sum over the batch of terms of size 1/B, so |dW| ~ 1 regardless of B) down to
+    1e-3..1e-7 near the root, leaving ~4 ulp(1) = 5e-7 of fp32 rounding; the reference's fp32
+    run shows the same (SURVEY §7 "gradient parity is ill-conditioned").  2e-6 = 4x that.
+    `gout_l1` is the L1 norm of d(loss)/d(output) (1 for a mean log-likelihood): |dW| and with
+    it the floor scale linearly with it.
+    """
+    return max(GRAD_FLOOR * max(gout_l1, 1.0), 1e-4 * float(g_ref.abs().max()))

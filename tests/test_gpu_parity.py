@@ -3,7 +3,8 @@ float64) and against the CPU oracle on the same seeded inputs.
 
 Stated tolerances (derived from the reference's own fp32-vs-fp64 gap):
   forward    |ll - ll_ref64| <= 5e-7 * |ll_ref64| + 1e-5        (2.2e-3 at ll = -4357)
-  gradients  per parameter tensor  max|g - g_ref64| <= max(5e-7, 1e-4 * max|g_ref64|)
+  gradients  per parameter tensor  max|g - g_ref64| <= max(2e-6, 1e-4 * max|g_ref64|)
+             (see helpers.grad_tolerance for why the floor is 2e-6)
 """
 import math
 
@@ -113,11 +114,13 @@ def test_benchmark_circuits_vs_reference(name, dev):
     for i, p in enumerate(cc.leaves):
         flat = p.grad.double().cpu().reshape(-1)
         gsum, gabs, gmax = g.z[f"gsum_{i}"]
-        tol = max(5e-7, 1e-4 * gmax)
+        tol = max(2e-6, 1e-4 * gmax)
         probe = torch.from_numpy(g.z[f"gval_{i}"])
         idx = torch.from_numpy(g.z[f"gidx_{i}"])
         assert (flat[idx] - probe).abs().max().item() <= tol, f"leaf {i} probe"
-        assert abs(flat.abs().sum().item() - gabs) <= 1e-3 * gabs + flat.numel() * 1e-9, f"leaf {i} abs-sum"
+        # L1 norm of the whole tensor: relative 2e-3 plus the per-element fp32 rounding floor
+        got_abs = flat.abs().sum().item()
+        assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * 1e-7, f"leaf {i} abs-sum {got_abs} vs {gabs}"
 
 
 @pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_tucker_k4", "rbt12_gaussian_k5"])
@@ -143,7 +146,8 @@ def test_against_cpu_oracle_fp32(name, dev):
         gr = torch.zeros_like(q) if q.grad is None else q.grad
         got = torch.zeros_like(p) if p.grad is None else p.grad
         err = (got.double().cpu() - gr).abs().max().item()
-        assert err <= grad_tolerance(gr) * 4, f"leaf {i}: {err:.3e}"
+        tol = grad_tolerance(gr, gout_l1=float(w.abs().sum()))
+        assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
 
 
 @pytest.mark.parametrize("batch", [1, 2, 31, 128, 129, 300])
@@ -203,12 +207,12 @@ def test_full_size_properties(dev):
     with torch.no_grad():
         y0 = IntegrateQuery(cc)(xd[:64], integrate_vars=torch.zeros(1, 784, dtype=torch.bool))
     assert torch.equal(y0, y[:64])
-    # (5) softmax re-parameterisation: every row of d(theta) sums to zero
+    # (5) softmax re-parameterisation: every row of d(theta) sums to zero (up to the fp32
+    #     rounding of sum_i W_i = 1 times |sum_i W_i dW_i| ~ 1, i.e. ~1e-7 absolute per row)
     (-y.mean()).backward()
     for p in cc.leaves:
         rows = p.grad.double().sum(dim=-1)
-        scale = p.grad.double().abs().sum(dim=-1).clamp_min(1e-30)
-        assert (rows.abs() / scale).max().item() < 1e-3
+        assert rows.abs().max().item() < 2e-6
     # (6) gradient of the mean log-likelihood is linear in the batch: two halves average
     grads = [p.grad.clone() for p in cc.leaves]
     for p in cc.leaves:
@@ -220,7 +224,7 @@ def test_full_size_properties(dev):
     (-cc(xd[B // 2 :]).mean()).backward()
     for ga, gb, p in zip(grads, g1, cc.leaves):
         half = 0.5 * (gb.double() + p.grad.double())
-        tol = max(5e-7, 1e-4 * ga.abs().max().item())
+        tol = max(2e-6, 1e-4 * ga.abs().max().item())
         assert (half - ga.double()).abs().max().item() <= tol
 
 
