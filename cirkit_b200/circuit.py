@@ -39,10 +39,10 @@ class LayerInfo:
 
 
 class B200Circuit(nn.Module):
-    def __init__(self, plan: CircuitPlan, *, seed: int | None = None):
+    def __init__(self, plan: CircuitPlan, *, seed: int | None = None, fuse_tables: bool = True):
         super().__init__()
         self.plan = plan
-        self.runtime = PlanRuntime(plan)
+        self.runtime = PlanRuntime(plan, fuse_tables=fuse_tables)
         self.leaves = nn.ParameterList(
             [nn.Parameter(torch.empty(l.shape, dtype=torch.float32), requires_grad=l.requires_grad)
              for l in plan.leaves]

@@ -594,4 +594,60 @@ int tucker_bwd(const ckb_step_desc_t& d, Ctx& c) {
   return kronecker_bwd_from(d, c, gkron);
 }
 
+// ------------------------------------------------------------------------------------------
+// TABLE_DENSE: the dense block applied to the table rows instead of to every sample.
+// ------------------------------------------------------------------------------------------
+static DenseArgs table_dense_args(const ckb_step_desc_t& d, Ctx& c) {
+  DenseArgs a{};
+  a.W = c.tensors[d.slot[1]];
+  a.in_rows = nullptr;
+  a.arena = c.tensors[d.slot[0]];  // (F, V, Ki): "samples" are the V states
+  a.y = c.tensors[d.slot[2]];      // (F, V, Ko)
+  a.B = d.num_states;
+  a.H = 1;
+  a.Ki = d.k_in;
+  a.Ko = d.k_out;
+  a.concat = 0;
+  a.Kred = d.k_in;
+  return a;
+}
+
+static ckb_step_desc_t as_table(const ckb_step_desc_t& d) {
+  ckb_step_desc_t t = d;
+  t.kind = CKB_STEP_TABLE;
+  t.slot[0] = d.slot[2];
+  t.int_slot = -1;
+  return t;
+}
+
+size_t table_dense_ws(const ckb_step_desc_t& d, int64_t B) {
+  const size_t a = (table_bwd_ws(as_table(d), B) + 255) & ~(size_t)255;
+  return a + run_dense_bwd_ws(d.num_folds, 1, d.k_out, d.k_in, d.num_states) + 256;
+}
+
+int table_dense_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  if (c.maskT != nullptr) {
+    set_error("table_dense: integration masks need the unfused plan");
+    return CKB_ERR_UNSUPPORTED;
+  }
+  if (int rc = run_dense_fwd(table_dense_args(d, c), d.num_folds, c)) return rc;
+  return table_fwd(as_table(d), c);
+}
+
+int table_dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  float* dT2 = c.grads[d.slot[2]];
+  float* dT = c.grads[d.slot[0]];
+  if (dT2 == nullptr || dT == nullptr) {
+    set_error("table_dense_bwd: gradient buffers of T and T2 are required");
+    return CKB_ERR_INVALID;
+  }
+  if (int rc = table_bwd(as_table(d), c)) return rc;  // dT2[f,v,:] = sum of g over samples in state v
+  DenseArgs a = table_dense_args(d, c);
+  a.gs = GradSrc{dT2, nullptr, nullptr, (int64_t)d.num_states};
+  a.gin = dT;
+  const size_t off = (table_bwd_ws(as_table(d), c.B) + 255) & ~(size_t)255;
+  return run_dense_bwd(a, d.num_folds, c.grads[d.slot[1]], c, c.ws + off,
+                       c.ws_bytes > off ? c.ws_bytes - off : 0);
+}
+
 }  // namespace ckb

@@ -64,6 +64,13 @@ static int check_step(const ckb_step_desc_t& d, int idx, int n_slots) {
         return CKB_ERR_INVALID;
       }
       break;
+    case CKB_STEP_TABLE_DENSE:
+      if (d.slot[0] < 0 || d.slot[1] < 0 || d.slot[2] < 0 || d.scope_var == nullptr ||
+          d.num_states <= 0 || d.k_in <= 0) {
+        set_error("step %d: fused table+dense layer needs T, W, T2, a scope and num_states", idx);
+        return CKB_ERR_INVALID;
+      }
+      break;
     case CKB_STEP_CONSTANT:
       if (d.slot[0] < 0) {
         set_error("step %d: constant layer needs a value", idx);
@@ -141,6 +148,7 @@ size_t ckb_plan_workspace_bytes(const ckb_plan_t* plan, int64_t batch) {
       case CKB_STEP_MIXING: w = mixing_bwd_ws(d, batch); break;
       case CKB_STEP_DENSE: w = dense_bwd_ws(d, batch); break;
       case CKB_STEP_TUCKER: w = tucker_ws(d, batch); break;
+      case CKB_STEP_TABLE_DENSE: w = table_dense_ws(d, batch); break;
       default: break;
     }
     need = std::max(need, w + 256);
@@ -194,7 +202,7 @@ static int make_ctx(ckb_plan_t* plan, int32_t s0, int32_t s1, int64_t batch, con
   c.launches = 0;
   for (int i = s0; i < s1; ++i) {
     const int k = plan->steps[i].kind;
-    if ((k == CKB_STEP_TABLE || k == CKB_STEP_GAUSSIAN) && xT == nullptr) {
+    if ((k == CKB_STEP_TABLE || k == CKB_STEP_GAUSSIAN || k == CKB_STEP_TABLE_DENSE) && xT == nullptr) {
       set_error("step %d reads the evidence but xT is NULL", i);
       return CKB_ERR_INVALID;
     }
@@ -225,6 +233,7 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
       case CKB_STEP_HADAMARD: rc = hadamard_fwd(d, c); break;
       case CKB_STEP_KRONECKER: rc = kronecker_fwd(d, c); break;
       case CKB_STEP_TUCKER: rc = tucker_fwd(d, c); break;
+      case CKB_STEP_TABLE_DENSE: rc = table_dense_fwd(d, c); break;
     }
     if (rc != CKB_OK) return rc;
   }
@@ -258,6 +267,7 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
       case CKB_STEP_HADAMARD: rc = hadamard_bwd(d, c); break;
       case CKB_STEP_KRONECKER: rc = kronecker_bwd(d, c); break;
       case CKB_STEP_TUCKER: rc = tucker_bwd(d, c); break;
+      case CKB_STEP_TABLE_DENSE: rc = table_dense_bwd(d, c); break;
     }
     if (rc != CKB_OK) return rc;
   }

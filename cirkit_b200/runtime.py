@@ -1,6 +1,6 @@
 """Device runtime: binds a :class:`CircuitPlan` to the CUDA library and to autograd.
 
-One `PlanRuntime` per circuit; per device it owns the index tables, the C plan handle, the
+One `PlanRuntime` per circuit; per device it owns the index tables, the C plan handles, the
 effective-parameter buffers and a scratch workspace.  A forward pass is ONE call into the library
 (`ckb_plan_forward`: parameter ops + every folded layer), a backward pass is one more
 (`ckb_plan_backward`), wrapped in a single `torch.autograd.Function` whose differentiable inputs
@@ -9,13 +9,21 @@ are the parameter tensors.  PyTorch is used for memory, streams and autograd plu
 What this replaces in the reference: `TorchDiAcyclicGraph.evaluate`
 (cirkit/backend/torch/graph/modules.py:303-335), `LayerAddressBook.lookup`
 (circuits.py:30-71), every `TorchLayer.forward` on the path and the autograd graph they record.
+
+Execution plans.  The same circuit is lowered to two step lists:
+  * "plain": one kernel group per folded layer, exactly the reference's layer sequence;
+  * "fused": an input table layer (Categorical / Embedding) that is consumed fold-by-fold by an
+    arity-1 sum layer is merged with it into one TABLE_DENSE step: the sum layer is applied to
+    the V rows of the table once per step instead of to every sample, and samples only gather
+    rows of the resulting table.  Used when the batch is at least V/2 and no integration mask is
+    given; values are the same as the plain plan's up to fp32 rounding.
 """
 
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
-from typing import Any, Sequence
+from dataclasses import dataclass, field
+from typing import Sequence
 
 import numpy as np
 import torch
@@ -32,6 +40,7 @@ _DTYPES = {
     torch.float32: L.F32,
     torch.float64: L.F64,
 }
+STEP_TABLE_DENSE = 8
 
 
 def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
@@ -148,16 +157,55 @@ _PARAM_ORDER = {
 }
 
 
+@dataclass
+class ExecStep:
+    """One entry of an execution plan (what a ckb_step_desc_t is built from)."""
+
+    kind: int  # ckb_step_kind
+    label: str
+    sids: tuple  # plan steps it covers
+    out_sid: int  # plan step whose arena block / consumer lists it uses
+    slots: list = field(default_factory=list)
+    scratch: tuple | None = None  # (slot, shape) of a runtime-owned buffer (TABLE_DENSE: T2)
+
+
+def find_table_dense_pairs(plan: CircuitPlan) -> dict[int, int]:
+    """input step -> sum step, for every table layer whose only consumer is an arity-1 sum layer
+    reading it fold by fold (e.g. the Categorical -> Sum pair every region-graph circuit starts
+    with, `cirkit/templates/region_graph/graph.py:344-588`)."""
+    consumers: dict[int, set] = {i: set() for i in range(len(plan.steps))}
+    for cid, c in enumerate(plan.steps):
+        if not c.is_input:
+            for p in np.unique(c.in_step):
+                consumers[int(p)].add(cid)
+    outs = set(int(s) for s in plan.out_step)
+    pairs = {}
+    for sid, s in enumerate(plan.steps):
+        if s.kind not in ("categorical", "embedding") or sid in outs or len(consumers[sid]) != 1:
+            continue
+        (cid,) = consumers[sid]
+        c = plan.steps[cid]
+        if c.kind not in ("sum", "cpt") or c.arity != 1 or c.num_folds != s.num_folds:
+            continue
+        if not np.array_equal(c.in_fold.reshape(-1), np.arange(s.num_folds)):
+            continue
+        if "weight" not in c.params or max(c.num_input_units, c.num_output_units) > 128:
+            continue
+        pairs[sid] = cid
+    return pairs
+
+
 class _DeviceState:
     """Everything that lives on one GPU for one plan."""
 
     def __init__(self, rt: "PlanRuntime", device: torch.device):
         self.device = device
+        self.rt = rt
+        self.lib = L.load()
+        self.keep: list[Tensor] = []  # index tables referenced by the C plans
         lay, plan = rt.layout, rt.plan
-        lib = L.load()
-        self.keep: list[Tensor] = []  # index tables referenced by the C plan
 
-        def up(a: np.ndarray, dtype) -> int:
+        def up(a, dtype) -> int:
             if a is None or a.size == 0:
                 t = torch.zeros(1, dtype=dtype, device=device)
             else:
@@ -165,44 +213,25 @@ class _DeviceState:
             self.keep.append(t)
             return t.data_ptr()
 
-        descs = (L.StepDesc * len(plan.steps))()
+        self.tables = []
         for sid, s in enumerate(plan.steps):
-            d = descs[sid]
-            d.kind = _KIND[s.kind]
-            d.num_folds, d.arity = s.num_folds, s.arity
-            d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
-            d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
-            d.num_states = int(s.config.get("num_categories", s.config.get("num_states", 0)))
-            d.gin_h = int(lay.gin_h[sid])
-            d.out_off = int(lay.out_off[sid])
-            d.gin_off = int(lay.gin_off[sid])
-            d.in_rows = up(lay.in_rows[sid], torch.int64) if lay.in_rows[sid] is not None else None
-            d.scope_var = up(s.scope_idx, torch.int32) if s.scope_idx is not None else None
-            d.cons_ptr = up(lay.cons_ptr[sid], torch.int32)
-            d.cons_rows = up(lay.cons_rows[sid], torch.int64)
-            slots = rt.step_slots[sid]
-            for i in range(4):
-                d.slot[i] = slots[i] if i < len(slots) else -1
-            d.int_slot = rt.int_slots.get(sid, -1)
-        ops = (L.ParamOp * max(1, len(rt.native_ops)))()
-        for i, (b, (kind, rows, cols, aux, a, bb)) in enumerate(rt.native_ops):
-            ops[i].kind, ops[i].src, ops[i].dst = kind, b.src_slot, b.dst_slot
-            ops[i].rows, ops[i].cols, ops[i].aux, ops[i].a, ops[i].b = rows, cols, aux, a, bb
-        handle = C.c_void_p()
-        with torch.cuda.device(device):
-            L.check(
-                lib.ckb_plan_create(descs, len(plan.steps), ops, len(rt.native_ops), rt.n_slots,
-                                    C.byref(handle)),
-                "ckb_plan_create",
-            )
-        self.handle = handle
-        self.lib = lib
+            self.tables.append({
+                "in_rows": up(lay.in_rows[sid], torch.int64) if lay.in_rows[sid] is not None else None,
+                "scope_var": up(s.scope_idx, torch.int32) if s.scope_idx is not None else None,
+                "cons_ptr": up(lay.cons_ptr[sid], torch.int32),
+                "cons_rows": up(lay.cons_rows[sid], torch.int64),
+            })
+        self.handles: dict[str, C.c_void_p] = {}
         # effective parameters and their gradients (runtime-owned, persistent)
         self.eff: dict[int, Tensor] = {}
         self.eff_grad: dict[int, Tensor] = {}
         for b in rt.bindings:
             if b.native is not None:
                 self.eff[b.dst_slot] = torch.empty(b.eff_shape, dtype=torch.float32, device=device)
+        for es in rt.exec_plans["fused"]:
+            if es.scratch is not None:
+                slot, shape = es.scratch
+                self.eff[slot] = torch.empty(shape, dtype=torch.float32, device=device)
         self.int_buf = {
             sid: torch.zeros(plan.steps[sid].num_folds, plan.steps[sid].num_output_units,
                              dtype=torch.float32, device=device)
@@ -210,21 +239,68 @@ class _DeviceState:
         }
         self.ws: Tensor | None = None
 
-    def workspace(self, batch: int) -> Tensor:
-        need = int(self.lib.ckb_plan_workspace_bytes(self.handle, batch))
+    def grad_buffer(self, slot: int) -> Tensor:
+        g = self.eff_grad.get(slot)
+        if g is None:
+            g = self.eff_grad[slot] = torch.empty_like(self.eff[slot])
+        return g
+
+    def handle(self, which: str) -> C.c_void_p:
+        h = self.handles.get(which)
+        if h is not None:
+            return h
+        rt, lay, plan = self.rt, self.rt.layout, self.rt.plan
+        steps = rt.exec_plans[which]
+        descs = (L.StepDesc * len(steps))()
+        for i, es in enumerate(steps):
+            s = plan.steps[es.out_sid]
+            first = plan.steps[es.sids[0]]
+            t_out, t_first = self.tables[es.out_sid], self.tables[es.sids[0]]
+            d = descs[i]
+            d.kind = es.kind
+            d.num_folds, d.arity = s.num_folds, s.arity
+            d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
+            d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
+            d.num_states = int(first.config.get("num_categories", first.config.get("num_states", 0)))
+            d.gin_h = int(lay.gin_h[es.out_sid])
+            d.out_off = int(lay.out_off[es.out_sid])
+            d.gin_off = int(lay.gin_off[es.out_sid])
+            d.in_rows = t_out["in_rows"] if es.kind != STEP_TABLE_DENSE else None
+            d.scope_var = t_first["scope_var"]
+            d.cons_ptr = t_out["cons_ptr"]
+            d.cons_rows = t_out["cons_rows"]
+            for j in range(4):
+                d.slot[j] = es.slots[j] if j < len(es.slots) else -1
+            d.int_slot = rt.int_slots.get(es.sids[0], -1) if es.kind != STEP_TABLE_DENSE else -1
+        ops = (L.ParamOp * max(1, len(rt.native_ops)))()
+        for i, (b, (kind, rows, cols, aux, a, bb)) in enumerate(rt.native_ops):
+            ops[i].kind, ops[i].src, ops[i].dst = kind, b.src_slot, b.dst_slot
+            ops[i].rows, ops[i].cols, ops[i].aux, ops[i].a, ops[i].b = rows, cols, aux, a, bb
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(
+                self.lib.ckb_plan_create(descs, len(steps), ops, len(rt.native_ops), rt.n_slots, C.byref(h)),
+                "ckb_plan_create",
+            )
+        self.handles[which] = h
+        return h
+
+    def workspace(self, which: str, batch: int) -> Tensor:
+        need = int(self.lib.ckb_plan_workspace_bytes(self.handle(which), batch))
         if self.ws is None or self.ws.numel() < need:
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self.ws
 
     def __del__(self):  # pragma: no cover
         try:
-            self.lib.ckb_plan_destroy(self.handle)
+            for h in self.handles.values():
+                self.lib.ckb_plan_destroy(h)
         except Exception:
             pass
 
 
 class PlanRuntime:
-    def __init__(self, plan: CircuitPlan):
+    def __init__(self, plan: CircuitPlan, *, fuse_tables: bool = True):
         plan.validate()
         if plan.semiring != "lse-sum":
             raise NotImplementedError("only the 'lse-sum' semiring has a CUDA path")
@@ -259,11 +335,47 @@ class PlanRuntime:
                 n += 1
             if s.kind == "gaussian" and "log_partition" in s.params:
                 self.int_slots[sid] = slots[2]
+        # execution plans
+        plain = [
+            ExecStep(_KIND[s.kind], f"{sid}:{s.kind}", (sid,), sid, list(self.step_slots[sid]))
+            for sid, s in enumerate(plan.steps)
+        ]
+        fused: list[ExecStep] = []
+        pairs = find_table_dense_pairs(plan) if fuse_tables else {}
+        # the fused step back-propagates into runtime-owned table buffers: both parameters must
+        # come out of a fused parameter op (true for every softmax/log-softmax parameterisation)
+        def owned(sid: int) -> bool:
+            return all(b.native is not None for b in self.bindings if b.sid == sid)
+
+        self.table_pairs = {a: c for a, c in pairs.items() if owned(a)}
+        absorbed = set(self.table_pairs.values())
+        self.table_states = 0
+        for sid, s in enumerate(plan.steps):
+            if sid in absorbed:
+                continue
+            if sid in self.table_pairs:
+                cid = self.table_pairs[sid]
+                c = plan.steps[cid]
+                V = int(s.config.get("num_categories", s.config.get("num_states", 0)))
+                self.table_states = max(self.table_states, V)
+                t2 = n
+                n += 1
+                fused.append(ExecStep(STEP_TABLE_DENSE, f"{sid}+{cid}:table_dense", (sid, cid), cid,
+                                      [self.step_slots[sid][0], self.step_slots[cid][0], t2],
+                                      scratch=(t2, (c.num_folds, V, c.num_output_units))))
+            else:
+                fused.append(plain[sid])
+        self.exec_plans = {"plain": plain, "fused": fused}
         self.n_slots = n
         self.native_ops = [(b, b.native) for b in self.bindings if b.native is not None]
         self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
         self._states: dict[torch.device, _DeviceState] = {}
         self.last_launches = 0
+
+    def choose_plan(self, batch: int, masked: bool) -> str:
+        if self.table_pairs and not masked and 2 * batch >= self.table_states:
+            return "fused"
+        return "plain"
 
     # ------------------------------------------------------------------ device state
     def state(self, device: torch.device) -> _DeviceState:
@@ -333,6 +445,98 @@ class PlanRuntime:
         return _PlanFn.apply(self, st, x, integrate_mask, *P)
 
 
+@dataclass
+class _Call:
+    """Device-side arguments shared by the forward and the backward library calls."""
+
+    which: str
+    B: int
+    xT: Tensor | None
+    x_is_float: int
+    maskT: Tensor | None
+    mask_rows: int
+    tensors: object
+    n_steps: int
+
+
+def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Call:
+    lib, dev, plan = st.lib, st.device, rt.plan
+    xT, x_is_float, B = None, 0, 1
+    if x is not None:
+        B = int(x.shape[0])
+        if B == 0:
+            raise ValueError("empty batch")
+        if x.dtype not in _DTYPES:
+            x = x.to(torch.float32 if x.is_floating_point() else torch.int64)
+        xd = x.detach()
+        if xd.device != dev:
+            xd = xd.to(dev, non_blocking=True)
+        if xd.stride(1) != 1:
+            xd = xd.contiguous()
+        x_is_float = 1 if xd.is_floating_point() else 0
+        D = plan.num_variables
+        xT = torch.empty((max(D, 1), B), dtype=torch.float32 if x_is_float else torch.int32, device=dev)
+        if rt.reads_evidence:
+            L.check(
+                lib.ckb_transpose_input(xd.data_ptr(), _DTYPES[xd.dtype], B, D, xd.stride(0),
+                                        xT.data_ptr(), stream),
+                "ckb_transpose_input",
+            )
+    maskT, mask_rows = None, 0
+    if mask is not None:
+        m = mask.to(device=dev, dtype=torch.uint8)
+        if m.ndim == 1:
+            m = m.unsqueeze(0)
+        if m.shape[0] not in (1, B) or m.shape[1] < plan.num_variables:
+            raise ValueError(f"integration mask of shape {tuple(mask.shape)} does not match x")
+        m = m[:, : plan.num_variables].contiguous()
+        mask_rows = int(m.shape[0])
+        maskT = torch.empty((plan.num_variables, mask_rows), dtype=torch.uint8, device=dev)
+        L.check(
+            lib.ckb_transpose_mask(m.data_ptr(), mask_rows, plan.num_variables, maskT.data_ptr(), stream),
+            "ckb_transpose_mask",
+        )
+        # values an integrated variable contributes for unnormalised categoricals
+        for sid, buf in st.int_buf.items():
+            i = next(j for j, bb in enumerate(rt.bindings) if bb.sid == sid and bb.name == "logits")
+            if rt.bindings[i].native[0] == L.POP_LOG_SOFTMAX_T:
+                buf.zero_()  # normalised logits integrate to log 1
+            else:
+                buf.copy_(torch.logsumexp(P[i].detach(), dim=2))
+    which = rt.choose_plan(B, mask is not None)
+    tensors = (C.c_void_p * rt.n_slots)()
+    for b, p in zip(rt.bindings, P):
+        tensors[b.src_slot] = p.data_ptr()
+    for slot, buf in st.eff.items():
+        tensors[slot] = buf.data_ptr()
+    for sid, slot in rt.int_slots.items():
+        if sid in st.int_buf:
+            tensors[slot] = st.int_buf[sid].data_ptr()
+    return _Call(which, B, xT, x_is_float, maskT, mask_rows, tensors, len(rt.exec_plans[which]))
+
+
+def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tuple[object, list]:
+    grads = (C.c_void_p * rt.n_slots)()
+    outs: list[Tensor | None] = []
+    for b, p, nd in zip(rt.bindings, P, need):
+        if not nd:
+            outs.append(None)
+            continue
+        g = torch.empty_like(p)
+        outs.append(g)
+        grads[b.src_slot] = g.data_ptr()
+        if b.native is not None:
+            grads[b.dst_slot] = st.grad_buffer(b.dst_slot).data_ptr()
+    for es in rt.exec_plans[call.which]:
+        if es.scratch is not None:
+            grads[es.scratch[0]] = st.grad_buffer(es.scratch[0]).data_ptr()
+            # the fused step back-propagates through the table: its gradient buffer must exist
+            t_slot = es.slots[0]
+            if not grads[t_slot]:
+                grads[t_slot] = st.grad_buffer(t_slot).data_ptr()
+    return grads, outs
+
+
 class _PlanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rt: PlanRuntime, st: _DeviceState, x, mask, *P):
@@ -340,71 +544,20 @@ class _PlanFn(torch.autograd.Function):
         lay, plan = rt.layout, rt.plan
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            xT = None
-            x_is_float = 0
-            B = 1
-            if x is not None:
-                B = int(x.shape[0])
-                if B == 0:
-                    raise ValueError("empty batch")
-                if x.dtype not in _DTYPES:
-                    x = x.to(torch.float32 if x.is_floating_point() else torch.int64)
-                xd = x.detach()
-                if xd.device != dev:
-                    xd = xd.to(dev, non_blocking=True)
-                if xd.stride(1) != 1:
-                    xd = xd.contiguous()
-                x_is_float = 1 if xd.is_floating_point() else 0
-                D = plan.num_variables
-                xT = torch.empty((max(D, 1), B), dtype=torch.float32 if x_is_float else torch.int32, device=dev)
-                if rt.reads_evidence:
-                    L.check(
-                        lib.ckb_transpose_input(xd.data_ptr(), _DTYPES[xd.dtype], B, D, xd.stride(0),
-                                                xT.data_ptr(), stream),
-                        "ckb_transpose_input",
-                    )
-            maskT, mask_rows = None, 0
-            if mask is not None:
-                m = mask.to(device=dev, dtype=torch.uint8).contiguous()
-                if m.ndim == 1:
-                    m = m.unsqueeze(0)
-                if m.shape[0] not in (1, B) or m.shape[1] < plan.num_variables:
-                    raise ValueError(f"integration mask of shape {tuple(mask.shape)} does not match x")
-                mask_rows = int(m.shape[0])
-                maskT = torch.empty((plan.num_variables, mask_rows), dtype=torch.uint8, device=dev)
-                L.check(
-                    lib.ckb_transpose_mask(m.data_ptr(), mask_rows, plan.num_variables, maskT.data_ptr(), stream)
-                    if m.shape[1] == plan.num_variables
-                    else lib.ckb_transpose_mask(m[:, : plan.num_variables].contiguous().data_ptr(), mask_rows,
-                                                plan.num_variables, maskT.data_ptr(), stream),
-                    "ckb_transpose_mask",
-                )
-                # values an integrated variable contributes for unnormalised categoricals
-                for sid, buf in st.int_buf.items():
-                    i = next(j for j, bb in enumerate(rt.bindings) if bb.sid == sid and bb.name == "logits")
-                    if rt.bindings[i].native[0] == L.POP_LOG_SOFTMAX_T:
-                        buf.zero_()  # normalised logits integrate to log 1
-                    else:
-                        buf.copy_(torch.logsumexp(P[i].detach(), dim=2))
-            tensors = (C.c_void_p * rt.n_slots)()
-            for b, p in zip(rt.bindings, P):
-                tensors[b.src_slot] = p.data_ptr()
-                if b.native is not None:
-                    tensors[b.dst_slot] = st.eff[b.dst_slot].data_ptr()
-            for sid, slot in rt.int_slots.items():
-                if sid in st.int_buf:
-                    tensors[slot] = st.int_buf[sid].data_ptr()
+            call = _prepare_call(rt, st, x, mask, P, stream)
+            B = call.B
             arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
-            ws = st.workspace(B)
+            ws = st.workspace(call.which, B)
             L.check(
                 lib.ckb_plan_forward(
-                    st.handle, 0, len(plan.steps), B,
-                    xT.data_ptr() if xT is not None else None, x_is_float,
-                    maskT.data_ptr() if maskT is not None else None, mask_rows,
-                    tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
+                    st.handle(call.which), 0, call.n_steps, B,
+                    call.xT.data_ptr() if call.xT is not None else None, call.x_is_float,
+                    call.maskT.data_ptr() if call.maskT is not None else None, call.mask_rows,
+                    call.tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
                 "ckb_plan_forward",
             )
-            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle)) + (1 if xT is not None else 0)
+            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which))) + (
+                1 if call.xT is not None else 0)
             K = plan.num_output_units
             rows = lay.out_rows
             if len(rows) == 1:
@@ -412,19 +565,18 @@ class _PlanFn(torch.autograd.Function):
                 out = arena[B * r : B * r + B * K].view(B, 1, K).clone()
             else:
                 out = torch.stack([arena[B * int(r) : B * int(r) + B * K].view(B, K) for r in rows], dim=1)
-        ctx.rt, ctx.st, ctx.B = rt, st, B
-        ctx.x_is_float, ctx.mask_rows = x_is_float, mask_rows
-        ctx.xT, ctx.maskT, ctx.arena = xT, maskT, arena
+        ctx.rt, ctx.st, ctx.call = rt, st, call
+        ctx.arena = arena
         ctx.P = P
-        ctx.tensors = tensors
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
-        rt, st, B = ctx.rt, ctx.st, ctx.B
+        rt, st, call = ctx.rt, ctx.st, ctx.call
         lib, dev = st.lib, st.device
         lay, plan = rt.layout, rt.plan
+        B = call.B
         need = ctx.needs_input_grad[4:]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -432,48 +584,41 @@ class _PlanFn(torch.autograd.Function):
             O, K = plan.num_outputs, plan.num_output_units
             go = garena[B * lay.out_goff : B * lay.out_goff + O * B * K].view(O, B, K)
             go.copy_(gout.to(torch.float32).transpose(0, 1))
-            grads = (C.c_void_p * rt.n_slots)()
-            outs: list[Tensor | None] = []
-            for b, p, nd in zip(rt.bindings, ctx.P, need):
-                if not nd:
-                    outs.append(None)
-                    continue
-                g = torch.empty_like(p)
-                outs.append(g)
-                grads[b.src_slot] = g.data_ptr()
-                if b.native is not None:
-                    eg = st.eff_grad.get(b.dst_slot)
-                    if eg is None:
-                        eg = st.eff_grad[b.dst_slot] = torch.empty_like(st.eff[b.dst_slot])
-                    grads[b.dst_slot] = eg.data_ptr()
-            ws = st.workspace(B)
+            grads, outs = _grad_table(rt, st, call, ctx.P, need)
+            ws = st.workspace(call.which, B)
             L.check(
                 lib.ckb_plan_backward(
-                    st.handle, 0, len(plan.steps), B,
-                    ctx.xT.data_ptr() if ctx.xT is not None else None, ctx.x_is_float,
-                    ctx.maskT.data_ptr() if ctx.maskT is not None else None, ctx.mask_rows,
-                    ctx.tensors, grads, ctx.arena.data_ptr(), garena.data_ptr(),
+                    st.handle(call.which), 0, call.n_steps, B,
+                    call.xT.data_ptr() if call.xT is not None else None, call.x_is_float,
+                    call.maskT.data_ptr() if call.maskT is not None else None, call.mask_rows,
+                    call.tensors, grads, ctx.arena.data_ptr(), garena.data_ptr(),
                     ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
                 "ckb_plan_backward",
             )
-            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle))
+            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which)))
         ctx.arena = None
         return (None, None, None, None, *outs)
 
 
 # ----------------------------------------------------------------------------- per-step timing
-def step_algorithmic_bytes(plan: CircuitPlan, sid: int, batch: int) -> tuple[int, int]:
-    """Algorithmic HBM bytes of the forward and of the backward launch of one step: every tensor
-    the step must read or write counted once, fp32 (see DESIGN.md "Kernels")."""
-    s = plan.steps[sid]
+def _exec_step_bytes(rt: PlanRuntime, es: ExecStep, batch: int) -> tuple[int, int]:
+    """Algorithmic HBM bytes of the forward and of the backward launches of one execution step:
+    every tensor the step must read or write counted once, fp32 (see DESIGN.md "Kernels")."""
+    plan = rt.plan
+    s = plan.steps[es.out_sid]
     F, H, Ki, Ko, B = s.num_folds, s.arity, s.num_input_units, s.num_output_units, batch
     out = F * B * Ko * 4
+    p = sum(int(np.prod(q.shape)) for sid in es.sids for q in plan.steps[sid].params.values()) * 4
+    if es.kind == STEP_TABLE_DENSE:
+        first = plan.steps[es.sids[0]]
+        V = int(first.config.get("num_categories", first.config.get("num_states", 0)))
+        t2 = F * V * Ko * 4
+        x = B * F * 4
+        return p + 2 * t2 + x + out, out + x + 3 * t2 + 2 * p
     if s.is_input:
-        p = sum(int(np.prod(q.shape)) for q in s.params.values()) * 4
         x = B * F * 4
         return out + x + p, out + x + p  # fwd: table + x -> y ; bwd: g + x -> dT
     inp = F * H * B * Ki * 4
-    p = sum(int(np.prod(q.shape)) for q in s.params.values()) * 4
     hg = 1 if s.kind in ("cpt", "hadamard") else H
     gin = F * hg * B * Ki * 4
     fwd = inp + p + out
@@ -482,81 +627,65 @@ def step_algorithmic_bytes(plan: CircuitPlan, sid: int, batch: int) -> tuple[int
 
 
 def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: int = 3) -> list[dict]:
-    """Times every step's forward and backward launch group in isolation with CUDA events on the
-    launching stream (bench.py's roofline leg).  Returns one dict per step."""
+    """Times every execution step's forward and backward launch group in isolation with CUDA
+    events on the launching stream (bench.py's roofline leg).  Returns one dict per step."""
     P = rt.parameter_tensors(leaves, None)
     st = rt.state(P[0].device)
     lib, dev, plan, lay = st.lib, st.device, rt.plan, rt.layout
-    S = len(plan.steps)
     with torch.cuda.device(dev), torch.no_grad():
         stream = torch.cuda.current_stream(dev).cuda_stream
-        B = int(x.shape[0])
-        xd = x.to(dev)
-        x_is_float = 1 if xd.is_floating_point() else 0
-        xT = torch.empty((plan.num_variables, B), dtype=torch.float32 if x_is_float else torch.int32, device=dev)
-        L.check(lib.ckb_transpose_input(xd.data_ptr(), _DTYPES[xd.dtype], B, plan.num_variables,
-                                        xd.stride(0), xT.data_ptr(), stream), "ckb_transpose_input")
-        tensors = (C.c_void_p * rt.n_slots)()
-        grads = (C.c_void_p * rt.n_slots)()
-        keep = []
-        for b, p in zip(rt.bindings, P):
-            tensors[b.src_slot] = p.data_ptr()
-            g = torch.empty_like(p)
-            keep.append(g)
-            grads[b.src_slot] = g.data_ptr()
-            if b.native is not None:
-                tensors[b.dst_slot] = st.eff[b.dst_slot].data_ptr()
-                eg = st.eff_grad.get(b.dst_slot)
-                if eg is None:
-                    eg = st.eff_grad[b.dst_slot] = torch.empty_like(st.eff[b.dst_slot])
-                grads[b.dst_slot] = eg.data_ptr()
+        call = _prepare_call(rt, st, x, None, P, stream)
+        B, S = call.B, call.n_steps
+        steps = rt.exec_plans[call.which]
+        handle = st.handle(call.which)
+        grads, keep = _grad_table(rt, st, call, P, [True] * len(P))
         arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
         garena = torch.zeros(B * lay.garena_units, dtype=torch.float32, device=dev)
         O, K = plan.num_outputs, plan.num_output_units
         garena[B * lay.out_goff : B * lay.out_goff + O * B * K] = -1.0 / B
-        ws = st.workspace(B)
+        ws = st.workspace(call.which, B)
+        xp = call.xT.data_ptr() if call.xT is not None else None
 
         def fwd(s0, s1, flags):
-            L.check(lib.ckb_plan_forward(st.handle, s0, s1, B, xT.data_ptr(), x_is_float, None, 0,
-                                         tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), flags,
-                                         stream), "ckb_plan_forward")
-            return int(lib.ckb_plan_last_launches(st.handle))
+            L.check(lib.ckb_plan_forward(handle, s0, s1, B, xp, call.x_is_float, None, 0,
+                                         call.tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         flags, stream), "ckb_plan_forward")
+            return int(lib.ckb_plan_last_launches(handle))
 
         def bwd(s0, s1, flags):
-            L.check(lib.ckb_plan_backward(st.handle, s0, s1, B, xT.data_ptr(), x_is_float, None, 0,
-                                          tensors, grads, arena.data_ptr(), garena.data_ptr(),
+            L.check(lib.ckb_plan_backward(handle, s0, s1, B, xp, call.x_is_float, None, 0,
+                                          call.tensors, grads, arena.data_ptr(), garena.data_ptr(),
                                           ws.data_ptr(), ws.numel(), flags, stream), "ckb_plan_backward")
-            return int(lib.ckb_plan_last_launches(st.handle))
+            return int(lib.ckb_plan_last_launches(handle))
 
         def timed(fn, *a):
-            best, n = [], 0
+            ts, n = [], 0
             for _ in range(iters):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 n = fn(*a)
                 e1.record()
                 e1.synchronize()
-                best.append(e0.elapsed_time(e1))
-            return float(np.mean(best)), n
+                ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts)), n
 
         fwd(0, S, L.RUN_PARAM_OPS)  # warm everything once
         bwd(0, S, L.RUN_PARAM_OPS)
         res = []
         t, n = timed(fwd, 0, 0, L.RUN_PARAM_OPS)
-        res.append({"step": -1, "kind": "param_ops", "fwd_ms": t, "fwd_launches": n})
-        for sid in range(S):
-            t, n = timed(fwd, sid, sid + 1, 0)
-            fb, bb = step_algorithmic_bytes(plan, sid, B)
-            res.append({"step": sid, "kind": plan.steps[sid].kind, "F": plan.steps[sid].num_folds,
+        pbytes = sum(int(np.prod(l.shape)) for l in plan.leaves) * 4
+        res.append({"step": "param_ops", "kind": "param_ops", "fwd_ms": t, "fwd_launches": n,
+                    "fwd_bytes": 2 * pbytes, "bwd_bytes": 3 * pbytes})
+        for i, es in enumerate(steps):
+            t, n = timed(fwd, i, i + 1, 0)
+            fb, bb = _exec_step_bytes(rt, es, B)
+            res.append({"step": es.label, "kind": es.label.split(":")[1], "F": plan.steps[es.out_sid].num_folds,
                         "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb})
-        for sid in reversed(range(S)):
-            t, n = timed(bwd, sid, sid + 1, 0)
-            res[sid + 1]["bwd_ms"] = t
-            res[sid + 1]["bwd_launches"] = n
+        for i in reversed(range(S)):
+            t, n = timed(bwd, i, i + 1, 0)
+            res[i + 1]["bwd_ms"] = t
+            res[i + 1]["bwd_launches"] = n
         t, n = timed(bwd, 0, 0, L.RUN_PARAM_OPS)
         res[0]["bwd_ms"] = t
         res[0]["bwd_launches"] = n
-        pbytes = sum(int(np.prod(l.shape)) for l in plan.leaves) * 4
-        res[0]["fwd_bytes"] = 2 * pbytes
-        res[0]["bwd_bytes"] = 3 * pbytes
     return res

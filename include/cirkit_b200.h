@@ -55,7 +55,13 @@ typedef enum {
                              (parameters/nodes.py:847-862), computed on the (F,K,H) weights     */
   CKB_STEP_HADAMARD = 5,  /* layers/inner.py:126-127                                            */
   CKB_STEP_KRONECKER = 6, /* layers/inner.py:178-187 (arity 2)                                  */
-  CKB_STEP_TUCKER = 7     /* layers/optimized.py:89-103 (arity 2)                               */
+  CKB_STEP_TUCKER = 7,    /* layers/optimized.py:89-103 (arity 2)                               */
+  CKB_STEP_TABLE_DENSE = 8 /* a TABLE layer consumed fold-by-fold by an arity-1 DENSE layer, fused:
+                             the dense block is applied to the V rows of the (F,V,Ki) table once
+                             per step (batch-independent), giving a (F,V,Ko) table T2, and the
+                             batch only gathers rows of T2.  Same values as running
+                             layers/input.py:399-412 then layers/inner.py:266-273 per sample.
+                             slots {T, W, T2}; out_off / consumers are those of the DENSE layer. */
 } ckb_step_kind;
 
 #define CKB_DENSE_CONCAT 1 /* reduce over the concatenation of the H inputs instead of their sum */

@@ -170,6 +170,32 @@ def test_ragged_batches_and_input_dtypes(batch, dev):
         assert torch.equal(y1[0], y64[0])
 
 
+@pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_cp_k6_embedding", "pd6_cp_k3_unopt"])
+def test_table_fusion_matches_layer_by_layer_plan(name, dev):
+    """The fused input-table plan (TABLE_DENSE) against the plain one-kernel-per-layer plan."""
+    from cirkit_b200 import B200Circuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden(name)
+    x = make_inputs(g.plan, 300, seed=5).to(dev)
+    res = []
+    for fuse in (True, False):
+        cc = B200Circuit(g.plan, fuse_tables=fuse)
+        with torch.no_grad():
+            for p, v in zip(cc.leaves, g.leaves(torch.float32)):
+                p.copy_(v)
+        cc = cc.to(dev)
+        # circuits whose input layer is read 1:1 by an arity-1 sum layer get the fused step
+        assert (cc.runtime.choose_plan(300, False) == "fused") == (fuse and bool(cc.runtime.table_pairs))
+        y = cc(x)
+        (-y.mean()).backward()
+        res.append((y.detach(), [p.grad for p in cc.leaves]))
+    (yf, gf), (yp, gp) = res
+    assert (yf - yp).abs().max().item() <= 5e-7 * yp.abs().max().item() + 1e-5
+    for a, b in zip(gf, gp):
+        assert (a - b).abs().max().item() <= max(2e-6, 1e-4 * b.abs().max().item())
+
+
 def test_errors(dev):
     g = Golden("qt8_cp_k4")
     cc = _circuit(g, dev)
