@@ -30,7 +30,9 @@ EXPORTS = (
     "ckb_plan_forward",
     "ckb_plan_backward",
     "ckb_plan_last_launches",
+    "ckb_set_option",
 )
+OPT_TENSOR_CORES = 0
 
 
 class LibraryNotBuiltError(RuntimeError):
@@ -111,6 +113,8 @@ def load():
     lib.ckb_plan_backward.restype = C.c_int
     lib.ckb_plan_last_launches.argtypes = [vp]
     lib.ckb_plan_last_launches.restype = i64
+    lib.ckb_set_option.argtypes = [i32, i32]
+    lib.ckb_set_option.restype = C.c_int
     _lib = lib
     return lib
 

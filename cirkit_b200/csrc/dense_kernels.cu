@@ -8,49 +8,9 @@
 // shared memory once, every warp turns SW samples into exp-shifted rows in shared memory and then
 // runs a register-tiled matrix-vector product against the staged weights, so an activation row
 // is read from HBM once and written once.
-#include "common.cuh"
+#include "dense.cuh"
 
 namespace ckb {
-
-struct DenseArgs {
-  const float* W;          // (F, Ko, Kred)
-  const int64_t* in_rows;  // (F*H) per-sample offsets, or nullptr: rows are x_base + f*B*Ki (H==1)
-  const float* arena;      // base the in_rows offsets refer to (or x_base when in_rows == nullptr)
-  float* y;                // (F, B, Ko) output block (forward: written; backward: read)
-  int64_t B;
-  int H, Ki, Ko, Kred, concat;
-  // backward only
-  GradSrc gs;
-  float* gin;   // (F, gin_h, B, Ki)
-  float* dWp;   // [splits][F][Ko][Kred] or nullptr
-  int64_t chunk;
-};
-
-__device__ __forceinline__ const float* in_row(const DenseArgs& a, int f, int h) {
-  return a.in_rows ? a.arena + a.B * a.in_rows[f * a.H + h] : a.arena + (int64_t)f * a.B * a.Ki;
-}
-
-// Writes u (pre-activation, log space) for one sample into `dst[0..Kred)`, returns the row max.
-__device__ __forceinline__ float load_u(const DenseArgs& a, const float* const* rows, int64_t b,
-                                        int lane, float* dst) {
-  float m = -INFINITY;
-  if (!a.concat) {
-    for (int k = lane; k < a.Kred; k += 32) {
-      float u = 0.f;
-      for (int h = 0; h < a.H; ++h) u += rows[h][b * a.Ki + k];
-      dst[k] = u;
-      m = fmaxf(m, u);
-    }
-  } else {
-    for (int h = 0; h < a.H; ++h)
-      for (int k = lane; k < a.Ki; k += 32) {
-        const float u = rows[h][b * a.Ki + k];
-        dst[h * a.Ki + k] = u;
-        m = fmaxf(m, u);
-      }
-  }
-  return clamp_max(warp_max(m));
-}
 
 constexpr int kMaxH = 64;  // inputs per fold the small kernels keep row pointers for
 
@@ -184,6 +144,10 @@ __global__ void dense_fwd_generic(DenseArgs a, int e_stride) {
 }
 
 static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
+  {
+    const int rc = dense_tc_fwd(a, F, c);  // tensor-core path for the hot shape
+    if (rc <= 0) return rc;
+  }
   if (a.Kred <= 128 && a.Ko <= 128 && a.H <= kMaxH) {
     const int kmax = max(a.Ko, 1);
     if (kmax <= 32) return launch_dense_fwd_small<1, 16>(a, F, c);

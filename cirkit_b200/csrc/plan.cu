@@ -20,6 +20,7 @@ void set_error(const char* fmt, ...) {
 
 int transpose_input(const void* x, int dtype, int64_t B, int D, int64_t ld, void* xT, cudaStream_t s);
 int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStream_t s);
+void set_tensor_cores(int on);
 
 }  // namespace ckb
 
@@ -279,5 +280,13 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
 }
 
 int64_t ckb_plan_last_launches(const ckb_plan_t* plan) { return plan ? plan->last_launches : 0; }
+
+int ckb_set_option(int32_t option, int32_t value) {
+  switch (option) {
+    case CKB_OPT_TENSOR_CORES: set_tensor_cores(value); return CKB_OK;
+  }
+  set_error("ckb_set_option: unknown option %d", option);
+  return CKB_ERR_INVALID;
+}
 
 }  // extern "C"

@@ -162,6 +162,10 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
 /* Number of kernels the last forward/backward call on this plan enqueued (bench bookkeeping). */
 int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 
+/* Process-wide switches (testing / A-B measurements). */
+#define CKB_OPT_TENSOR_CORES 0 /* 1 (default): tcgen05 kernels for the shapes that have one; 0: FP32 SIMT only */
+int ckb_set_option(int32_t option, int32_t value);
+
 #ifdef __cplusplus
 }
 #endif

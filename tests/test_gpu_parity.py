@@ -196,6 +196,35 @@ def test_table_fusion_matches_layer_by_layer_plan(name, dev):
         assert (a - b).abs().max().item() <= max(2e-6, 1e-4 * b.abs().max().item())
 
 
+@pytest.mark.parametrize("batch", [8, 128, 200, 1024])
+def test_tensor_core_path_matches_simt(batch, dev):
+    """K=64 layers run on tcgen05 (3xTF32) by default; the FP32 SIMT kernels are the yardstick."""
+    from cirkit_b200 import _lib
+
+    g = Golden("qt28_cp_k64")
+    cc = _circuit(g, dev)
+    x = torch.randint(0, 256, (batch, 784), generator=torch.Generator().manual_seed(batch)).to(dev)
+    lib = _lib.load()
+    res = []
+    try:
+        for on in (1, 0):
+            assert lib.ckb_set_option(_lib.OPT_TENSOR_CORES, on) == 0
+            for p in cc.leaves:
+                p.grad = None
+            y = cc(x)
+            (-y.mean()).backward()
+            res.append((y.detach().clone(), [p.grad.clone() for p in cc.leaves]))
+    finally:
+        lib.ckb_set_option(_lib.OPT_TENSOR_CORES, 1)
+    (yt, gt), (ys, gs) = res
+    assert torch.isfinite(yt).all()
+    err = (yt.double() - ys.double()).abs().max().item()
+    assert err <= 5e-7 * ys.abs().max().item() + 1e-5, f"forward {err:.3e}"
+    for i, (a, b) in enumerate(zip(gt, gs)):
+        e = (a.double() - b.double()).abs().max().item()
+        assert e <= max(2e-6, 1e-4 * b.abs().max().item()), f"leaf {i}: {e:.3e}"
+
+
 def test_errors(dev):
     g = Golden("qt8_cp_k4")
     cc = _circuit(g, dev)
