@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 int transpose_input(const void* x, int dtype, int64_t B, int D, int64_t ld, void* xT, cudaStream_t s);
 int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStream_t s);
 void set_tensor_cores(int on);
+void set_tc_fast_math(int bits);
 
 }  // namespace ckb
 
@@ -284,6 +285,7 @@ int64_t ckb_plan_last_launches(const ckb_plan_t* plan) { return plan ? plan->las
 int ckb_set_option(int32_t option, int32_t value) {
   switch (option) {
     case CKB_OPT_TENSOR_CORES: set_tensor_cores(value); return CKB_OK;
+    case CKB_OPT_TC_FAST_MATH: set_tc_fast_math(value); return CKB_OK;
   }
   set_error("ckb_set_option: unknown option %d", option);
   return CKB_ERR_INVALID;

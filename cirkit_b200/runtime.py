@@ -371,6 +371,15 @@ class PlanRuntime:
         self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
         self._states: dict[torch.device, _DeviceState] = {}
         self.last_launches = 0
+        self.keep_arena = False
+        self.last_arena: Tensor | None = None
+
+    def step_output(self, sid: int, batch: int) -> Tensor:
+        """(F, B, K) activations of plan step `sid` from the last forward pass (keep_arena=True)."""
+        s = self.plan.steps[sid]
+        off = batch * int(self.layout.out_off[sid])
+        n = s.num_folds * batch * s.num_output_units
+        return self.last_arena[off : off + n].view(s.num_folds, batch, s.num_output_units)
 
     def choose_plan(self, batch: int, masked: bool) -> str:
         if self.table_pairs and not masked and 2 * batch >= self.table_states:
@@ -567,6 +576,8 @@ class _PlanFn(torch.autograd.Function):
                 out = torch.stack([arena[B * int(r) : B * int(r) + B * K].view(B, K) for r in rows], dim=1)
         ctx.rt, ctx.st, ctx.call = rt, st, call
         ctx.arena = arena
+        if rt.keep_arena:  # debugging aid: per-step activations of the last forward pass
+            rt.last_arena = arena
         ctx.P = P
         return out
 

@@ -273,6 +273,7 @@ class OracleCircuit(nn.Module):
                 t = outs[src[0]] if len(src) == 1 else torch.cat([outs[p] for p in src], dim=0)
                 y = self._inner_layer(s, t[self._idx[sid]])
             outs.append(y)
+        self.last_outputs = outs  # per-step (F, B, K) tensors, for layer-by-layer parity reports
         src = self._out_sources
         t = outs[src[0]] if len(src) == 1 else torch.cat([outs[p] for p in src], dim=0)
         y = t[self._out_idx].transpose(0, 1)  # (O, B, K) -> (B, O, K)
