@@ -61,6 +61,7 @@ class StepDesc(C.Structure):
         ("cons_rows", C.c_void_p),
         ("slot", C.c_int32 * 4),
         ("int_slot", C.c_int32),
+        ("max_consumers", C.c_int32),
     ]
 
 

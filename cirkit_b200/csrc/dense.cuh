@@ -17,6 +17,7 @@ struct DenseArgs {
   float* gin;   // (F, gin_h, B, Ki)
   float* dWp;   // [splits][F][Ko][Kred] or nullptr
   int64_t chunk;
+  int max_cons;  // largest number of consumer rows any fold sums (1 in a tree)
 };
 
 __device__ __forceinline__ const float* in_row(const DenseArgs& a, int f, int h) {

@@ -404,14 +404,20 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
 }
 
 static size_t run_dense_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
-  if (!dense_small_ok(H, Ko, Kred)) return 0;
+  const size_t tc = dense_tc_bwd_ws(F, H, Ko, Kred, B);
+  if (!dense_small_ok(H, Ko, Kred)) return tc;
   int SW, splits;
   int64_t chunk;
   dense_bwd_config(F, Ko, Kred, B, SW, splits, chunk);
-  return splits > 1 ? (size_t)splits * F * Ko * Kred * 4 : 0;
+  const size_t simt = splits > 1 ? (size_t)splits * F * Ko * Kred * 4 : 0;
+  return simt > tc ? simt : tc;
 }
 
 static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
+  {
+    const int rc = dense_tc_bwd(a, F, dW, c, ws, ws_bytes);  // tensor-core path for the hot shape
+    if (rc <= 0) return rc;
+  }
   const size_t n = (size_t)F * a.Ko * a.Kred;
   if (dense_small_ok(a.H, a.Ko, a.Kred)) {
     int SW, splits;
@@ -488,6 +494,7 @@ int dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
   DenseArgs a = make_args(d, c);
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
   a.gin = c.garena + c.B * d.gin_off;
+  a.max_cons = d.max_consumers;
   return run_dense_bwd(a, d.num_folds, c.grads[d.slot[0]], c, c.ws, c.ws_bytes);
 }
 
@@ -552,6 +559,7 @@ int tucker_bwd(const ckb_step_desc_t& d, Ctx& c) {
   DenseArgs a = tucker_args(d, c, kron);
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
   a.gin = gkron;
+  a.max_cons = d.max_consumers;
   if (int rc = run_dense_bwd(a, d.num_folds, c.grads[d.slot[0]], c, c.ws + 2 * kron_bytes,
                              c.ws_bytes - 2 * kron_bytes))
     return rc;
@@ -609,6 +617,7 @@ int table_dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
   DenseArgs a = table_dense_args(d, c);
   a.gs = GradSrc{dT2, nullptr, nullptr, (int64_t)d.num_states};
   a.gin = dT;
+  a.max_cons = 1;
   const size_t off = (table_bwd_ws(as_table(d), c.B) + 255) & ~(size_t)255;
   return run_dense_bwd(a, d.num_folds, c.grads[d.slot[1]], c, c.ws + off,
                        c.ws_bytes > off ? c.ws_bytes - off : 0);

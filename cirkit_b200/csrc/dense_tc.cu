@@ -290,7 +290,371 @@ int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
   return CKB_OK;
 }
 
-int dense_tc_bwd(const DenseArgs&, int, float*, Ctx&, char*, size_t) { return 1; }
-size_t dense_tc_bwd_ws(int, int, int, int, int64_t) { return 0; }
+// ==========================================================================================
+// Backward.  With e = exp(u - m), S = exp(y - m) (so the forward product is not recomputed) and
+// r[b,o] = g[b,o] / S[b,o]:
+//     d/du[b,i]  = e[b,i] * sum_o r[b,o] W[o,i]         GEMM 1  (M = samples, N = i, K = o)
+//     d/dW[o,i]  = sum_b r[b,o] e[b,i]                  GEMM 2  (M = o, N = i, K = samples)
+// r is contracted over o in GEMM 1 and over the samples in GEMM 2, and tf32 operands must be
+// K-major (MN-major tf32 only exists with the 32-byte-atom swizzle), so the transform warps write
+// r twice: as [sample][o] tiles for GEMM 1 and, after a 4x4 register transpose across lanes
+// (warp shuffles), as [o][sample] tiles for GEMM 2; e is only needed as [i][sample] (GEMM 2 and
+// the du epilogue, which reads it column-wise).  tf32 splits:
+//   GEMM 1: r_hi W_hi -> main accumulator, r_lo W_hi + r_hi W_lo -> correction accumulator;
+//   GEMM 2: ONE M=128 x N=128 instruction stream on the stacked operands [r_hi; r_lo]^T x
+//           [e_hi; e_lo]^T gives all four products in separate quadrants of a 128x128
+//           accumulator that stays in TMEM for the whole CTA (the lo*lo quadrant is dropped).
+// dW leaves the CTA as two partial slabs per batch split which the caller reduces.
+// ==========================================================================================
+namespace {
+
+constexpr int kBwdTransformWarps = 16, kBwdEpilogueWarps = 8;
+constexpr int kBwdMmaWarp = kBwdTransformWarps + kBwdEpilogueWarps;
+constexpr int kBwdThreads = (kBwdMmaWarp + 1) * 32;  // 800
+
+struct __align__(1024) BwdSmem {
+  float r_hi[2][TM * 32];  // [o-block][sample][32]            GEMM 1 A operand        32 KB
+  float r_lo[2][TM * 32];  //                                                           32 KB
+  float rT[4][128 * 32];   // [sample-block][hi o 0..63 | lo o 0..63][32 samples]       64 KB
+  float eT[4][128 * 32];   // [sample-block][hi i 0..63 | lo i 0..63][32 samples]       64 KB
+  float w_hi[2][KK * 32];  // W^T: [o-block][i][32 o's]        GEMM 1 B operand        16 KB
+  float w_lo[2][KK * 32];  //                                                           16 KB
+  uint64_t ab_full, ab_empty, e_done, d1_full[2], d1_empty[2], d2_full;
+  uint32_t tmem_base;
+};
+
+constexpr int kMaxCons = 4;  // consumer rows per fold the tensor-core path sums
+
+// 4x4 transpose across the 4 lanes that differ in their two low lane bits: on entry lane j holds
+// (row j, cols 0..3); on exit it holds (rows 0..3, col j).
+__device__ __forceinline__ float4 transpose4(float4 v, int j) {
+  const bool p = j & 1, q = j & 2;
+  float s0 = p ? v.x : v.y, s1 = p ? v.z : v.w;
+  float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  if (p) { v.x = r0; v.z = r1; } else { v.y = r0; v.w = r1; }
+  s0 = q ? v.x : v.z;
+  s1 = q ? v.y : v.w;
+  r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+  r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+  if (q) { v.x = r0; v.y = r1; } else { v.z = r0; v.w = r1; }
+  return v;
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x);
+  split_tf32(v.y, hi.y, lo.y);
+  split_tf32(v.z, hi.z, lo.z);
+  split_tf32(v.w, hi.w, lo.w);
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdSmem& s = *reinterpret_cast<BwdSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int n_tiles_total = (int)((a.B + TM - 1) / TM);
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
+  if (n_tiles <= 0) return;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.d1_full[i], 1);
+      mbar_init(&s.d1_empty[i], kBwdEpilogueWarps * 32);
+    }
+    mbar_init(&s.ab_full, kBwdTransformWarps);
+    mbar_init(&s.ab_empty, 1);
+    mbar_init(&s.e_done, kBwdEpilogueWarps * 32);
+    mbar_init(&s.d2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kBwdMmaWarp) tmem_alloc(&s.tmem_base, 512);
+  {
+    // W^T image: rows i, K = o
+    const float* Wf = a.W + (int64_t)f * KK * KK;  // [o][i]
+    for (int idx = tid; idx < KK * KK; idx += kBwdThreads) {
+      const int o = idx >> 6, i = idx & 63;
+      float hi, lo;
+      split_tf32(Wf[idx], hi, lo);
+      const uint32_t off = swz_off(i, o & 31) >> 2;
+      s.w_hi[o >> 5][off] = hi;
+      s.w_lo[o >> 5][off] = lo;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+  constexpr uint32_t kD2Col = 256;  // D1 buffers: [0,128) and [128,256); D2: [256,384)
+
+  if (warp == kBwdMmaWarp) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_tf32(TM, KK, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc_tf32(128, 128, 0, 0);
+      const uint32_t r_addr[2] = {smem_u32(s.r_hi), smem_u32(s.r_lo)};
+      const uint32_t w_addr[2] = {smem_u32(s.w_hi), smem_u32(s.w_lo)};
+      const uint32_t rT_addr = smem_u32(s.rT), eT_addr = smem_u32(s.eT);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int buf = it & 1;
+        mbar_wait(&s.d1_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&s.ab_full, it & 1);
+        tc_fence_after_sync();
+        // ---- GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
+          const uint32_t ab = r_addr[p == 1 ? 1 : 0], wb = w_addr[p == 2 ? 1 : 0];
+          const uint32_t d = tmem_base + buf * 128 + (p == 0 ? 0 : KK);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 8 o's per step
+            const uint64_t da = make_desc(ab + (ks >> 2) * (TM * 128) + (ks & 3) * 32, 16, 1024);
+            const uint64_t db = make_desc(wb + (ks >> 2) * (KK * 128) + (ks & 3) * 32, 16, 1024);
+            mma_tf32(d, da, db, idesc1, (p == 2 || ks) ? 1u : 0u);
+          }
+        }
+        mma_commit(&s.d1_full[buf]);
+        // ---- GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
+        if (want_dw) {
+#pragma unroll
+          for (int ks = 0; ks < TM / 8; ++ks) {
+            const uint32_t o = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
+            mma_tf32(tmem_base + kD2Col, make_desc(rT_addr + o, 16, 1024),
+                     make_desc(eT_addr + o, 16, 1024), idesc2, (it || ks) ? 1u : 0u);
+          }
+        }
+        mma_commit(&s.ab_empty);
+      }
+      mma_commit(&s.d2_full);
+    }
+  } else if (warp < kBwdTransformWarps) {
+    // ================= transform: rows -> r, r^T, e^T operand tiles =================
+    const int og = lane >> 2, bsub = lane & 3;  // 16-byte chunk within a 32-column half; row in group
+    const float* row0 = in_row(a, f, 0);
+    const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
+    const float* yrow = a.y + (int64_t)f * a.B * KK;
+    const float* grow[kMaxCons];
+    int n_cons = 1;
+    if (a.gs.cons_ptr == nullptr) {
+      grow[0] = a.gs.garena + (int64_t)f * a.gs.B * KK;
+    } else {
+      const int c0 = a.gs.cons_ptr[f];
+      n_cons = a.gs.cons_ptr[f + 1] - c0;
+#pragma unroll
+      for (int c = 0; c < kMaxCons; ++c)
+        grow[c] = c < n_cons ? a.gs.garena + a.gs.B * a.gs.cons_rows[c0 + c] : nullptr;
+    }
+    uint8_t* rhi = reinterpret_cast<uint8_t*>(s.r_hi);
+    uint8_t* rlo = reinterpret_cast<uint8_t*>(s.r_lo);
+    uint8_t* rT = reinterpret_cast<uint8_t*>(s.rT);
+    uint8_t* eT = reinterpret_cast<uint8_t*>(s.eT);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int64_t b0 = (int64_t)(t_begin + it) * TM;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int rbase = warp * 8 + pass * 4;  // 4 consecutive samples handled by this warp
+        const int r = rbase + bsub;
+        const int64_t b = b0 + r;
+        const bool ok = b < a.B;
+        float4 xu[2], yv[2], gv[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          xu[ch] = yv[ch] = gv[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            const int64_t o = b * KK + 32 * ch + 4 * og;
+            xu[ch] = ldg_stream(row0 + o);
+            if (row1) {
+              const float4 z = ldg_stream(row1 + o);
+              xu[ch].x += z.x; xu[ch].y += z.y; xu[ch].z += z.z; xu[ch].w += z.w;
+            }
+            yv[ch] = ldg_stream(yrow + o);
+#pragma unroll
+            for (int c = 0; c < kMaxCons; ++c)
+              if (c < n_cons) {
+                const float4 z = ldg_stream(grow[c] + o);
+                gv[ch].x += z.x; gv[ch].y += z.y; gv[ch].z += z.z; gv[ch].w += z.w;
+              }
+          }
+        }
+        if (pass == 0) {
+          // operand tiles of the previous tile must be drained (both GEMMs + the du epilogue)
+          mbar_wait(&s.ab_empty, (it & 1) ^ 1);
+          mbar_wait(&s.e_done, (it & 1) ^ 1);
+        }
+        float m = fmaxf(fmaxf(fmaxf(xu[0].x, xu[0].y), fmaxf(xu[0].z, xu[0].w)),
+                        fmaxf(fmaxf(xu[1].x, xu[1].y), fmaxf(xu[1].z, xu[1].w)));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        m = clamp_max(m);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float4 e, rr, hi, lo;
+          e.x = ok ? expf(xu[ch].x - m) : 0.f;
+          e.y = ok ? expf(xu[ch].y - m) : 0.f;
+          e.z = ok ? expf(xu[ch].z - m) : 0.f;
+          e.w = ok ? expf(xu[ch].w - m) : 0.f;
+          rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * expf(m - yv[ch].x);
+          rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * expf(m - yv[ch].y);
+          rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * expf(m - yv[ch].z);
+          rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * expf(m - yv[ch].w);
+          // r as [sample][o]
+          split4(rr, hi, lo);
+          const uint32_t off = (uint32_t)ch * (TM * 128) + (uint32_t)r * 128u +
+                               ((((uint32_t)og ^ (uint32_t)r) & 7u) << 4);
+          *reinterpret_cast<float4*>(rhi + off) = hi;
+          *reinterpret_cast<float4*>(rlo + off) = lo;
+          // r and e as [unit][4 consecutive samples]
+          const uint32_t u = 32u * ch + 4u * og + bsub;          // unit this lane owns afterwards
+          const uint32_t chunk = ((uint32_t)rbase & 31u) >> 2;   // 16-byte chunk of the 4 samples
+          const uint32_t blk = ((uint32_t)rbase >> 5) * (128 * 128);
+          const uint32_t off_hi = blk + u * 128u + (((chunk ^ u) & 7u) << 4);
+          const uint32_t off_lo = blk + (64u + u) * 128u + (((chunk ^ (64u + u)) & 7u) << 4);
+          split4(transpose4(rr, bsub), hi, lo);
+          *reinterpret_cast<float4*>(rT + off_hi) = hi;
+          *reinterpret_cast<float4*>(rT + off_lo) = lo;
+          split4(transpose4(e, bsub), hi, lo);
+          *reinterpret_cast<float4*>(eT + off_hi) = hi;
+          *reinterpret_cast<float4*>(eT + off_lo) = lo;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.ab_full);
+      if (it + 1 < n_tiles && og == 0) {  // warm L2 with the next tile (one lane per 128-byte line)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int64_t b = b0 + TM + warp * 8 + j * 4 + bsub;
+          if (b < a.B) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              const int64_t o = b * KK + 32 * ch;
+              prefetch_l2(row0 + o);
+              if (row1) prefetch_l2(row1 + o);
+              prefetch_l2(yrow + o);
+              if (n_cons > 0) prefetch_l2(grow[0] + o);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: du = e * T -> gin; finally dW partials =================
+    const int ew = warp - kBwdTransformWarps;  // 0..7
+    const int q = warp & 3;                    // TMEM lane quadrant (warps 16..23 -> 0..3,0..3)
+    const int chalf = ew >> 2;                 // which 32 of the 64 columns this warp handles
+    const uint8_t* eT = reinterpret_cast<const uint8_t*>(s.eT);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int buf = it & 1;
+      const int64_t b = (int64_t)(t_begin + it) * TM + q * 32 + lane;
+      mbar_wait(&s.d1_full[buf], (it >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + chalf * 32;
+      // e[b][i] = eT[(i)][b] + eT[(64 + i)][b]: sample block q, column `lane`
+      const uint32_t ecol = (uint32_t)q * (128 * 128) + ((uint32_t)lane & 3u) * 4u;
+      float* dst = a.gin + ((int64_t)f * a.B + b) * KK + chalf * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[16], w[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld16(taddr + KK + c * 16, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t i = (uint32_t)chalf * 32u + c * 16u + j + t;
+            const uint32_t ohi = ecol + i * 128u + (((((uint32_t)lane >> 2) ^ i) & 7u) << 4);
+            const uint32_t olo = ecol + (64u + i) * 128u + (((((uint32_t)lane >> 2) ^ (64u + i)) & 7u) << 4);
+            const float e = *reinterpret_cast<const float*>(eT + ohi) + *reinterpret_cast<const float*>(eT + olo);
+            o[t] = e * (v[j + t] + w[j + t]);
+          }
+          if (b < a.B) *reinterpret_cast<float4*>(dst + c * 16 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s.d1_empty[buf]);
+      mbar_arrive(&s.e_done);
+    }
+    if (want_dw) {
+      // D2 quadrants: rows 0..63 = r_hi^T [e_hi | e_lo], rows 64..127 = r_lo^T [e_hi | (dropped)]
+      mbar_wait(&s.d2_full, 0);
+      tc_fence_after_sync();
+      const int row = q * 32 + lane;  // 0..127
+      const int o = row & 63;
+      const int slab = 2 * blockIdx.x + (row >> 6);
+      float* out = a.dWp + (((int64_t)slab * gridDim.y + f) * KK + o) * KK + chalf * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + chalf * 32;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[16], w[16];
+        tmem_ld16(taddr + c * 16, v);
+        if (row < 64) tmem_ld16(taddr + KK + c * 16, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (row < 64) { t.x += w[j]; t.y += w[j + 1]; t.z += w[j + 2]; t.w += w[j + 3]; }
+          *reinterpret_cast<float4*>(out + c * 16 + j) = t;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kBwdMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+void dense_tc_bwd_config(int F, int64_t B, int& splits, int& tiles_per_cta) {
+  const int n_tiles = ceil_div(B, TM);
+  splits = (int)max64(1, min64(n_tiles, ceil_div(2 * kNumSMs, F)));
+  tiles_per_cta = ceil_div(n_tiles, splits);
+  splits = ceil_div(n_tiles, tiles_per_cta);
+}
+
+bool dense_tc_bwd_ok(const DenseArgs& a) {
+  return a.Ki == KK && a.Ko == KK && !a.concat && a.H >= 1 && a.H <= 2 && a.Kred == KK;
+}
+
+}  // namespace
+
+size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
+  if (Ko != KK || Kred != KK || H > 2) return 0;
+  int splits, tpc;
+  dense_tc_bwd_config(F, B, splits, tpc);
+  return (size_t)2 * splits * F * KK * KK * 4;
+}
+
+int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
+  if (tc_disabled() || !dense_tc_bwd_ok(a_in) || a_in.max_cons > kMaxCons) return 1;
+  DenseArgs a = a_in;
+  int splits, tpc;
+  dense_tc_bwd_config(F, a.B, splits, tpc);
+  const size_t n = (size_t)F * KK * KK;
+  if (dW) {
+    if (ws_bytes < 2 * splits * n * 4) {
+      set_error("dense_tc_bwd: workspace too small (%zu < %zu)", ws_bytes, 2 * splits * n * 4);
+      return CKB_ERR_WORKSPACE;
+    }
+    a.dWp = (float*)ws;
+  }
+  const size_t smem = sizeof(BwdSmem) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(splits, F);
+  dense_tc_bwd_kernel<<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  if (dW) return reduce_partials(a.dWp, dW, (int64_t)n, 2 * splits, c);
+  return CKB_OK;
+}
 
 }  // namespace ckb

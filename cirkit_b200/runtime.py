@@ -272,6 +272,8 @@ class _DeviceState:
             for j in range(4):
                 d.slot[j] = es.slots[j] if j < len(es.slots) else -1
             d.int_slot = rt.int_slots.get(es.sids[0], -1) if es.kind != STEP_TABLE_DENSE else -1
+            cp = lay.cons_ptr[es.out_sid]
+            d.max_consumers = int(np.max(np.diff(cp))) if len(cp) > 1 else 0
         ops = (L.ParamOp * max(1, len(rt.native_ops)))()
         for i, (b, (kind, rows, cols, aux, a, bb)) in enumerate(rt.native_ops):
             ops[i].kind, ops[i].src, ops[i].dst = kind, b.src_slot, b.dst_slot

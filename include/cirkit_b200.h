@@ -85,6 +85,7 @@ typedef struct {
                            TABLE: {T}   GAUSSIAN: {mean, stddev, log_partition}
                            CONSTANT: {value}   DENSE/TUCKER: {W (F,Ko,Kred)}   MIXING: {w (F,K,H)} */
   int32_t int_slot;   /* slot of the (F,Ko) values an integrated variable yields, -1 = zeros   */
+  int32_t max_consumers; /* largest cons_ptr[f+1]-cons_ptr[f] (lets kernels pick a fast path)   */
 } ckb_step_desc_t;
 
 /* Parameter re-parameterisation ops, run before the layers (forward) and after them (backward).

@@ -43,6 +43,7 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.ParamOp) == 40
     assert _lib.StepDesc.out_off.offset == 32 and _lib.StepDesc.in_rows.offset == 48
     assert _lib.StepDesc.slot.offset == 80 and _lib.StepDesc.int_slot.offset == 96
+    assert _lib.StepDesc.max_consumers.offset == 100
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):
