@@ -175,10 +175,10 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         const float m = clamp_max(half_warp_max(fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w))));
         float4 hi, lo;
         if (fast_math & 1) {
-          split_tf32(__expf(u.x - m), hi.x, lo.x);
-          split_tf32(__expf(u.y - m), hi.y, lo.y);
-          split_tf32(__expf(u.z - m), hi.z, lo.z);
-          split_tf32(__expf(u.w - m), hi.w, lo.w);
+          split_tf32(fast_exp(u.x - m), hi.x, lo.x);
+          split_tf32(fast_exp(u.y - m), hi.y, lo.y);
+          split_tf32(fast_exp(u.z - m), hi.z, lo.z);
+          split_tf32(fast_exp(u.w - m), hi.w, lo.w);
         } else {
           split_tf32(expf(u.x - m), hi.x, lo.x);
           split_tf32(expf(u.y - m), hi.y, lo.y);
@@ -218,10 +218,10 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         for (int j = 0; j < 4; ++j) {
           float4 o;
           if (fast_math & 2) {
-            o.x = __logf(v[4 * j]) + m;
-            o.y = __logf(v[4 * j + 1]) + m;
-            o.z = __logf(v[4 * j + 2]) + m;
-            o.w = __logf(v[4 * j + 3]) + m;
+            o.x = fast_log(v[4 * j]) + m;
+            o.y = fast_log(v[4 * j + 1]) + m;
+            o.z = fast_log(v[4 * j + 2]) + m;
+            o.w = fast_log(v[4 * j + 3]) + m;
           } else {
             o.x = logf(v[4 * j]) + m;
             o.y = logf(v[4 * j + 1]) + m;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
 }  // namespace
 
 static int g_tc_enabled = -1;
-static int g_tc_fast_math = 0;
+static int g_tc_fast_math = 3;
 void set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; }
 void set_tc_fast_math(int bits) { g_tc_fast_math = bits; }
 static bool tc_disabled() {
@@ -347,7 +347,7 @@ __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) 
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw) {
+dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -490,14 +490,26 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           float4 e, rr, hi, lo;
-          e.x = ok ? expf(xu[ch].x - m) : 0.f;
-          e.y = ok ? expf(xu[ch].y - m) : 0.f;
-          e.z = ok ? expf(xu[ch].z - m) : 0.f;
-          e.w = ok ? expf(xu[ch].w - m) : 0.f;
-          rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * expf(m - yv[ch].x);
-          rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * expf(m - yv[ch].y);
-          rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * expf(m - yv[ch].z);
-          rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * expf(m - yv[ch].w);
+          if (fast_math & 1) {
+            e.x = ok ? fast_exp(xu[ch].x - m) : 0.f;
+            e.y = ok ? fast_exp(xu[ch].y - m) : 0.f;
+            e.z = ok ? fast_exp(xu[ch].z - m) : 0.f;
+            e.w = ok ? fast_exp(xu[ch].w - m) : 0.f;
+            // m - y = -log S may be positive: fast_exp is exact enough there too (|x| small)
+            rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * fast_exp(m - yv[ch].x);
+            rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * fast_exp(m - yv[ch].y);
+            rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * fast_exp(m - yv[ch].z);
+            rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * fast_exp(m - yv[ch].w);
+          } else {
+            e.x = ok ? expf(xu[ch].x - m) : 0.f;
+            e.y = ok ? expf(xu[ch].y - m) : 0.f;
+            e.z = ok ? expf(xu[ch].z - m) : 0.f;
+            e.w = ok ? expf(xu[ch].w - m) : 0.f;
+            rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * expf(m - yv[ch].x);
+            rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * expf(m - yv[ch].y);
+            rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * expf(m - yv[ch].z);
+            rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * expf(m - yv[ch].w);
+          }
           // r as [sample][o]
           split4(rr, hi, lo);
           const uint32_t off = (uint32_t)ch * (TM * 128) + (uint32_t)r * 128u +
@@ -650,7 +662,7 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
     attr = true;
   }
   dim3 grid(splits, F);
-  dense_tc_bwd_kernel<<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0);
+  dense_tc_bwd_kernel<<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_fast_math);
   CKB_LAUNCH_CHECK();
   c.launches++;
   if (dW) return reduce_partials(a.dWp, dW, (int64_t)n, 2 * splits, c);

@@ -117,67 +117,128 @@ int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
 }
 
 // Backward of the lookup: dT[f,v,:] = sum over samples with x=v of g[f,b,:]  (the reference gets
-// this from autograd as an `index_put_`, 26 % of its CPU step -- SURVEY §3(b)).  One CTA owns a
-// (fold, unit tile, batch split) and accumulates into a shared-memory histogram.
-__global__ void table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var,
-                                 const void* __restrict__ xT, int x_is_float,
-                                 const uint8_t* __restrict__ maskT, int64_t mask_ld,
-                                 float* __restrict__ out, int64_t B, int K, int V, int KT,
-                                 int64_t chunk) {
-  extern __shared__ float hist[];  // [V][KT]
+// this from autograd as an `index_put_`, 26 % of its CPU step -- SURVEY §3(b)).
+//
+// One CTA owns a (fold, unit tile, batch split).  It first buckets its samples by state in shared
+// memory -- integer counts, an exclusive scan, and a *stable* fill (one warp walks the samples in
+// order and ranks equal states inside each group of 32 with match_any), so every bucket lists its
+// samples in ascending order -- and then each warp sums the gradient rows of whole buckets in
+// registers and writes each table row once.  No floating-point atomics: the result is
+// deterministic, and every g row is read exactly once as one contiguous segment.
+constexpr int kTableBwdThreads = 512;
+constexpr int kTableBwdKT = 128;  // units per CTA (4 per lane)
+
+__global__ void __launch_bounds__(kTableBwdThreads)
+table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* __restrict__ xT,
+                 int x_is_float, const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                 float* __restrict__ out, int64_t B, int K, int V, int64_t chunk) {
+  extern __shared__ int smem_i[];
+  int* cnt = smem_i;                                     // [V]  bucket sizes, then fill cursors
+  int* start = cnt + V;                                  // [V+1] bucket offsets
+  uint16_t* list = reinterpret_cast<uint16_t*>(start + V + 1);  // [chunk] sample ids (chunk-local)
   const int f = blockIdx.y;
-  const int k0 = blockIdx.z * KT;
-  const int kt = min(KT, K - k0);
+  const int k0 = blockIdx.z * kTableBwdKT;
   const int var = scope_var[f];
-  for (int i = threadIdx.x; i < V * KT; i += blockDim.x) hist[i] = 0.f;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int64_t b_begin = (int64_t)blockIdx.x * chunk;
-  const int64_t b_end = min(B, b_begin + chunk);
-  for (int64_t b = b_begin + warp; b < b_end; b += nwarps) {
+  const int n = (int)(min64(B, b_begin + chunk) - b_begin);
+
+  for (int i = tid; i < V; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int64_t b = b_begin + i;
     if (read_mask(maskT, mask_ld, var, b)) continue;
-    int v = read_state(xT, x_is_float, (int64_t)var * B + b);
-    v = min(max(v, 0), V - 1);
-    for (int kk = lane; kk < kt; kk += 32) {
-      const float g = pull_grad(gs, f, b, K, k0 + kk);
-      atomicAdd(&hist[v * KT + kk], g);
+    const int v = min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1);
+    atomicAdd(&cnt[v], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the counts (V is a few hundred at most)
+    int carry = 0;
+    for (int i0 = 0; i0 < V; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < V ? cnt[i] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < V) {
+        start[i] = carry + incl - c;
+        cnt[i] = carry + incl - c;  // becomes the fill cursor
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) start[V] = carry;
+    __syncwarp();
+    // stable fill: samples in ascending order
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const int64_t b = b_begin + i;
+      const bool valid = i < n && !read_mask(maskT, mask_ld, var, b);
+      const int v = valid ? min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1) : -1 - lane;
+      const unsigned same = __match_any_sync(0xffffffffu, v);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      int base = 0;
+      if (valid) base = cnt[v];
+      __syncwarp();
+      if (valid) {
+        list[base + rank] = (uint16_t)i;
+        if (rank == __popc(same) - 1) cnt[v] = base + rank + 1;  // last lane of the group
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
-  // out: [split][F][V][K]
+  // sum whole buckets: warp per state, lanes over units
   float* o = out + ((int64_t)blockIdx.x * gridDim.y + f) * V * K;
-  for (int i = threadIdx.x; i < V * kt; i += blockDim.x) {
-    const int v = i / kt, kk = i - v * kt;
-    o[(int64_t)v * K + k0 + kk] = hist[v * KT + kk];
+  for (int v = warp; v < V; v += nwarps) {
+    const int s0 = start[v], s1 = start[v + 1];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j = s0; j < s1; ++j) {
+      const int64_t b = b_begin + list[j];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = k0 + lane + 32 * t;
+        if (k < K) acc[t] += pull_grad(gs, f, b, K, k);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = k0 + lane + 32 * t;
+      if (k < K && k < k0 + kTableBwdKT) o[(int64_t)v * K + k] = acc[t];
+    }
   }
 }
 
-static void table_bwd_config(const ckb_step_desc_t& d, int64_t B, int& KT, int& splits, int64_t& chunk) {
-  KT = min(d.k_out, 64);
-  while ((size_t)d.num_states * KT * 4 > 96 * 1024 && KT > 1) KT = (KT + 1) / 2;
-  const int ktiles = ceil_div(d.k_out, KT);
-  const int64_t want = ceil_div(3 * kNumSMs, (int64_t)d.num_folds * ktiles);
-  splits = (int)max64(1, min64(want, ceil_div(B, 256)));
+static void table_bwd_config(const ckb_step_desc_t& d, int64_t B, int& splits, int64_t& chunk) {
+  // a CTA buckets at most 32768 samples (uint16 ids, 64 KB of shared memory)
+  splits = ceil_div(B, 32768);
+  const int ktiles = ceil_div(d.k_out, kTableBwdKT);
+  const int64_t want = ceil_div(2 * kNumSMs, (int64_t)d.num_folds * ktiles);
+  splits = (int)max64(splits, min64(want, ceil_div(B, 1024)));
   chunk = ceil_div(B, splits);
   splits = ceil_div(B, chunk);
 }
 
 size_t table_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
-  int KT, splits;
+  int splits;
   int64_t chunk;
-  table_bwd_config(d, B, KT, splits, chunk);
+  table_bwd_config(d, B, splits, chunk);
   return splits > 1 ? (size_t)splits * d.num_folds * d.num_states * d.k_out * 4 : 0;
 }
 
 int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   float* dT = c.grads[d.slot[0]];
   if (dT == nullptr) return CKB_OK;
-  int KT, splits;
+  int splits;
   int64_t chunk;
-  table_bwd_config(d, c.B, KT, splits, chunk);
-  const size_t smem = (size_t)d.num_states * KT * 4;
+  table_bwd_config(d, c.B, splits, chunk);
+  const int V = d.num_states;
+  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 2 + 16;
   if (smem > 200 * 1024) {
-    set_error("table_bwd: %d states do not fit the shared-memory histogram", d.num_states);
+    set_error("table_bwd: %d states do not fit shared memory", V);
     return CKB_ERR_UNSUPPORTED;
   }
   static bool attr_set = false;
@@ -186,7 +247,7 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
                                         200 * 1024));
     attr_set = true;
   }
-  const size_t n = (size_t)d.num_folds * d.num_states * d.k_out;
+  const size_t n = (size_t)d.num_folds * V * d.k_out;
   float* out = dT;
   if (splits > 1) {
     if (c.ws_bytes < (size_t)splits * n * 4) {
@@ -196,10 +257,9 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
     out = (float*)c.ws;
   }
   GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
-  dim3 grid(splits, d.num_folds, ceil_div(d.k_out, KT));
-  table_bwd_kernel<<<grid, 256, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
-                                                  c.mask_ld, out, c.B, d.k_out, d.num_states, KT,
-                                                  chunk);
+  dim3 grid(splits, d.num_folds, ceil_div(d.k_out, kTableBwdKT));
+  table_bwd_kernel<<<grid, kTableBwdThreads, smem, c.stream>>>(
+      gs, d.scope_var, c.xT, c.x_is_float, c.maskT, c.mask_ld, out, c.B, d.k_out, V, chunk);
   CKB_LAUNCH_CHECK();
   c.launches++;
   if (splits > 1) return reduce_partials(out, dT, (int64_t)n, splits, c);

@@ -165,7 +165,7 @@ int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 
 /* Process-wide switches (testing / A-B measurements). */
 #define CKB_OPT_TENSOR_CORES 0 /* 1 (default): tcgen05 kernels for the shapes that have one; 0: FP32 SIMT only */
-#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: ex2.approx-based exp, bit 1: lg2.approx-based log in the tcgen05 kernels (default 0) */
+#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels (default 3) */
 int ckb_set_option(int32_t option, int32_t value);
 
 #ifdef __cplusplus
