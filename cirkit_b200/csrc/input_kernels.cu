@@ -67,25 +67,33 @@ __global__ void table_fwd_kernel(const float* __restrict__ T, const int32_t* __r
   const float* Tf = T + (int64_t)f * V * K;
   float* yf = y + (int64_t)f * B * K;
   const float* integ_f = integ ? integ + (int64_t)f * K : nullptr;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if ((K & 3) == 0) {
+    // a group of G = min(32, K/4 rounded up to a power of two) lanes copies one K-float row
     const int K4 = K >> 2;
-    const int64_t total = B * K4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-      const int64_t b = idx / K4;
-      const int k4 = (int)(idx - b * K4);
-      float4 val;
+    int G = 1;
+    while (G < K4 && G < 32) G <<= 1;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const int rows_per_warp = 32 / G;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b0 = warp_global * rows_per_warp; b0 < B; b0 += n_warps * rows_per_warp) {
+      const int64_t b = b0 + lane / G;
+      if (b >= B) continue;
+      const float4* src;
       if (read_mask(maskT, mask_ld, var, b)) {
-        val = integ_f ? ((const float4*)integ_f)[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        src = reinterpret_cast<const float4*>(integ_f);
       } else {
         int v = read_state(xT, x_is_float, (int64_t)var * B + b);
         v = min(max(v, 0), V - 1);
-        val = ((const float4*)(Tf + (int64_t)v * K))[k4];
+        src = reinterpret_cast<const float4*>(Tf + (int64_t)v * K);
       }
-      ((float4*)yf)[idx] = val;
+      float4* dst = reinterpret_cast<float4*>(yf + b * K);
+      for (int k4 = gl; k4 < K4; k4 += G)
+        dst[k4] = src ? src[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else {
     const int64_t total = B * K;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
       const int64_t b = idx / K;
       const int k = (int)(idx - b * K);
@@ -104,8 +112,15 @@ __global__ void table_fwd_kernel(const float* __restrict__ T, const int32_t* __r
 
 int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
   const int K = d.k_out;
-  const int64_t per_fold = (K % 4 == 0) ? c.B * (K / 4) : c.B * K;
-  const int bx = (int)min64(ceil_div(per_fold, 256), 4 * kNumSMs);
+  int bx;
+  if (K % 4 == 0) {
+    int G = 1;
+    while (G < K / 4 && G < 32) G <<= 1;
+    const int64_t rows_per_block = 8 * (32 / G);      // 256 threads
+    bx = (int)min64(ceil_div(c.B, rows_per_block * 4), 2 * kNumSMs);  // >= 4 rows per lane group
+  } else {
+    bx = (int)min64(ceil_div(c.B * K, 256), 4 * kNumSMs);
+  }
   dim3 grid(max(bx, 1), d.num_folds);
   table_fwd_kernel<<<grid, 256, 0, c.stream>>>(
       c.tensors[d.slot[0]], d.scope_var, c.xT, c.x_is_float, c.maskT, c.mask_ld,
@@ -126,33 +141,52 @@ int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
 // registers and writes each table row once.  No floating-point atomics: the result is
 // deterministic, and every g row is read exactly once as one contiguous segment.
 constexpr int kTableBwdThreads = 512;
-constexpr int kTableBwdKT = 128;  // units per CTA (4 per lane)
+constexpr int kTableMaxCons = 8;
 
-__global__ void __launch_bounds__(kTableBwdThreads)
+template <int NT>  // units per lane: a CTA covers 32*NT units
+__global__ void __launch_bounds__(kTableBwdThreads, 1)
 table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* __restrict__ xT,
                  int x_is_float, const uint8_t* __restrict__ maskT, int64_t mask_ld,
                  float* __restrict__ out, int64_t B, int K, int V, int64_t chunk) {
   extern __shared__ int smem_i[];
   int* cnt = smem_i;                                     // [V]  bucket sizes, then fill cursors
   int* start = cnt + V;                                  // [V+1] bucket offsets
-  uint16_t* list = reinterpret_cast<uint16_t*>(start + V + 1);  // [chunk] sample ids (chunk-local)
+  uint16_t* xs = reinterpret_cast<uint16_t*>(start + V + 1);  // [chunk] state of every sample
+  uint16_t* list = xs + chunk;                           // [chunk] sample ids grouped by state
+  __shared__ const float* grows[kTableMaxCons];
+  __shared__ int n_cons_s;
   const int f = blockIdx.y;
-  const int k0 = blockIdx.z * kTableBwdKT;
+  const int k0 = blockIdx.z * (32 * NT);
   const int var = scope_var[f];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int64_t b_begin = (int64_t)blockIdx.x * chunk;
   const int n = (int)(min64(B, b_begin + chunk) - b_begin);
 
   for (int i = tid; i < V; i += blockDim.x) cnt[i] = 0;
+  if (tid == 0) {
+    // rows of the gradient arena this fold sums (its consumers), resolved once
+    if (gs.cons_ptr == nullptr) {
+      n_cons_s = 1;
+      grows[0] = gs.garena + (int64_t)f * gs.B * K;
+    } else {
+      const int c0 = gs.cons_ptr[f];
+      const int nc = gs.cons_ptr[f + 1] - c0;
+      n_cons_s = nc <= kTableMaxCons ? nc : -1;  // -1: fall back to the generic pull
+      for (int c = 0; c < nc && c < kTableMaxCons; ++c) grows[c] = gs.garena + gs.B * gs.cons_rows[c0 + c];
+    }
+  }
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {
     const int64_t b = b_begin + i;
-    if (read_mask(maskT, mask_ld, var, b)) continue;
-    const int v = min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1);
-    atomicAdd(&cnt[v], 1);
+    int v = 0xFFFF;
+    if (!read_mask(maskT, mask_ld, var, b)) {
+      v = min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1);
+      atomicAdd(&cnt[v], 1);
+    }
+    xs[i] = (uint16_t)v;
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of the counts (V is a few hundred at most)
+  if (warp == 0) {  // exclusive scan of the counts, then the stable fill
     int carry = 0;
     for (int i0 = 0; i0 < V; i0 += 32) {
       const int i = i0 + lane;
@@ -171,51 +205,76 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
     }
     if (lane == 0) start[V] = carry;
     __syncwarp();
-    // stable fill: samples in ascending order
     for (int i0 = 0; i0 < n; i0 += 32) {
       const int i = i0 + lane;
-      const int64_t b = b_begin + i;
-      const bool valid = i < n && !read_mask(maskT, mask_ld, var, b);
-      const int v = valid ? min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1) : -1 - lane;
-      const unsigned same = __match_any_sync(0xffffffffu, v);
+      const int xv = i < n ? xs[i] : 0xFFFF;
+      const bool valid = xv != 0xFFFF;
+      const int key = valid ? xv : 0x10000 + lane;
+      const unsigned same = __match_any_sync(0xffffffffu, key);
       const int rank = __popc(same & ((1u << lane) - 1u));
       int base = 0;
-      if (valid) base = cnt[v];
+      if (valid) base = cnt[xv];
       __syncwarp();
       if (valid) {
         list[base + rank] = (uint16_t)i;
-        if (rank == __popc(same) - 1) cnt[v] = base + rank + 1;  // last lane of the group
+        if (rank == __popc(same) - 1) cnt[xv] = base + rank + 1;  // last lane of the group
       }
       __syncwarp();
     }
   }
   __syncthreads();
-  // sum whole buckets: warp per state, lanes over units
+  // sum whole buckets: warp per state, lanes over units, 8 rows (8*NT loads per lane) in flight
   float* o = out + ((int64_t)blockIdx.x * gridDim.y + f) * V * K;
+  const int n_cons = n_cons_s;
   for (int v = warp; v < V; v += nwarps) {
     const int s0 = start[v], s1 = start[v + 1];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int j = s0; j < s1; ++j) {
-      const int64_t b = b_begin + list[j];
+    float acc[NT];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int k = k0 + lane + 32 * t;
-        if (k < K) acc[t] += pull_grad(gs, f, b, K, k);
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    if (n_cons >= 0) {
+      for (int c = 0; c < n_cons; ++c) {
+        const float* g0 = grows[c] + k0 + lane;
+        for (int j0 = s0; j0 < s1; j0 += 8) {
+          float g[8][NT];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            const bool ok = j < s1;
+            const float* row = g0 + (b_begin + (ok ? list[j] : 0)) * K;
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+              g[u][t] = (ok && k0 + lane + 32 * t < K) ? __ldg(row + 32 * t) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t] += g[u][t];
+        }
+      }
+    } else {
+      for (int j = s0; j < s1; ++j) {
+        const int64_t b = b_begin + list[j];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int k = k0 + lane + 32 * t;
+          if (k < K) acc[t] += pull_grad(gs, f, b, K, k);
+        }
       }
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < NT; ++t) {
       const int k = k0 + lane + 32 * t;
-      if (k < K && k < k0 + kTableBwdKT) o[(int64_t)v * K + k] = acc[t];
+      if (k < K) o[(int64_t)v * K + k] = acc[t];
     }
   }
 }
 
+static int table_bwd_nt(int K) { return K <= 32 ? 1 : (K <= 64 ? 2 : 4); }
+
 static void table_bwd_config(const ckb_step_desc_t& d, int64_t B, int& splits, int64_t& chunk) {
-  // a CTA buckets at most 32768 samples (uint16 ids, 64 KB of shared memory)
+  // a CTA buckets at most 32768 samples (uint16 states + ids, 128 KB of shared memory)
   splits = ceil_div(B, 32768);
-  const int ktiles = ceil_div(d.k_out, kTableBwdKT);
+  const int ktiles = ceil_div(d.k_out, 32 * table_bwd_nt(d.k_out));
   const int64_t want = ceil_div(2 * kNumSMs, (int64_t)d.num_folds * ktiles);
   splits = (int)max64(splits, min64(want, ceil_div(B, 1024)));
   chunk = ceil_div(B, splits);
@@ -236,15 +295,16 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   int64_t chunk;
   table_bwd_config(d, c.B, splits, chunk);
   const int V = d.num_states;
-  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 2 + 16;
+  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 4 + 16;
   if (smem > 200 * 1024) {
     set_error("table_bwd: %d states do not fit shared memory", V);
     return CKB_ERR_UNSUPPORTED;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const size_t n = (size_t)d.num_folds * V * d.k_out;
@@ -257,9 +317,11 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
     out = (float*)c.ws;
   }
   GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
-  dim3 grid(splits, d.num_folds, ceil_div(d.k_out, kTableBwdKT));
-  table_bwd_kernel<<<grid, kTableBwdThreads, smem, c.stream>>>(
-      gs, d.scope_var, c.xT, c.x_is_float, c.maskT, c.mask_ld, out, c.B, d.k_out, V, chunk);
+  const int nt = table_bwd_nt(d.k_out);
+  dim3 grid(splits, d.num_folds, ceil_div(d.k_out, 32 * nt));
+  auto kern = nt == 1 ? table_bwd_kernel<1> : (nt == 2 ? table_bwd_kernel<2> : table_bwd_kernel<4>);
+  kern<<<grid, kTableBwdThreads, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
+                                                  c.mask_ld, out, c.B, d.k_out, V, chunk);
   CKB_LAUNCH_CHECK();
   c.launches++;
   if (splits > 1) return reduce_partials(out, dT, (int64_t)n, splits, c);
