@@ -62,6 +62,7 @@ int table_dense_bwd(const ckb_step_desc_t& d, Ctx& c);
 size_t table_dense_ws(const ckb_step_desc_t& d, int64_t B);
 int param_op_fwd(const ckb_param_op_t& op, Ctx& c);
 int param_op_bwd(const ckb_param_op_t& op, Ctx& c);
+int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c);
 
 size_t table_bwd_ws(const ckb_step_desc_t& d, int64_t B);
 size_t mixing_bwd_ws(const ckb_step_desc_t& d, int64_t B);

@@ -143,10 +143,110 @@ __global__ void dense_fwd_generic(DenseArgs a, int e_stride) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-output layers (Ko = 1: the root sum of a circuit).  One warp per sample, the weight
+// row in registers; the batch reduction of dW goes through per-block partials.
+// ------------------------------------------------------------------------------------------
+constexpr int kKo1MaxPerLane = 4;  // Kred <= 128
+
+__device__ __forceinline__ float ko1_load(const DenseArgs& a, int f, int64_t b, int lane, float* u) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < kKo1MaxPerLane; ++t) {
+    const int k = lane + 32 * t;
+    float v = -INFINITY;
+    if (k < a.Kred) {
+      if (!a.concat) {
+        v = 0.f;
+        for (int h = 0; h < a.H; ++h) v += in_row(a, f, h)[b * a.Ki + k];
+      } else {
+        const int h = k / a.Ki;
+        v = in_row(a, f, h)[b * a.Ki + (k - h * a.Ki)];
+      }
+    }
+    u[t] = v;
+    m = fmaxf(m, v);
+  }
+  return clamp_max(warp_max(m));
+}
+
+__global__ void dense_ko1_fwd_kernel(DenseArgs a) {
+  const int f = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float w[kKo1MaxPerLane];
+#pragma unroll
+  for (int t = 0; t < kKo1MaxPerLane; ++t)
+    w[t] = lane + 32 * t < a.Kred ? a.W[(int64_t)f * a.Kred + lane + 32 * t] : 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < a.B; b += (int64_t)gridDim.x * nwarps) {
+    float u[kKo1MaxPerLane];
+    const float m = ko1_load(a, f, b, lane, u);
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < kKo1MaxPerLane; ++t)
+      if (lane + 32 * t < a.Kred) s = fmaf(w[t], expf(u[t] - m), s);
+    s = warp_sum(s);
+    if (lane == 0) a.y[(int64_t)f * a.B + b] = logf(s) + m;
+  }
+}
+
+__global__ void dense_ko1_bwd_kernel(DenseArgs a) {
+  __shared__ float red[8][32 * kKo1MaxPerLane];
+  const int f = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float w[kKo1MaxPerLane], dw[kKo1MaxPerLane];
+#pragma unroll
+  for (int t = 0; t < kKo1MaxPerLane; ++t) {
+    w[t] = lane + 32 * t < a.Kred ? a.W[(int64_t)f * a.Kred + lane + 32 * t] : 0.f;
+    dw[t] = 0.f;
+  }
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < a.B; b += (int64_t)gridDim.x * nwarps) {
+    float u[kKo1MaxPerLane];
+    const float m = ko1_load(a, f, b, lane, u);
+    const float g = pull_grad(a.gs, f, b, 1, 0);
+    const float r = (g == 0.f) ? 0.f : g * expf(m - a.y[(int64_t)f * a.B + b]);
+#pragma unroll
+    for (int t = 0; t < kKo1MaxPerLane; ++t) {
+      const int i = lane + 32 * t;
+      if (i < a.Kred) {
+        const float e = expf(u[t] - m);
+        dw[t] = fmaf(r, e, dw[t]);
+        const float du = e * r * w[t];
+        if (!a.concat) {
+          a.gin[((int64_t)f * a.B + b) * a.Ki + i] = du;
+        } else {
+          const int h = i / a.Ki;
+          a.gin[(((int64_t)f * a.H + h) * a.B + b) * a.Ki + (i - h * a.Ki)] = du;
+        }
+      }
+    }
+  }
+  if (a.dWp == nullptr) return;
+#pragma unroll
+  for (int t = 0; t < kKo1MaxPerLane; ++t) red[warp][lane + 32 * t] = dw[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.Kred; i += blockDim.x) {
+    float s2 = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) s2 += red[wv][i];
+    a.dWp[((int64_t)blockIdx.x * gridDim.y + f) * a.Kred + i] = s2;
+  }
+}
+
+static bool dense_ko1_ok(const DenseArgs& a) { return a.Ko == 1 && a.Kred <= 32 * kKo1MaxPerLane; }
+static int dense_ko1_blocks(int F, int64_t B) {
+  return (int)max64(1, min64(ceil_div(B, 8), ceil_div(4 * kNumSMs, F)));
+}
+
 static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
   {
     const int rc = dense_tc_fwd(a, F, c);  // tensor-core path for the hot shape
     if (rc <= 0) return rc;
+  }
+  if (dense_ko1_ok(a)) {
+    dim3 grid(dense_ko1_blocks(F, a.B), F);
+    dense_ko1_fwd_kernel<<<grid, 256, 0, c.stream>>>(a);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+    return CKB_OK;
   }
   if (a.Kred <= 128 && a.Ko <= 128 && a.H <= kMaxH) {
     const int kmax = max(a.Ko, 1);
@@ -404,6 +504,7 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
 }
 
 static size_t run_dense_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
+  if (Ko == 1 && Kred <= 32 * kKo1MaxPerLane) return (size_t)dense_ko1_blocks(F, B) * F * Kred * 4;
   const size_t tc = dense_tc_bwd_ws(F, H, Ko, Kred, B);
   if (!dense_small_ok(H, Ko, Kred)) return tc;
   int SW, splits;
@@ -419,6 +520,23 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
     if (rc <= 0) return rc;
   }
   const size_t n = (size_t)F * a.Ko * a.Kred;
+  if (dense_ko1_ok(a)) {
+    const int blocks = dense_ko1_blocks(F, a.B);
+    a.dWp = dW;
+    if (dW && blocks > 1) {
+      if (ws_bytes < blocks * n * 4) {
+        set_error("dense_bwd: workspace too small (%zu < %zu)", ws_bytes, blocks * n * 4);
+        return CKB_ERR_WORKSPACE;
+      }
+      a.dWp = (float*)ws;
+    }
+    dim3 grid(blocks, F);
+    dense_ko1_bwd_kernel<<<grid, 256, 0, c.stream>>>(a);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+    if (dW && blocks > 1) return reduce_partials(a.dWp, dW, (int64_t)n, blocks, c);
+    return CKB_OK;
+  }
   if (dense_small_ok(a.H, a.Ko, a.Kred)) {
     int SW, splits;
     int64_t chunk;

@@ -590,26 +590,39 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
       mbar_arrive(&s.e_done);
     }
     if (want_dw) {
-      // D2 quadrants: rows 0..63 = r_hi^T [e_hi | e_lo], rows 64..127 = r_lo^T [e_hi | (dropped)]
+      // D2 quadrants: rows 0..63 = r_hi^T [e_hi | e_lo], rows 64..127 = r_lo^T [e_hi | (dropped)].
+      // dW[o][i] = D2[o][i] + D2[o][64+i] + D2[64+o][i]: the lower half goes through shared
+      // memory (the operand tiles are dead once every MMA has completed).
       mbar_wait(&s.d2_full, 0);
       tc_fence_after_sync();
       const int row = q * 32 + lane;  // 0..127
       const int o = row & 63;
-      const int slab = 2 * blockIdx.x + (row >> 6);
-      float* out = a.dWp + (((int64_t)slab * gridDim.y + f) * KK + o) * KK + chalf * 32;
+      float* xch = s.rT[0];           // [64 columns][64 + 1] exchange buffer (spans rT[0..1])
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + chalf * 32;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[16], w[16];
-        tmem_ld16(taddr + c * 16, v);
-        if (row < 64) tmem_ld16(taddr + KK + c * 16, w);
+      float v[32];
+      tmem_ld16(taddr, v);
+      tmem_ld16(taddr + 16, v + 16);
+      if (row < 64) {
+        float w[32];
+        tmem_ld16(taddr + KK, w);
+        tmem_ld16(taddr + KK + 16, w + 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (row < 64) { t.x += w[j]; t.y += w[j + 1]; t.z += w[j + 2]; t.w += w[j + 3]; }
-          *reinterpret_cast<float4*>(out + c * 16 + j) = t;
-        }
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      } else {
+        tmem_ld_wait();
+        // stored [column][o] with a padded stride: the 32 lanes (32 rows o) hit 32 banks
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xch[(chalf * 32 + j) * (KK + 1) + o] = v[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpilogueWarps * 32) : "memory");
+      if (row < 64) {
+        float* out = a.dWp + (((int64_t)blockIdx.x * gridDim.y + f) * KK + o) * KK + chalf * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += xch[(chalf * 32 + j) * (KK + 1) + o];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
   }
@@ -638,7 +651,7 @@ size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
   if (Ko != KK || Kred != KK || H > 2) return 0;
   int splits, tpc;
   dense_tc_bwd_config(F, B, splits, tpc);
-  return (size_t)2 * splits * F * KK * KK * 4;
+  return splits > 1 ? (size_t)splits * F * KK * KK * 4 : 0;
 }
 
 int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
@@ -647,9 +660,10 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
   int splits, tpc;
   dense_tc_bwd_config(F, a.B, splits, tpc);
   const size_t n = (size_t)F * KK * KK;
-  if (dW) {
-    if (ws_bytes < 2 * splits * n * 4) {
-      set_error("dense_tc_bwd: workspace too small (%zu < %zu)", ws_bytes, 2 * splits * n * 4);
+  a.dWp = dW;
+  if (dW && splits > 1) {
+    if (ws_bytes < splits * n * 4) {
+      set_error("dense_tc_bwd: workspace too small (%zu < %zu)", ws_bytes, splits * n * 4);
       return CKB_ERR_WORKSPACE;
     }
     a.dWp = (float*)ws;
@@ -665,7 +679,7 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
   dense_tc_bwd_kernel<<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_fast_math);
   CKB_LAUNCH_CHECK();
   c.launches++;
-  if (dW) return reduce_partials(a.dWp, dW, (int64_t)n, 2 * splits, c);
+  if (dW && splits > 1) return reduce_partials(a.dWp, dW, (int64_t)n, splits, c);
   return CKB_OK;
 }
 

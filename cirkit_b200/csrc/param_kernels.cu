@@ -179,6 +179,93 @@ __global__ void lse_rows_kernel(const float* __restrict__ src, float* __restrict
   }
 }
 
+// ---- all softmax ops of a plan in one launch ------------------------------------------------
+// Every sum layer re-normalises its weights each step (TorchSoftmaxParameter, nodes.py:764-772);
+// a circuit has one such tensor per folded layer, mostly tiny, so they are batched: the op table
+// travels in the kernel parameters and a warp finds its (op, row) by a linear scan.
+constexpr int kMultiOps = 24;
+struct MultiSoftmax {
+  int n;
+  int cols[kMultiOps];
+  int64_t row_end[kMultiOps];  // cumulative row counts
+  const float* a[kMultiOps];   // fwd: src      bwd: W
+  const float* b[kMultiOps];   // fwd: unused   bwd: dW
+  float* out[kMultiOps];       // fwd: dst      bwd: dsrc
+};
+
+template <bool BWD>
+__global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t total = m.row_end[m.n - 1];
+  for (int64_t gr = (int64_t)blockIdx.x * nwarps + warp; gr < total; gr += (int64_t)gridDim.x * nwarps) {
+    int op = 0;
+    while (gr >= m.row_end[op]) ++op;
+    const int64_t r = gr - (op ? m.row_end[op - 1] : 0);
+    const int cols = m.cols[op];
+    const float* a = m.a[op] + r * cols;
+    float* out = m.out[op] + r * cols;
+    if (!BWD) {
+      float mx = -INFINITY;
+      for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, a[c]);
+      mx = warp_max(mx);
+      float z = 0.f;
+      for (int c = lane; c < cols; c += 32) z += expf(a[c] - mx);
+      z = warp_sum(z);
+      const float inv = 1.f / z;
+      for (int c = lane; c < cols; c += 32) out[c] = expf(a[c] - mx) * inv;
+    } else {
+      const float* g = m.b[op] + r * cols;
+      float dot = 0.f;
+      for (int c = lane; c < cols; c += 32) dot = fmaf(a[c], g[c], dot);
+      dot = warp_sum(dot);
+      for (int c = lane; c < cols; c += 32) out[c] = a[c] * (g[c] - dot);
+    }
+  }
+}
+
+// Runs every CKB_POP_SOFTMAX op of `ops` (forward, or backward when `bwd`); returns how many
+// launches it made through c.launches.
+int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
+  MultiSoftmax m;
+  m.n = 0;
+  int64_t rows = 0;
+  auto flush = [&]() -> int {
+    if (m.n == 0) return CKB_OK;
+    const int blocks = (int)max64(1, min64(ceil_div(rows, 8), 8 * kNumSMs));
+    if (bwd) multi_softmax_kernel<true><<<blocks, 256, 0, c.stream>>>(m);
+    else multi_softmax_kernel<false><<<blocks, 256, 0, c.stream>>>(m);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+    m.n = 0;
+    rows = 0;
+    return CKB_OK;
+  };
+  for (int i = 0; i < n_ops; ++i) {
+    const ckb_param_op_t& op = ops[i];
+    if (op.kind != CKB_POP_SOFTMAX) continue;
+    if (bwd) {
+      if (c.grads[op.src] == nullptr) continue;
+      if (c.grads[op.dst] == nullptr) {
+        set_error("softmax op: gradient of slot %d requested but slot %d has none", op.src, op.dst);
+        return CKB_ERR_INVALID;
+      }
+      m.a[m.n] = c.tensors[op.dst];
+      m.b[m.n] = c.grads[op.dst];
+      m.out[m.n] = c.grads[op.src];
+    } else {
+      m.a[m.n] = c.tensors[op.src];
+      m.b[m.n] = nullptr;
+      m.out[m.n] = c.tensors[op.dst];
+    }
+    m.cols[m.n] = op.cols;
+    rows += op.rows;
+    m.row_end[m.n] = rows;
+    if (++m.n == kMultiOps)
+      if (int rc = flush()) return rc;
+  }
+  return flush();
+}
+
 static int grid1d(int64_t n, int per_block) {
   return (int)max64(1, min64(ceil_div(n, per_block), 8 * kNumSMs));
 }

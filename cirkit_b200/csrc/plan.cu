@@ -220,9 +220,13 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
   if (int rc = make_ctx(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows,
                         tensors, nullptr, arena, nullptr, workspace, workspace_bytes, stream, c))
     return rc;
-  if (flags & CKB_RUN_PARAM_OPS)
+  if (flags & CKB_RUN_PARAM_OPS) {
+    // ops are independent of each other (one per parameter): softmaxes go out as one batch
+    if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), false, c)) return rc;
     for (const ckb_param_op_t& op : plan->ops)
-      if (int rc = param_op_fwd(op, c)) return rc;
+      if (op.kind != CKB_POP_SOFTMAX)
+        if (int rc = param_op_fwd(op, c)) return rc;
+  }
   for (int i = step_begin; i < step_end; ++i) {
     const ckb_step_desc_t& d = plan->steps[i];
     int rc = CKB_OK;
@@ -273,9 +277,12 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
     }
     if (rc != CKB_OK) return rc;
   }
-  if (flags & CKB_RUN_PARAM_OPS)
+  if (flags & CKB_RUN_PARAM_OPS) {
+    if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), true, c)) return rc;
     for (auto it = plan->ops.rbegin(); it != plan->ops.rend(); ++it)
-      if (int rc = param_op_bwd(*it, c)) return rc;
+      if (it->kind != CKB_POP_SOFTMAX)
+        if (int rc = param_op_bwd(*it, c)) return rc;
+  }
   plan->last_launches = c.launches;
   return CKB_OK;
 }
