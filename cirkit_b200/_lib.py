@@ -31,6 +31,7 @@ EXPORTS = (
     "ckb_plan_backward",
     "ckb_plan_last_launches",
     "ckb_set_option",
+    "ckb_debug_read",
 )
 OPT_TENSOR_CORES = 0
 
@@ -116,6 +117,8 @@ def load():
     lib.ckb_plan_last_launches.restype = i64
     lib.ckb_set_option.argtypes = [i32, i32]
     lib.ckb_set_option.restype = C.c_int
+    lib.ckb_debug_read.argtypes = [vp, C.c_size_t]
+    lib.ckb_debug_read.restype = C.c_int
     _lib = lib
     return lib
 

@@ -1,40 +1,32 @@
-// Tensor-core (tcgen05 / TMEM) version of the fused sum-product block for the hot shape
+// Tensor-core (tcgen05 / TMEM) versions of the fused sum-product block for the hot shape
 // Ki = Ko = 64 (Hadamard arity <= 2), sm_100a only.
 //
-//   y[b,o] = log( sum_i W[o,i] * exp(u[b,i] - m[b]) ) + m[b],   u = sum_h x_h,  m = max_i u
+//   forward   y[b,o] = log( sum_i W[o,i] * exp(u[b,i] - m[b]) ) + m[b],  u = sum_h x_h, m = max_i u
+//   backward  r = g / S,  d/du[b,i] = e[b,i] * sum_o r[b,o] W[o,i],  d/dW[o,i] = sum_b r[b,o] e[b,i]
 //
-// One CTA owns a fold and walks over 128-sample tiles with a warp-specialised pipeline
-// (two CTAs are resident per SM, so the phases of one overlap the other's):
-//
-//   transform warps : coalesced 16-byte loads of the H input rows (a half-warp per 256-byte row),
-//                     u -> max (shuffles) -> e = exp(u - m) -> split e into two tf32 terms
-//                     (hi, lo) written as 128B-swizzled UMMA operand tiles; the next tile's rows
-//                     are prefetched into L2 meanwhile                              [a_full/empty]
-//   MMA thread      : D(128x64, TMEM) = e_hi W_hi^T + e_lo W_hi^T + e_hi W_lo^T
-//                     (kind::tf32, three products = fp32-grade accuracy)        [tmem_full/empty]
-//   epilogue warps  : tcgen05.ld D -> log -> + m -> staged through shared memory so that every
-//                     store instruction writes whole 32-byte sectors of y (two TMEM buffers: the
-//                     epilogue of tile t overlaps the transform + MMA of tile t+1)
-//
-// The 64x64 weight slice of the fold is split (hi, lo) and swizzled into shared memory once per
-// CTA.  No intermediate of the block touches HBM: inputs are read once, y is written once.
+// All matrix products run as 3xTF32 on the 5th-generation tensor cores: every fp32 operand x is
+// split into hi + lo (hi = x rounded to tf32, lo = x - hi) and hi*hi + lo*hi + hi*lo is
+// accumulated in TMEM, which keeps fp32-grade accuracy (the dropped lo*lo term is 2^-22).
+// Operand tiles are written by the CUDA cores straight into 128-byte-swizzled shared-memory
+// tiles in the K-major UMMA layout, so nothing but the layer's inputs and outputs touches HBM.
 #include "dense.cuh"
 #include "sm100.cuh"
 
 namespace ckb {
 using namespace sm100;
 
+// Debug timeline: with CKB_OPT_TC_FAST_MATH bit 7 set, CTA (0,0) of the backward kernel records
+// clock64() at phase boundaries (read back with ckb_debug_read).
+__device__ long long g_dbg[512];
+
 namespace {
 
 constexpr int TM = 128;  // samples per tile (UMMA M)
 constexpr int KK = 64;   // Ki = Ko
-constexpr int kTransformWarps = 8, kEpilogueWarps = 4;
-constexpr int kMmaWarp = kTransformWarps + kEpilogueWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;  // 416
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
@@ -47,6 +39,74 @@ __device__ __forceinline__ float half_warp_max(float v) {
   for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+template <bool FAST>
+__device__ __forceinline__ float exp_(float x) {
+  return FAST ? fast_exp(x) : expf(x);
+}
+// exp(d) for d <= 0, d possibly -inf: one clamp keeps the MUFU path finite (exp(-104) flushes to 0)
+template <bool FAST>
+__device__ __forceinline__ float exp_nonpos(float d) {
+  return FAST ? fast_exp_finite(fmaxf(d, -104.f)) : expf(d);
+}
+// exp(min(d, 88)): finite, so that a zero gradient times it stays zero
+template <bool FAST>
+__device__ __forceinline__ float exp_capped(float d) {
+  return FAST ? fast_exp_finite(fminf(d, 88.f)) : expf(fminf(d, 88.f));
+}
+// 16-byte streaming load that leaves zeros when `ok` is false (no divergent branch)
+__device__ __forceinline__ float4 ldg_stream_if(const float* p, bool ok) {
+  float4 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+      : "l"(p), "r"((int)ok));
+  return v;
+}
+template <bool FAST>
+__device__ __forceinline__ float log_(float x) {
+  return FAST ? fast_log(x) : logf(x);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x);
+  split_tf32(v.y, hi.y, lo.y);
+  split_tf32(v.z, hi.z, lo.z);
+  split_tf32(v.w, hi.w, lo.w);
+}
+
+// Splits the fold's 64x64 weight slice into (hi, lo) swizzled K-major tiles.
+// TRANSPOSED = false: rows o, K = i  (forward:  S = e W^T)
+// TRANSPOSED = true : rows i, K = o  (backward: T = r W)
+template <bool TRANSPOSED>
+__device__ __forceinline__ void stage_weights(const float* Wf, uint32_t w_hi, uint32_t w_lo, int tid,
+                                              int nthreads) {
+  for (int idx = tid; idx < KK * KK; idx += nthreads) {
+    const int o = idx >> 6, i = idx & 63;
+    float hi, lo;
+    split_tf32(Wf[idx], hi, lo);
+    const int row = TRANSPOSED ? i : o, k = TRANSPOSED ? o : i;
+    const uint32_t off = (uint32_t)(k >> 5) * (KK * 128) + swz_off(row, k & 31);
+    sts32(w_hi + off, hi);
+    sts32(w_lo + off, lo);
+  }
+}
+
+// ==========================================================================================
+// Forward.  One CTA owns a fold and walks over 128-sample tiles with a warp-specialised pipeline
+// (two CTAs are resident per SM, so the phases of one overlap the other's):
+//   transform warps : coalesced 16-byte loads of the H input rows (a half-warp per 256-byte row),
+//                     u -> max (shuffles) -> e = exp(u - m) -> (hi, lo) operand tiles; the next
+//                     tile's rows are prefetched into L2 meanwhile                  [a_full/empty]
+//   MMA thread      : D(128x64, TMEM) = e_hi W_hi^T (+ correction accumulator e_lo W_hi^T +
+//                     e_hi W_lo^T)                                              [tmem_full/empty]
+//   epilogue warps  : tcgen05.ld D -> log -> + m -> staged through shared memory so that every
+//                     store instruction writes whole 32-byte sectors of y (two TMEM buffers: the
+//                     epilogue of tile t overlaps the transform + MMA of tile t+1)
+// ==========================================================================================
+constexpr int kTransformWarps = 8, kEpilogueWarps = 4;
+constexpr int kMmaWarp = kTransformWarps + kEpilogueWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;  // 416
 
 struct __align__(1024) FwdSmem {
   float a_hi[2][TM * 32];  // [k-block][row][32] swizzled               32 KB
@@ -59,7 +119,8 @@ struct __align__(1024) FwdSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, int tiles_per_cta, int fast_math) {
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, int tiles_per_cta) {
   extern __shared__ uint8_t smem_raw[];
   FwdSmem& s = *reinterpret_cast<FwdSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -69,7 +130,10 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
   if (n_tiles <= 0) return;
 
-  // ---- one-time setup: barriers, TMEM, weights
+  // input row pointers first: their (dependent) index loads overlap the rest of the setup
+  const float* row0 = in_row(a, f, 0);
+  const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
+
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tmem_full[i], 1);
@@ -80,17 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s.tmem_base, 256);
-  {
-    const float* Wf = a.W + (int64_t)f * KK * KK;  // [o][i]
-    for (int idx = tid; idx < KK * KK; idx += kThreads) {
-      const int o = idx >> 6, i = idx & 63;
-      float hi, lo;
-      split_tf32(Wf[idx], hi, lo);
-      const uint32_t off = swz_off(o, i & 31) >> 2;
-      s.w_hi[i >> 5][off] = hi;
-      s.w_lo[i >> 5][off] = lo;
-    }
-  }
+  stage_weights<false>(a.W + (int64_t)f * KK * KK, smem_u32(s.w_hi), smem_u32(s.w_lo), tid, kThreads);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -132,40 +186,46 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   } else if (warp < kTransformWarps) {
     // ================= transform: input rows -> (e_hi, e_lo) operand tiles + row max ==========
     const int l16 = lane & 15, half = lane >> 4;
-    const float* row0 = in_row(a, f, 0);
-    const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
-    uint8_t* ahi = reinterpret_cast<uint8_t*>(s.a_hi);
-    uint8_t* alo = reinterpret_cast<uint8_t*>(s.a_lo);
+    const uint32_t ahi = smem_u32(s.a_hi), alo = smem_u32(s.a_lo);
     // this lane's 16-byte chunk inside a swizzled row: k-block l16/8, chunk l16%8
     const uint32_t kb_off = (uint32_t)(l16 >> 3) * (TM * 128);
+    // this lane's element of row `warp*16 + half` of the current tile; row j adds 2 rows
+    const int64_t e0 = ((int64_t)t_begin * TM + warp * 16 + half) * KK + 4 * l16;
+    const float* p0 = row0 + e0;
+    const float* p1 = row1 ? row1 + e0 : nullptr;
+    int64_t rows_left = a.B - ((int64_t)t_begin * TM + warp * 16 + half);
+    // L2 warm-up of the tile after: this warp's 16 rows are 4 KB per input = 32 lines
+    const int pf_off = TM * KK + (warp * 16 - (warp * 16 + half)) * KK - 4 * l16 + lane * 32;
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
-      const int64_t b0 = (int64_t)(t_begin + it) * TM;
       // issue the loads of this tile before waiting for the operand buffers to drain
       float4 x[8];
+      if (rows_left + warp * 16 + half >= TM) {  // whole tile in range (uniform over the CTA)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = warp * 16 + 2 * j + half;
-        const int64_t b = b0 + r;
-        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < a.B) {
-          x[j] = ldg_stream(row0 + b * KK + 4 * l16);
-          if (row1) {
-            const float4 z = ldg_stream(row1 + b * KK + 4 * l16);
+        for (int j = 0; j < 8; ++j) x[j] = ldg_stream(p0 + 2 * j * KK);
+        if (p1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 z = ldg_stream(p1 + 2 * j * KK);
             x[j].x += z.x; x[j].y += z.y; x[j].z += z.z; x[j].w += z.w;
           }
         }
-      }
-      if (it + 1 < n_tiles) {  // warm L2 with the next tile while this one is processed
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int64_t b = b0 + TM + warp * 16 + 2 * j + half;
-          if (b < a.B && (l16 & 7) == 0) {
-            prefetch_l2(row0 + b * KK + 4 * l16);
-            if (row1) prefetch_l2(row1 + b * KK + 4 * l16);
-          }
+          const bool ok = rows_left > 2 * j;
+          x[j] = ldg_stream_if(p0 + 2 * j * KK, ok);
+          const float4 z = ldg_stream_if(p1 + 2 * j * KK, ok && p1 != nullptr);
+          x[j].x += z.x; x[j].y += z.y; x[j].z += z.z; x[j].w += z.w;
         }
       }
+      if (it + 1 < n_tiles && rows_left - TM > 15 - half) {
+        prefetch_l2(p0 + pf_off);
+        if (p1) prefetch_l2(p1 + pf_off);
+      }
+      p0 += TM * KK;
+      if (p1) p1 += TM * KK;
+      rows_left -= TM;
       mbar_wait(&s.a_empty, (it & 1) ^ 1);
       mbar_wait(&s.tmem_empty[buf], ((it >> 1) & 1) ^ 1);  // m_buf[buf] is free again
 #pragma unroll
@@ -173,21 +233,15 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         const int r = warp * 16 + 2 * j + half;
         const float4 u = x[j];
         const float m = clamp_max(half_warp_max(fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w))));
-        float4 hi, lo;
-        if (fast_math & 1) {
-          split_tf32(fast_exp(u.x - m), hi.x, lo.x);
-          split_tf32(fast_exp(u.y - m), hi.y, lo.y);
-          split_tf32(fast_exp(u.z - m), hi.z, lo.z);
-          split_tf32(fast_exp(u.w - m), hi.w, lo.w);
-        } else {
-          split_tf32(expf(u.x - m), hi.x, lo.x);
-          split_tf32(expf(u.y - m), hi.y, lo.y);
-          split_tf32(expf(u.z - m), hi.z, lo.z);
-          split_tf32(expf(u.w - m), hi.w, lo.w);
-        }
+        float4 e, hi, lo;
+        e.x = exp_nonpos<FAST>(u.x - m);
+        e.y = exp_nonpos<FAST>(u.y - m);
+        e.z = exp_nonpos<FAST>(u.z - m);
+        e.w = exp_nonpos<FAST>(u.w - m);
+        split4(e, hi, lo);
         const uint32_t off = kb_off + (uint32_t)r * 128u + ((((uint32_t)l16 ^ (uint32_t)r) & 7u) << 4);
-        *reinterpret_cast<float4*>(ahi + off) = hi;
-        *reinterpret_cast<float4*>(alo + off) = lo;
+        sts128(ahi + off, hi);
+        sts128(alo + off, lo);
         if (l16 == 0) s.m_buf[buf][r] = m;
       }
       fence_proxy_async_smem();
@@ -197,11 +251,11 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   } else {
     // ================= epilogue: TMEM -> log -> + m -> y =================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read (warps 8..11 -> 0..3)
-    float* stg = s.stage[q];
+    const uint32_t stg = smem_u32(s.stage[q]);
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
       const int64_t b0 = (int64_t)(t_begin + it) * TM + q * 32;
-      mbar_wait(&s.tmem_full[buf], (it >> 1) & 1);
+      mbar_wait_relaxed(&s.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after_sync();
       const float m = s.m_buf[buf][q * 32 + lane];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
@@ -211,31 +265,22 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         tmem_ld16(taddr + c * 16, v);
         tmem_ld16(taddr + KK + c * 16, w);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += w[j];
         // row `lane`, 16 columns -> staging (64-byte rows, chunk swizzled by (row>>1)&3)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4 o;
-          if (fast_math & 2) {
-            o.x = fast_log(v[4 * j]) + m;
-            o.y = fast_log(v[4 * j + 1]) + m;
-            o.z = fast_log(v[4 * j + 2]) + m;
-            o.w = fast_log(v[4 * j + 3]) + m;
-          } else {
-            o.x = logf(v[4 * j]) + m;
-            o.y = logf(v[4 * j + 1]) + m;
-            o.z = logf(v[4 * j + 2]) + m;
-            o.w = logf(v[4 * j + 3]) + m;
-          }
-          *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = o;
+          o.x = log_<FAST>(v[4 * j] + w[4 * j]) + m;
+          o.y = log_<FAST>(v[4 * j + 1] + w[4 * j + 1]) + m;
+          o.z = log_<FAST>(v[4 * j + 2] + w[4 * j + 2]) + m;
+          o.w = log_<FAST>(v[4 * j + 3] + w[4 * j + 3]) + m;
+          sts128(stg + (uint32_t)(lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) * 4u, o);
         }
         __syncwarp();
         // 8 rows x 64 bytes per instruction: whole sectors of y
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = i * 8 + (lane >> 2), ch = lane & 3;
-          const float4 o = *reinterpret_cast<const float4*>(stg + row * 16 + ((ch ^ ((row >> 1) & 3)) << 2));
+          const float4 o = lds128(stg + (uint32_t)(row * 16 + ((ch ^ ((row >> 1) & 3)) << 2)) * 4u);
           const int64_t b = b0 + row;
           if (b < a.B)
             *reinterpret_cast<float4*>(a.y + ((int64_t)f * a.B + b) * KK + c * 16 + ch * 4) = o;
@@ -254,63 +299,24 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   }
 }
 
-}  // namespace
-
-static int g_tc_enabled = -1;
-static int g_tc_fast_math = 3;
-void set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; }
-void set_tc_fast_math(int bits) { g_tc_fast_math = bits; }
-static bool tc_disabled() {
-  if (g_tc_enabled < 0) {
-    const char* e = getenv("CKB_DISABLE_TC");
-    g_tc_enabled = (e && e[0] == '1') ? 0 : 1;
-  }
-  return g_tc_enabled == 0;
-}
-
-int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
-  if (tc_disabled() || a.Ki != KK || a.Ko != KK || a.concat || a.H < 1 || a.H > 2 || a.Kred != KK)
-    return 1;
-  const size_t smem = sizeof(FwdSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_fwd_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  const int n_tiles = ceil_div(a.B, TM);
-  // ~4 CTAs per SM over the launch (2 resident), several tiles per CTA when the batch allows
-  int splits = (int)max64(1, min64(n_tiles, ceil_div(4 * kNumSMs, F)));
-  const int tiles_per_cta = ceil_div(n_tiles, splits);
-  splits = ceil_div(n_tiles, tiles_per_cta);
-  dim3 grid(splits, F);
-  dense_tc_fwd_kernel<<<grid, kThreads, smem, c.stream>>>(a, tiles_per_cta, g_tc_fast_math);
-  CKB_LAUNCH_CHECK();
-  c.launches++;
-  return CKB_OK;
-}
-
 // ==========================================================================================
-// Backward.  With e = exp(u - m), S = exp(y - m) (so the forward product is not recomputed) and
-// r[b,o] = g[b,o] / S[b,o]:
-//     d/du[b,i]  = e[b,i] * sum_o r[b,o] W[o,i]         GEMM 1  (M = samples, N = i, K = o)
-//     d/dW[o,i]  = sum_b r[b,o] e[b,i]                  GEMM 2  (M = o, N = i, K = samples)
-// r is contracted over o in GEMM 1 and over the samples in GEMM 2, and tf32 operands must be
-// K-major (MN-major tf32 only exists with the 32-byte-atom swizzle), so the transform warps write
-// r twice: as [sample][o] tiles for GEMM 1 and, after a 4x4 register transpose across lanes
-// (warp shuffles), as [o][sample] tiles for GEMM 2; e is only needed as [i][sample] (GEMM 2 and
-// the du epilogue, which reads it column-wise).  tf32 splits:
+// Backward.  r is contracted over o in GEMM 1 (T = r W) and over the samples in GEMM 2
+// (dW = r^T e), and tf32 operands must be K-major (MN-major tf32 only exists with the 32-byte
+// atom swizzle), so r is written twice: as [sample][o] tiles for GEMM 1 and, after a 4x4
+// register transpose across lanes (warp shuffles), as [o][sample] tiles for GEMM 2; e is only
+// needed as [i][sample] (GEMM 2 and the du epilogue, which reads it column-wise).
 //   GEMM 1: r_hi W_hi -> main accumulator, r_lo W_hi + r_hi W_lo -> correction accumulator;
 //   GEMM 2: ONE M=128 x N=128 instruction stream on the stacked operands [r_hi; r_lo]^T x
 //           [e_hi; e_lo]^T gives all four products in separate quadrants of a 128x128
 //           accumulator that stays in TMEM for the whole CTA (the lo*lo quadrant is dropped).
-// dW leaves the CTA as two partial slabs per batch split which the caller reduces.
+// 16 worker warps do both the operand transform of tile t and, once GEMM 1 has finished, its du
+// epilogue (each warp: 32 samples x 16 columns), so every warp is busy in both phases and the
+// registers left (one CTA per SM) hold the next tile's loads while the tensor core works.
+// du is staged through the r tile (dead after GEMM 1) so that stores cover whole sectors.
 // ==========================================================================================
-namespace {
-
-constexpr int kBwdTransformWarps = 16, kBwdEpilogueWarps = 8;
-constexpr int kBwdMmaWarp = kBwdTransformWarps + kBwdEpilogueWarps;
-constexpr int kBwdThreads = (kBwdMmaWarp + 1) * 32;  // 800
+constexpr int kWorkers = 16;
+constexpr int kBwdMmaWarp = kWorkers;
+constexpr int kBwdThreads = (kWorkers + 1) * 32;  // 544
 
 struct __align__(1024) BwdSmem {
   float r_hi[2][TM * 32];  // [o-block][sample][32]            GEMM 1 A operand        32 KB
@@ -319,7 +325,7 @@ struct __align__(1024) BwdSmem {
   float eT[4][128 * 32];   // [sample-block][hi i 0..63 | lo i 0..63][32 samples]       64 KB
   float w_hi[2][KK * 32];  // W^T: [o-block][i][32 o's]        GEMM 1 B operand        16 KB
   float w_lo[2][KK * 32];  //                                                           16 KB
-  uint64_t ab_full, ab_empty, e_done, d1_full[2], d1_empty[2], d2_full;
+  uint64_t ab_full, ab_empty, d1_full, d2_full;
   uint32_t tmem_base;
 };
 
@@ -339,15 +345,103 @@ __device__ __forceinline__ float4 transpose4(float4 v, int j) {
   if (q) { v.x = r0; v.y = r1; } else { v.z = r0; v.w = r1; }
   return v;
 }
-__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x);
-  split_tf32(v.y, hi.y, lo.y);
-  split_tf32(v.z, hi.z, lo.z);
-  split_tf32(v.w, hi.w, lo.w);
+
+struct BwdLoads {
+  float4 x0[2][2], x1[2][2], y[2][2], g[2][2];  // [pass][column half]
+};
+
+// What a worker thread needs to stream its share of the tiles: pointers to its first element of
+// the tile to be loaded next (row warp*8 + bsub, columns 4*og; pass p adds 4 rows, column half
+// ch adds 32 columns) and how many rows are left below that row.
+struct BwdStream {
+  const float *x0, *x1, *y, *g;  // x1 / g may be null (arity 1 / no consumer)
+  int64_t rows_left;             // B - (row of pass 0 in the next tile)
+};
+
+// MODE 2: the tile is complete, 1: rows must be checked, 0: nothing to load
+template <int MODE>
+__device__ __forceinline__ void bwd_load_pass(BwdLoads& L, const BwdStream& st, int p) {
+  if (MODE == 0) return;
+  const bool ok = MODE == 2 || st.rows_left > 4 * p;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const int o = p * 4 * KK + ch * 32;
+    if (MODE == 2) {
+      L.x0[p][ch] = ldg_stream(st.x0 + o);
+      if (st.x1) L.x1[p][ch] = ldg_stream(st.x1 + o);
+      L.y[p][ch] = ldg_stream(st.y + o);
+      if (st.g) L.g[p][ch] = ldg_stream(st.g + o);
+    } else {
+      L.x0[p][ch] = ldg_stream_if(st.x0 + o, ok);
+      L.x1[p][ch] = ldg_stream_if(st.x1 + o, ok && st.x1 != nullptr);
+      L.y[p][ch] = ldg_stream_if(st.y + o, ok);
+      L.g[p][ch] = ldg_stream_if(st.g + o, ok && st.g != nullptr);
+    }
+  }
 }
 
+// Shared-memory byte offsets of a worker thread's stores (all other terms are immediates).
+struct BwdOffsets {
+  uint32_t nat[2];  // [pass]: r as [sample][o]
+  uint32_t tr[2];   // [pass]: r / e as [unit][4 consecutive samples]
+};
+
+// One tile of the operand transform.  Rows that do not exist were loaded as zeros, which makes
+// their r rows zero (g = 0), so they drop out of both GEMMs without any further masking.
+template <bool FAST, int NEXT>
+__device__ __forceinline__ void bwd_transform(BwdLoads& L, const BwdStream& st, const BwdOffsets& off,
+                                              uint32_t smem_rhi, int bsub) {
+  constexpr uint32_t kRlo = offsetof(BwdSmem, r_lo) - offsetof(BwdSmem, r_hi);
+  constexpr uint32_t kRT = offsetof(BwdSmem, rT) - offsetof(BwdSmem, r_hi);
+  constexpr uint32_t kET = offsetof(BwdSmem, eT) - offsetof(BwdSmem, r_hi);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    float4 xu[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      xu[ch].x = L.x0[p][ch].x + L.x1[p][ch].x;
+      xu[ch].y = L.x0[p][ch].y + L.x1[p][ch].y;
+      xu[ch].z = L.x0[p][ch].z + L.x1[p][ch].z;
+      xu[ch].w = L.x0[p][ch].w + L.x1[p][ch].w;
+    }
+    float m = fmaxf(fmaxf(fmaxf(xu[0].x, xu[0].y), fmaxf(xu[0].z, xu[0].w)),
+                    fmaxf(fmaxf(xu[1].x, xu[1].y), fmaxf(xu[1].z, xu[1].w)));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    m = clamp_max(m);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      float4 e, rr, hi, lo;
+      e.x = exp_nonpos<FAST>(xu[ch].x - m);
+      e.y = exp_nonpos<FAST>(xu[ch].y - m);
+      e.z = exp_nonpos<FAST>(xu[ch].z - m);
+      e.w = exp_nonpos<FAST>(xu[ch].w - m);
+      rr.x = L.g[p][ch].x * exp_capped<FAST>(m - L.y[p][ch].x);
+      rr.y = L.g[p][ch].y * exp_capped<FAST>(m - L.y[p][ch].y);
+      rr.z = L.g[p][ch].z * exp_capped<FAST>(m - L.y[p][ch].z);
+      rr.w = L.g[p][ch].w * exp_capped<FAST>(m - L.y[p][ch].w);
+      const uint32_t a_nat = smem_rhi + off.nat[p] + ch * (TM * 128);
+      const uint32_t a_tr = smem_rhi + off.tr[p] + ch * (32 * 128);
+      split4(rr, hi, lo);
+      sts128(a_nat, hi);
+      sts128(a_nat + kRlo, lo);
+      split4(transpose4(rr, bsub), hi, lo);
+      sts128(a_tr + kRT, hi);
+      sts128(a_tr + kRT + 64 * 128, lo);  // (64 + u) & 7 == u & 7: same swizzle
+      split4(transpose4(e, bsub), hi, lo);
+      sts128(a_tr + kET, hi);
+      sts128(a_tr + kET + 64 * 128, lo);
+    }
+    // this pass's registers are free again: refill them with the next tile's rows right away,
+    // so the requests are spread over the transform and have a whole tile period to land
+    bwd_load_pass<NEXT>(L, st, p);
+  }
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) {
+dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -356,37 +450,44 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
   if (n_tiles <= 0) return;
+  const bool dbg = (flags & 128) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#ifdef CKB_TIMELINE
+#define DBG(slot) do { if (dbg) g_dbg[slot] = clock64(); } while (0)
+#else
+#define DBG(slot) do { (void)dbg; } while (0)
+#endif
+  if (tid == 0) DBG(0);
+
+  // row pointers first: their dependent index loads overlap the rest of the setup
+  const float* row0 = in_row(a, f, 0);
+  const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
+  const float* yrow = a.y + (int64_t)f * a.B * KK;
+  const float* grow0 = nullptr;
+  int n_cons = 1, cons0 = 0;
+  if (a.gs.cons_ptr == nullptr) {
+    grow0 = a.gs.garena + (int64_t)f * a.gs.B * KK;
+  } else {
+    cons0 = a.gs.cons_ptr[f];
+    n_cons = a.gs.cons_ptr[f + 1] - cons0;
+    if (n_cons > 0) grow0 = a.gs.garena + a.gs.B * a.gs.cons_rows[cons0];
+  }
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.d1_full[i], 1);
-      mbar_init(&s.d1_empty[i], kBwdEpilogueWarps * 32);
-    }
-    mbar_init(&s.ab_full, kBwdTransformWarps);
+    mbar_init(&s.ab_full, kWorkers);
     mbar_init(&s.ab_empty, 1);
-    mbar_init(&s.e_done, kBwdEpilogueWarps * 32);
+    mbar_init(&s.d1_full, 1);
     mbar_init(&s.d2_full, 1);
     fence_barrier_init();
   }
-  if (warp == kBwdMmaWarp) tmem_alloc(&s.tmem_base, 512);
-  {
-    // W^T image: rows i, K = o
-    const float* Wf = a.W + (int64_t)f * KK * KK;  // [o][i]
-    for (int idx = tid; idx < KK * KK; idx += kBwdThreads) {
-      const int o = idx >> 6, i = idx & 63;
-      float hi, lo;
-      split_tf32(Wf[idx], hi, lo);
-      const uint32_t off = swz_off(i, o & 31) >> 2;
-      s.w_hi[o >> 5][off] = hi;
-      s.w_lo[o >> 5][off] = lo;
-    }
-  }
+  if (warp == kBwdMmaWarp) tmem_alloc(&s.tmem_base, 256);
+  stage_weights<true>(a.W + (int64_t)f * KK * KK, smem_u32(s.w_hi), smem_u32(s.w_lo), tid, kBwdThreads);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
-  constexpr uint32_t kD2Col = 256;  // D1 buffers: [0,128) and [128,256); D2: [256,384)
+  constexpr uint32_t kD2Col = 128;  // D1: [0,128) (main | correction); D2: [128,256)
+  if (tid == 0) DBG(1);
 
   if (warp == kBwdMmaWarp) {
     // ================= MMA issuer =================
@@ -397,15 +498,14 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
       const uint32_t w_addr[2] = {smem_u32(s.w_hi), smem_u32(s.w_lo)};
       const uint32_t rT_addr = smem_u32(s.rT), eT_addr = smem_u32(s.eT);
       for (int it = 0; it < n_tiles; ++it) {
-        const int buf = it & 1;
-        mbar_wait(&s.d1_empty[buf], ((it >> 1) & 1) ^ 1);
         mbar_wait(&s.ab_full, it & 1);
         tc_fence_after_sync();
+        if (it < 4) DBG(16 + it * 8 + 0);
         // ---- GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
 #pragma unroll
         for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
           const uint32_t ab = r_addr[p == 1 ? 1 : 0], wb = w_addr[p == 2 ? 1 : 0];
-          const uint32_t d = tmem_base + buf * 128 + (p == 0 ? 0 : KK);
+          const uint32_t d = tmem_base + (p == 0 ? 0 : KK);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // 8 o's per step
             const uint64_t da = make_desc(ab + (ks >> 2) * (TM * 128) + (ks & 3) * 32, 16, 1024);
@@ -413,7 +513,7 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
             mma_tf32(d, da, db, idesc1, (p == 2 || ks) ? 1u : 0u);
           }
         }
-        mma_commit(&s.d1_full[buf]);
+        mma_commit(&s.d1_full);
         // ---- GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
         if (want_dw) {
 #pragma unroll
@@ -424,170 +524,131 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
           }
         }
         mma_commit(&s.ab_empty);
+        if (it < 4) DBG(16 + it * 8 + 1);
       }
       mma_commit(&s.d2_full);
     }
-  } else if (warp < kBwdTransformWarps) {
-    // ================= transform: rows -> r, r^T, e^T operand tiles =================
+  } else {
+    // ================= workers: operand transform, then du epilogue =================
     const int og = lane >> 2, bsub = lane & 3;  // 16-byte chunk within a 32-column half; row in group
-    const float* row0 = in_row(a, f, 0);
-    const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
-    const float* yrow = a.y + (int64_t)f * a.B * KK;
-    const float* grow[kMaxCons];
-    int n_cons = 1;
-    if (a.gs.cons_ptr == nullptr) {
-      grow[0] = a.gs.garena + (int64_t)f * a.gs.B * KK;
-    } else {
-      const int c0 = a.gs.cons_ptr[f];
-      n_cons = a.gs.cons_ptr[f + 1] - c0;
+    const int q = warp & 3;                     // TMEM lane quadrant for the epilogue
+    const int cg = warp >> 2;                   // epilogue column group: columns 16*cg .. 16*cg+15
+    const uint32_t rhi = smem_u32(s.r_hi);
+    const uint32_t eT = smem_u32(s.eT);
+    const uint32_t stg = rhi + (uint32_t)warp * 2048u;  // 32 rows x 16 columns, inside the dead r tile
+
+    BwdOffsets off;
 #pragma unroll
-      for (int c = 0; c < kMaxCons; ++c)
-        grow[c] = c < n_cons ? a.gs.garena + a.gs.B * a.gs.cons_rows[c0 + c] : nullptr;
+    for (int p = 0; p < 2; ++p) {
+      const uint32_t r = warp * 8 + p * 4 + bsub;           // sample row inside the tile
+      off.nat[p] = r * 128u + ((((uint32_t)og ^ r) & 7u) << 4);
+      const uint32_t u = 4u * og + bsub;                    // unit (mod 32) this lane owns afterwards
+      const uint32_t chunk = ((r & 31u) >> 2);              // 16-byte chunk of the 4 samples
+      off.tr[p] = (r >> 5) * (128 * 128) + u * 128u + (((chunk ^ u) & 7u) << 4);
     }
-    uint8_t* rhi = reinterpret_cast<uint8_t*>(s.r_hi);
-    uint8_t* rlo = reinterpret_cast<uint8_t*>(s.r_lo);
-    uint8_t* rT = reinterpret_cast<uint8_t*>(s.rT);
-    uint8_t* eT = reinterpret_cast<uint8_t*>(s.eT);
+    BwdStream st;
+    {
+      const int64_t row = (int64_t)t_begin * TM + warp * 8 + bsub;
+      const int64_t e0 = row * KK + 4 * og;
+      st.x0 = row0 + e0;
+      st.x1 = row1 ? row1 + e0 : nullptr;
+      st.y = yrow + e0;
+      st.g = n_cons > 0 ? grow0 + e0 : nullptr;
+      st.rows_left = a.B - row;
+    }
+    auto advance = [&]() {
+      st.x0 += TM * KK;
+      if (st.x1) st.x1 += TM * KK;
+      st.y += TM * KK;
+      if (st.g) st.g += TM * KK;
+      st.rows_left -= TM;
+    };
+
+    // du stores: rows q*32 + (lane>>2) + 8i of the tile, columns cg*16 + (lane&3)*4 ..+3
+    float* pdu = a.gin + ((int64_t)f * a.B + (int64_t)t_begin * TM + q * 32 + (lane >> 2)) * KK +
+                 cg * 16 + (lane & 3) * 4;
+    int64_t du_left = a.B - ((int64_t)t_begin * TM + q * 32 + (lane >> 2));
+    const bool store_du = !(flags & 32);
+
+    BwdLoads L;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+        L.x0[p][ch] = L.x1[p][ch] = L.y[p][ch] = L.g[p][ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bwd_load_pass<1>(L, st, 0);
+    bwd_load_pass<1>(L, st, 1);
+    advance();
     for (int it = 0; it < n_tiles; ++it) {
       const int64_t b0 = (int64_t)(t_begin + it) * TM;
+      if (warp == 0 && it < 4) DBG(16 + it * 8 + 2);
+      // every worker has finished the previous epilogue (reads of eT / the staging area) and both
+      // GEMMs of the previous tile have completed: the operand tiles may be overwritten
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
+      mbar_wait(&s.ab_empty, (it & 1) ^ 1);
+      if (warp == 0 && it < 4) DBG(16 + it * 8 + 3);
+      if (n_cons > 1) {  // rare (DAG-shaped circuits): add the other consumers' rows to g
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int rbase = warp * 8 + pass * 4;  // 4 consecutive samples handled by this warp
-        const int r = rbase + bsub;
-        const int64_t b = b0 + r;
-        const bool ok = b < a.B;
-        float4 xu[2], yv[2], gv[2];
+        for (int p = 0; p < 2; ++p) {
+          const int64_t b = b0 + warp * 8 + p * 4 + bsub;
+          for (int c = 1; c < n_cons; ++c) {
+            const float* gr = a.gs.garena + a.gs.B * a.gs.cons_rows[cons0 + c] + b * KK + 4 * og;
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          xu[ch] = yv[ch] = gv[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            const int64_t o = b * KK + 32 * ch + 4 * og;
-            xu[ch] = ldg_stream(row0 + o);
-            if (row1) {
-              const float4 z = ldg_stream(row1 + o);
-              xu[ch].x += z.x; xu[ch].y += z.y; xu[ch].z += z.z; xu[ch].w += z.w;
+            for (int ch = 0; ch < 2; ++ch) {
+              const float4 z = ldg_stream_if(gr + 32 * ch, b < a.B);
+              L.g[p][ch].x += z.x; L.g[p][ch].y += z.y; L.g[p][ch].z += z.z; L.g[p][ch].w += z.w;
             }
-            yv[ch] = ldg_stream(yrow + o);
-#pragma unroll
-            for (int c = 0; c < kMaxCons; ++c)
-              if (c < n_cons) {
-                const float4 z = ldg_stream(grow[c] + o);
-                gv[ch].x += z.x; gv[ch].y += z.y; gv[ch].z += z.z; gv[ch].w += z.w;
-              }
           }
-        }
-        if (pass == 0) {
-          // operand tiles of the previous tile must be drained (both GEMMs + the du epilogue)
-          mbar_wait(&s.ab_empty, (it & 1) ^ 1);
-          mbar_wait(&s.e_done, (it & 1) ^ 1);
-        }
-        float m = fmaxf(fmaxf(fmaxf(xu[0].x, xu[0].y), fmaxf(xu[0].z, xu[0].w)),
-                        fmaxf(fmaxf(xu[1].x, xu[1].y), fmaxf(xu[1].z, xu[1].w)));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-        m = clamp_max(m);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float4 e, rr, hi, lo;
-          if (fast_math & 1) {
-            e.x = ok ? fast_exp(xu[ch].x - m) : 0.f;
-            e.y = ok ? fast_exp(xu[ch].y - m) : 0.f;
-            e.z = ok ? fast_exp(xu[ch].z - m) : 0.f;
-            e.w = ok ? fast_exp(xu[ch].w - m) : 0.f;
-            // m - y = -log S may be positive: fast_exp is exact enough there too (|x| small)
-            rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * fast_exp(m - yv[ch].x);
-            rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * fast_exp(m - yv[ch].y);
-            rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * fast_exp(m - yv[ch].z);
-            rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * fast_exp(m - yv[ch].w);
-          } else {
-            e.x = ok ? expf(xu[ch].x - m) : 0.f;
-            e.y = ok ? expf(xu[ch].y - m) : 0.f;
-            e.z = ok ? expf(xu[ch].z - m) : 0.f;
-            e.w = ok ? expf(xu[ch].w - m) : 0.f;
-            rr.x = gv[ch].x == 0.f ? 0.f : gv[ch].x * expf(m - yv[ch].x);
-            rr.y = gv[ch].y == 0.f ? 0.f : gv[ch].y * expf(m - yv[ch].y);
-            rr.z = gv[ch].z == 0.f ? 0.f : gv[ch].z * expf(m - yv[ch].z);
-            rr.w = gv[ch].w == 0.f ? 0.f : gv[ch].w * expf(m - yv[ch].w);
-          }
-          // r as [sample][o]
-          split4(rr, hi, lo);
-          const uint32_t off = (uint32_t)ch * (TM * 128) + (uint32_t)r * 128u +
-                               ((((uint32_t)og ^ (uint32_t)r) & 7u) << 4);
-          *reinterpret_cast<float4*>(rhi + off) = hi;
-          *reinterpret_cast<float4*>(rlo + off) = lo;
-          // r and e as [unit][4 consecutive samples]
-          const uint32_t u = 32u * ch + 4u * og + bsub;          // unit this lane owns afterwards
-          const uint32_t chunk = ((uint32_t)rbase & 31u) >> 2;   // 16-byte chunk of the 4 samples
-          const uint32_t blk = ((uint32_t)rbase >> 5) * (128 * 128);
-          const uint32_t off_hi = blk + u * 128u + (((chunk ^ u) & 7u) << 4);
-          const uint32_t off_lo = blk + (64u + u) * 128u + (((chunk ^ (64u + u)) & 7u) << 4);
-          split4(transpose4(rr, bsub), hi, lo);
-          *reinterpret_cast<float4*>(rT + off_hi) = hi;
-          *reinterpret_cast<float4*>(rT + off_lo) = lo;
-          split4(transpose4(e, bsub), hi, lo);
-          *reinterpret_cast<float4*>(eT + off_hi) = hi;
-          *reinterpret_cast<float4*>(eT + off_lo) = lo;
         }
       }
+      if (it + 1 >= n_tiles) bwd_transform<FAST, 0>(L, st, off, rhi, bsub);
+      else if (st.rows_left >= TM - warp * 8 - bsub) bwd_transform<FAST, 2>(L, st, off, rhi, bsub);
+      else bwd_transform<FAST, 1>(L, st, off, rhi, bsub);
+      advance();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.ab_full);
-      if (it + 1 < n_tiles && og == 0) {  // warm L2 with the next tile (one lane per 128-byte line)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int64_t b = b0 + TM + warp * 8 + j * 4 + bsub;
-          if (b < a.B) {
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              const int64_t o = b * KK + 32 * ch;
-              prefetch_l2(row0 + o);
-              if (row1) prefetch_l2(row1 + o);
-              prefetch_l2(yrow + o);
-              if (n_cons > 0) prefetch_l2(grow[0] + o);
-            }
-          }
-        }
-      }
-    }
-  } else {
-    // ================= epilogue: du = e * T -> gin; finally dW partials =================
-    const int ew = warp - kBwdTransformWarps;  // 0..7
-    const int q = warp & 3;                    // TMEM lane quadrant (warps 16..23 -> 0..3,0..3)
-    const int chalf = ew >> 2;                 // which 32 of the 64 columns this warp handles
-    const uint8_t* eT = reinterpret_cast<const uint8_t*>(s.eT);
-    for (int it = 0; it < n_tiles; ++it) {
-      const int buf = it & 1;
-      const int64_t b = (int64_t)(t_begin + it) * TM + q * 32 + lane;
-      mbar_wait(&s.d1_full[buf], (it >> 1) & 1);
+      if (warp == 0 && it < 4) DBG(16 + it * 8 + 4);
+      // ---- du epilogue: rows 32q..32q+31, columns 16cg..16cg+15
+      mbar_wait(&s.d1_full, it & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + chalf * 32;
-      // e[b][i] = eT[(i)][b] + eT[(64 + i)][b]: sample block q, column `lane`
-      const uint32_t ecol = (uint32_t)q * (128 * 128) + ((uint32_t)lane & 3u) * 4u;
-      float* dst = a.gin + ((int64_t)f * a.B + b) * KK + chalf * 32;
+      if (warp == 0 && it < 4) DBG(16 + it * 8 + 5);
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 16;
+        // e[b][i] = eT[i][b] + eT[64 + i][b]: sample block q, column `lane`
+        const uint32_t ecol = eT + (uint32_t)q * (128 * 128) + ((uint32_t)lane & 3u) * 4u;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[16], w[16];
-        tmem_ld16(taddr + c * 16, v);
-        tmem_ld16(taddr + KK + c * 16, w);
-        tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {  // 8 columns at a time keeps the register footprint small
+          float v[8], w[8];
+          tmem_ld8(taddr + 8 * h, v);
+          tmem_ld8(taddr + KK + 8 * h, w);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float o[4];
+          for (int j = 0; j < 2; ++j) {
+            float o[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t i = (uint32_t)chalf * 32u + c * 16u + j + t;
-            const uint32_t ohi = ecol + i * 128u + (((((uint32_t)lane >> 2) ^ i) & 7u) << 4);
-            const uint32_t olo = ecol + (64u + i) * 128u + (((((uint32_t)lane >> 2) ^ (64u + i)) & 7u) << 4);
-            const float e = *reinterpret_cast<const float*>(eT + ohi) + *reinterpret_cast<const float*>(eT + olo);
-            o[t] = e * (v[j + t] + w[j + t]);
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t i = (uint32_t)cg * 16u + 8 * h + 4 * j + t;
+              const uint32_t ohi = ecol + i * 128u + (((((uint32_t)lane >> 2) ^ i) & 7u) << 4);
+              const float e = lds32(ohi) + lds32(ohi + 64u * 128u);
+              o[t] = e * (v[4 * j + t] + w[4 * j + t]);
+            }
+            sts128(stg + (uint32_t)(lane * 16 + (((2 * h + j) ^ ((lane >> 1) & 3)) << 2)) * 4u,
+                   make_float4(o[0], o[1], o[2], o[3]));
           }
-          if (b < a.B) *reinterpret_cast<float4*>(dst + c * 16 + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + (lane >> 2), ch = lane & 3;
+          const float4 o = lds128(stg + (uint32_t)(row * 16 + ((ch ^ ((row >> 1) & 3)) << 2)) * 4u);
+          if (du_left > 8 * i && store_du) *reinterpret_cast<float4*>(pdu + i * 8 * KK) = o;
+        }
+        pdu += TM * KK;
+        du_left -= TM;
       }
       tc_fence_before_sync();
-      mbar_arrive(&s.d1_empty[buf]);
-      mbar_arrive(&s.e_done);
+      if (warp == 0 && it < 4) DBG(16 + it * 8 + 6);
     }
     if (want_dw) {
       // D2 quadrants: rows 0..63 = r_hi^T [e_hi | e_lo], rows 64..127 = r_lo^T [e_hi | (dropped)].
@@ -595,43 +656,45 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int fast_math) 
       // memory (the operand tiles are dead once every MMA has completed).
       mbar_wait(&s.d2_full, 0);
       tc_fence_after_sync();
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");  // staging area is idle
       const int row = q * 32 + lane;  // 0..127
       const int o = row & 63;
-      float* xch = s.rT[0];           // [64 columns][64 + 1] exchange buffer (spans rT[0..1])
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + chalf * 32;
-      float v[32];
+      const uint32_t xch = smem_u32(s.rT);  // [64 columns][64 + 1] exchange buffer
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + cg * 16;
+      float v[16];
       tmem_ld16(taddr, v);
-      tmem_ld16(taddr + 16, v + 16);
       if (row < 64) {
-        float w[32];
+        float w[16];
         tmem_ld16(taddr + KK, w);
-        tmem_ld16(taddr + KK + 16, w + 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w[j];
+        for (int j = 0; j < 16; ++j) v[j] += w[j];
       } else {
         tmem_ld_wait();
         // stored [column][o] with a padded stride: the 32 lanes (32 rows o) hit 32 banks
 #pragma unroll
-        for (int j = 0; j < 32; ++j) xch[(chalf * 32 + j) * (KK + 1) + o] = v[j];
+        for (int j = 0; j < 16; ++j) sts32(xch + (uint32_t)((cg * 16 + j) * (KK + 1) + o) * 4u, v[j]);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpilogueWarps * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
       if (row < 64) {
-        float* out = a.dWp + (((int64_t)blockIdx.x * gridDim.y + f) * KK + o) * KK + chalf * 32;
+        float* out = a.dWp + (((int64_t)blockIdx.x * gridDim.y + f) * KK + o) * KK + cg * 16;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += xch[(chalf * 32 + j) * (KK + 1) + o];
+        for (int j = 0; j < 16; ++j) v[j] += lds32(xch + (uint32_t)((cg * 16 + j) * (KK + 1) + o) * 4u);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
   }
+  if (tid == 0) DBG(2);
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) DBG(3);
   if (warp == kBwdMmaWarp) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
+#undef DBG
 }
 
 void dense_tc_bwd_config(int F, int64_t B, int& splits, int& tiles_per_cta) {
@@ -641,11 +704,55 @@ void dense_tc_bwd_config(int F, int64_t B, int& splits, int& tiles_per_cta) {
   splits = ceil_div(n_tiles, tiles_per_cta);
 }
 
-bool dense_tc_bwd_ok(const DenseArgs& a) {
+bool dense_tc_ok(const DenseArgs& a) {
   return a.Ki == KK && a.Ko == KK && !a.concat && a.H >= 1 && a.H <= 2 && a.Kred == KK;
 }
 
 }  // namespace
+
+static int g_tc_enabled = -1;
+static int g_tc_flags = 3;  // bit 0: MUFU exp, bit 1: MUFU log (both set: the fast-math kernels)
+void set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; }
+void set_tc_fast_math(int bits) { g_tc_flags = bits; }
+static bool tc_disabled() {
+  if (g_tc_enabled < 0) {
+    const char* e = getenv("CKB_DISABLE_TC");
+    g_tc_enabled = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_tc_enabled == 0;
+}
+
+int debug_read(void* dst, size_t bytes) {
+  if (bytes > sizeof(long long) * 512) bytes = sizeof(long long) * 512;
+  CKB_CUDA_CHECK(cudaMemcpyFromSymbol(dst, g_dbg, bytes));
+  return CKB_OK;
+}
+
+int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
+  if (tc_disabled() || !dense_tc_ok(a)) return 1;
+  const size_t smem = sizeof(FwdSmem) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_fwd_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_fwd_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int n_tiles = ceil_div(a.B, TM);
+  // ~4 CTAs per SM over the launch (2 resident), several tiles per CTA when the batch allows
+  int splits = (int)max64(1, min64(n_tiles, ceil_div(4 * kNumSMs, F)));
+  const int tiles_per_cta = ceil_div(n_tiles, splits);
+  splits = ceil_div(n_tiles, tiles_per_cta);
+  dim3 grid(splits, F);
+  if ((g_tc_flags & 3) == 3)
+    dense_tc_fwd_kernel<true><<<grid, kThreads, smem, c.stream>>>(a, tiles_per_cta);
+  else
+    dense_tc_fwd_kernel<false><<<grid, kThreads, smem, c.stream>>>(a, tiles_per_cta);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
 
 size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
   if (Ko != KK || Kred != KK || H > 2) return 0;
@@ -655,7 +762,7 @@ size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
 }
 
 int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
-  if (tc_disabled() || !dense_tc_bwd_ok(a_in) || a_in.max_cons > kMaxCons) return 1;
+  if (tc_disabled() || !dense_tc_ok(a_in) || a_in.max_cons > kMaxCons) return 1;
   DenseArgs a = a_in;
   int splits, tpc;
   dense_tc_bwd_config(F, a.B, splits, tpc);
@@ -671,12 +778,17 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
   const size_t smem = sizeof(BwdSmem) + 1024;
   static bool attr = false;
   if (!attr) {
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel,
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   dim3 grid(splits, F);
-  dense_tc_bwd_kernel<<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_fast_math);
+  if ((g_tc_flags & 3) == 3)
+    dense_tc_bwd_kernel<true><<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);
+  else
+    dense_tc_bwd_kernel<false><<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);
   CKB_LAUNCH_CHECK();
   c.launches++;
   if (dW && splits > 1) return reduce_partials(a.dWp, dW, (int64_t)n, splits, c);

@@ -22,6 +22,7 @@ int transpose_input(const void* x, int dtype, int64_t B, int D, int64_t ld, void
 int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStream_t s);
 void set_tensor_cores(int on);
 void set_tc_fast_math(int bits);
+int debug_read(void* dst, size_t bytes);
 
 }  // namespace ckb
 
@@ -288,6 +289,8 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
 }
 
 int64_t ckb_plan_last_launches(const ckb_plan_t* plan) { return plan ? plan->last_launches : 0; }
+
+int ckb_debug_read(void* dst, size_t bytes) { return debug_read(dst, bytes); }
 
 int ckb_set_option(int32_t option, int32_t value) {
   switch (option) {

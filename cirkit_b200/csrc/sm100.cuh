@@ -28,18 +28,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-// try_wait suspends the thread in hardware until the phase completes or the time hint (ns)
-// expires; with a long hint a waiting warp costs no issue slots (an un-hinted try_wait returns
-// after a very short system limit and turns the wait into a busy loop that starves the warps
-// doing the work -- measured: 45 % of all issued instructions).
+// try_wait blocks in hardware for a short, implementation-defined time and returns whether the
+// phase has completed.  (Measured on B200: passing a long suspend-time hint makes waiters wake
+// up several microseconds late when the arrival comes from tcgen05.commit, so the latency
+// critical waits poll without a hint; waits that may be slow back off with nanosleep so that
+// they do not take issue slots from the warps doing the work.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -48,7 +49,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 20)) __trap();
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
@@ -157,37 +165,79 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- fp32 -> (tf32 hi, tf32 lo)
-// x = hi + lo up to 2^-22 |x|, both representable in tf32 (round-to-nearest, so the split is
-// unbiased): three tf32 products hi*hi + lo*hi + hi*lo then carry fp32-grade accuracy.
+// x = hi + lo exactly; hi is x rounded to tf32 (10 explicit mantissa bits, ties away from zero:
+// add half a tf32 ulp to the bit pattern and clear the low 13 bits -- two integer ALU ops, where
+// cvt.rna.tf32.f32 would go through the quarter-rate conversion pipe), lo = x - hi is exact in
+// fp32.  The tensor core reads only the upper 19 bits of each operand, i.e. it truncates lo to
+// tf32; lo is symmetric around zero, so that truncation is unbiased and costs 2^-22 |x|.
+// Three tf32 products hi*hi + lo*hi + hi*lo then carry fp32-grade accuracy.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
 
-// exp(x) for x <= 0 on the MUFU: 2^(x*log2e) with the rounding error of the product fed back
-// (Cody-Waite style), so the relative error is that of ex2.approx (2^-22) instead of growing
-// with |x|.  5 instructions instead of ~30 for expf.
-__device__ __forceinline__ float fast_exp(float x) {
-  x = fminf(fmaxf(x, -104.f), 88.f);  // keeps -inf / +inf inputs finite: exp(-104) flushes to 0
+// exp(x) on the MUFU for finite x: e = 2^t with t = fl(x*log2e), times (1 + d) where
+// d = x - t*ln2 is the part of the exponent the rounding of t lost (Cody-Waite, two fma's with
+// ln2 split into fl(ln2) + tail), so the relative error is that of ex2.approx (2^-22) instead
+// of growing with |x|.  5 instructions instead of ~30 for expf.  The caller clamps x into the
+// finite range first (-104 flushes to 0, 88 stays finite).
+__device__ __forceinline__ float fast_exp_finite(float x) {
   const float t = x * 1.4426950408889634f;
-  const float r = fmaf(x, 1.4426950408889634f, -t) + x * 1.9259629911266175e-8f;
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  return fmaf(e, r * 0.6931471805599453f, e);
+  float d = fmaf(t, -0.6931471805599453f, x);
+  d = fmaf(t, 1.9046542e-9f, d);  // fl(ln2) - ln2
+  return fmaf(e, d, e);
+}
+__device__ __forceinline__ float fast_exp(float x) {
+  return fast_exp_finite(fminf(fmaxf(x, -104.f), 88.f));
 }
 // log(x) on the MUFU: lg2.approx * ln2 (absolute error ~2^-22 * |log2 x| + 2^-24).
 __device__ __forceinline__ float fast_log(float x) {
   float l;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
   return l * 0.6931471805599453f;
+}
+
+// Explicit shared-state-space accesses with 32-bit addresses (the operand tiles are addressed
+// through computed byte offsets; generic pointers would cost 64-bit address math and LD/ST
+// instead of LDS/STS).
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // Byte offset of element (row, col) inside one 128B-swizzled block of [rows][32 fp32].

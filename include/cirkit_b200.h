@@ -168,6 +168,9 @@ int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 #define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels (default 3) */
 int ckb_set_option(int32_t option, int32_t value);
 
+/* Copies the device-side debug timeline (clock64 stamps of the tcgen05 kernels) to host memory. */
+int ckb_debug_read(void* dst, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif
