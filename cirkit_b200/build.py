@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("CKB_NVCC_EXTRA", "").split(), "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

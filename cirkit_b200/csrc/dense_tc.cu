@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
 // du is staged through the r tile (dead after GEMM 1) so that stores cover whole sectors.
 // ==========================================================================================
 constexpr int kWorkers = 16;
-constexpr int kBwdMmaWarp = kWorkers;
-constexpr int kBwdThreads = (kWorkers + 1) * 32;  // 544
+constexpr int kBwdThreads = kWorkers * 32;  // 512: 128 registers per thread, no spills
+constexpr int kGemm1Warp = 0, kGemm2Warp = 1;  // lane 0 of these workers issues the MMAs
 
 struct __align__(1024) BwdSmem {
   float r_hi[2][TM * 32];  // [o-block][sample][32]            GEMM 1 A operand        32 KB
@@ -474,12 +474,12 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
 
   if (tid == 0) {
     mbar_init(&s.ab_full, kWorkers);
-    mbar_init(&s.ab_empty, 1);
+    mbar_init(&s.ab_empty, want_dw ? 2 : 1);  // one commit per GEMM
     mbar_init(&s.d1_full, 1);
     mbar_init(&s.d2_full, 1);
     fence_barrier_init();
   }
-  if (warp == kBwdMmaWarp) tmem_alloc(&s.tmem_base, 256);
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
   stage_weights<true>(a.W + (int64_t)f * KK * KK, smem_u32(s.w_hi), smem_u32(s.w_lo), tid, kBwdThreads);
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -489,46 +489,7 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
   constexpr uint32_t kD2Col = 128;  // D1: [0,128) (main | correction); D2: [128,256)
   if (tid == 0) DBG(1);
 
-  if (warp == kBwdMmaWarp) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_tf32(TM, KK, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc_tf32(128, 128, 0, 0);
-      const uint32_t r_addr[2] = {smem_u32(s.r_hi), smem_u32(s.r_lo)};
-      const uint32_t w_addr[2] = {smem_u32(s.w_hi), smem_u32(s.w_lo)};
-      const uint32_t rT_addr = smem_u32(s.rT), eT_addr = smem_u32(s.eT);
-      for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&s.ab_full, it & 1);
-        tc_fence_after_sync();
-        if (it < 4) DBG(16 + it * 8 + 0);
-        // ---- GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
-          const uint32_t ab = r_addr[p == 1 ? 1 : 0], wb = w_addr[p == 2 ? 1 : 0];
-          const uint32_t d = tmem_base + (p == 0 ? 0 : KK);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 8 o's per step
-            const uint64_t da = make_desc(ab + (ks >> 2) * (TM * 128) + (ks & 3) * 32, 16, 1024);
-            const uint64_t db = make_desc(wb + (ks >> 2) * (KK * 128) + (ks & 3) * 32, 16, 1024);
-            mma_tf32(d, da, db, idesc1, (p == 2 || ks) ? 1u : 0u);
-          }
-        }
-        mma_commit(&s.d1_full);
-        // ---- GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
-        if (want_dw) {
-#pragma unroll
-          for (int ks = 0; ks < TM / 8; ++ks) {
-            const uint32_t o = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
-            mma_tf32(tmem_base + kD2Col, make_desc(rT_addr + o, 16, 1024),
-                     make_desc(eT_addr + o, 16, 1024), idesc2, (it || ks) ? 1u : 0u);
-          }
-        }
-        mma_commit(&s.ab_empty);
-        if (it < 4) DBG(16 + it * 8 + 1);
-      }
-      mma_commit(&s.d2_full);
-    }
-  } else {
+  {
     // ================= workers: operand transform, then du epilogue =================
     const int og = lane >> 2, bsub = lane & 3;  // 16-byte chunk within a 32-column half; row in group
     const int q = warp & 3;                     // TMEM lane quadrant for the epilogue
@@ -609,6 +570,53 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.ab_full);
       if (warp == 0 && it < 4) DBG(16 + it * 8 + 4);
+      // ---- MMA issue.  There is no dedicated MMA warp (a 17th warp would cap the kernel at 96
+      // registers per thread): lane 0 of worker 0 issues GEMM 1 and lane 0 of worker 1 GEMM 2
+      // once every worker has arrived; both workers would be waiting for GEMM 1 anyway.
+      if (warp == kGemm1Warp) {
+        if (lane == 0) {
+          mbar_wait(&s.ab_full, it & 1);
+          tc_fence_after_sync();
+          if (it < 4) DBG(16 + it * 8 + 0);
+          // GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
+          constexpr uint32_t idesc1 = make_idesc_tf32(TM, KK, 0, 0);
+          constexpr uint32_t kRlo = offsetof(BwdSmem, r_lo) - offsetof(BwdSmem, r_hi);
+          constexpr uint32_t kWhi = offsetof(BwdSmem, w_hi) - offsetof(BwdSmem, r_hi);
+          constexpr uint32_t kWlo = offsetof(BwdSmem, w_lo) - offsetof(BwdSmem, r_hi);
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
+            const uint32_t ab = rhi + (p == 1 ? kRlo : 0), wb = rhi + (p == 2 ? kWlo : kWhi);
+            const uint32_t d = tmem_base + (p == 0 ? 0 : KK);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // 8 o's per step
+              const uint64_t da = make_desc(ab + (ks >> 2) * (TM * 128) + (ks & 3) * 32, 16, 1024);
+              const uint64_t db = make_desc(wb + (ks >> 2) * (KK * 128) + (ks & 3) * 32, 16, 1024);
+              mma_tf32(d, da, db, idesc1, (p == 2 || ks) ? 1u : 0u);
+            }
+          }
+          mma_commit(&s.d1_full);
+          mma_commit(&s.ab_empty);
+          if (it < 4) DBG(16 + it * 8 + 1);
+        }
+        __syncwarp();
+      } else if (warp == kGemm2Warp && want_dw) {
+        if (lane == 0) {
+          mbar_wait(&s.ab_full, it & 1);
+          tc_fence_after_sync();
+          // GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
+          constexpr uint32_t idesc2 = make_idesc_tf32(128, 128, 0, 0);
+          constexpr uint32_t kRT = offsetof(BwdSmem, rT) - offsetof(BwdSmem, r_hi);
+#pragma unroll
+          for (int ks = 0; ks < TM / 8; ++ks) {
+            const uint32_t o = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
+            mma_tf32(tmem_base + kD2Col, make_desc(rhi + kRT + o, 16, 1024),
+                     make_desc(eT + o, 16, 1024), idesc2, (it || ks) ? 1u : 0u);
+          }
+          mma_commit(&s.ab_empty);
+          if (it + 1 == n_tiles) mma_commit(&s.d2_full);
+        }
+        __syncwarp();
+      }
       // ---- du epilogue: rows 32q..32q+31, columns 16cg..16cg+15
       mbar_wait(&s.d1_full, it & 1);
       tc_fence_after_sync();
@@ -690,7 +698,7 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
   tc_fence_before_sync();
   __syncthreads();
   if (tid == 0) DBG(3);
-  if (warp == kBwdMmaWarp) {
+  if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 256);
   }
