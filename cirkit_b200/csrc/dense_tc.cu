@@ -75,20 +75,23 @@ __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) 
   split_tf32(v.w, hi.w, lo.w);
 }
 
-// Splits the fold's 64x64 weight slice into (hi, lo) swizzled K-major tiles.
+// Splits the fold's 64x64 weight slice into (hi, lo) swizzled K-major tiles, stacked per k-block
+// as 128 rows [hi rows 0..63 | lo rows 0..63] so that ONE N=128 instruction multiplies an A tile
+// with both halves (W_hi -> accumulator columns 0..63, W_lo -> 64..127) and an N=64 instruction
+// on the same descriptor uses W_hi alone.
 // TRANSPOSED = false: rows o, K = i  (forward:  S = e W^T)
 // TRANSPOSED = true : rows i, K = o  (backward: T = r W)
+constexpr uint32_t kWBlock = 128 * 128;  // bytes per k-block of the stacked weight tile
 template <bool TRANSPOSED>
-__device__ __forceinline__ void stage_weights(const float* Wf, uint32_t w_hi, uint32_t w_lo, int tid,
-                                              int nthreads) {
+__device__ __forceinline__ void stage_weights(const float* Wf, uint32_t w, int tid, int nthreads) {
   for (int idx = tid; idx < KK * KK; idx += nthreads) {
     const int o = idx >> 6, i = idx & 63;
     float hi, lo;
     split_tf32(Wf[idx], hi, lo);
     const int row = TRANSPOSED ? i : o, k = TRANSPOSED ? o : i;
-    const uint32_t off = (uint32_t)(k >> 5) * (KK * 128) + swz_off(row, k & 31);
-    sts32(w_hi + off, hi);
-    sts32(w_lo + off, lo);
+    const uint32_t off = (uint32_t)(k >> 5) * kWBlock + swz_off(row, k & 31);
+    sts32(w + off, hi);
+    sts32(w + off + KK * 128, lo);  // (row + 64) & 7 == row & 7: same swizzle
   }
 }
 
@@ -111,8 +114,7 @@ constexpr int kThreads = (kMmaWarp + 1) * 32;  // 416
 struct __align__(1024) FwdSmem {
   float a_hi[2][TM * 32];  // [k-block][row][32] swizzled               32 KB
   float a_lo[2][TM * 32];  //                                           32 KB
-  float w_hi[2][KK * 32];  // [k-block][o][32] swizzled                 16 KB
-  float w_lo[2][KK * 32];  //                                           16 KB
+  float w[2][128 * 32];    // [k-block][hi o 0..63 | lo o 0..63][32] swizzled     32 KB
   float stage[kEpilogueWarps][32 * 16];  // per-warp 32 rows x 16 columns   8 KB
   float m_buf[2][TM];
   uint64_t a_full, a_empty, tmem_full[2], tmem_empty[2];
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s.tmem_base, 256);
-  stage_weights<false>(a.W + (int64_t)f * KK * KK, smem_u32(s.w_hi), smem_u32(s.w_lo), tid, kThreads);
+  stage_weights<false>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid, kThreads);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -154,9 +156,11 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TM, KK, 0, 0);
-      const uint32_t a_addr[2] = {smem_u32(s.a_hi), smem_u32(s.a_lo)};
-      const uint32_t w_addr[2] = {smem_u32(s.w_hi), smem_u32(s.w_lo)};
+      constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
+      constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
+      const uint64_t d_ahi = make_desc(smem_u32(s.a_hi), 16, 1024);
+      const uint64_t d_alo = make_desc(smem_u32(s.a_lo), 16, 1024);
+      const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
       for (int it = 0; it < n_tiles; ++it) {
         const int buf = it & 1;
         mbar_wait(&s.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -164,21 +168,19 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         tc_fence_after_sync();
         // The tensor core truncates when it folds a product group into the fp32 accumulator
         // (measured: ~0.6 ulp low per accumulating instruction), so the two small correction
-        // products get their own accumulator: only the 8 hi*hi steps touch the large one, and
-        // the epilogue adds the two in round-to-nearest fp32.
+        // products get their own accumulator (columns 64..127): only the 8 hi*hi steps touch the
+        // large one, and the epilogue adds the two in round-to-nearest fp32.
+        //   e_hi x [W_hi | W_lo]  (N = 128): main | correction
+        //   e_lo x  W_hi          (N =  64): correction
+        const uint32_t d = tmem_base + buf * 128;
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
-          const uint32_t ab = a_addr[p == 1 ? 1 : 0], wb = w_addr[p == 2 ? 1 : 0];
-          const uint32_t d = tmem_base + buf * 128 + (p == 0 ? 0 : KK);
+        for (int ks = 0; ks < 8; ++ks)
+          mma_tf32(d, desc_at(d_ahi, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+                   desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n128, ks ? 1u : 0u);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = make_desc(ab + kb * (TM * 128) + ks * 32, 16, 1024);
-              const uint64_t db = make_desc(wb + kb * (KK * 128) + ks * 32, 16, 1024);
-              mma_tf32(d, da, db, idesc, (p == 2 || kb || ks) ? 1u : 0u);
-            }
-        }
+        for (int ks = 0; ks < 8; ++ks)
+          mma_tf32(d + KK, desc_at(d_alo, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+                   desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n64, 1u);
         mma_commit(&s.a_empty);
         mma_commit(&s.tmem_full[buf]);
       }
@@ -323,8 +325,7 @@ struct __align__(1024) BwdSmem {
   float r_lo[2][TM * 32];  //                                                           32 KB
   float rT[4][128 * 32];   // [sample-block][hi o 0..63 | lo o 0..63][32 samples]       64 KB
   float eT[4][128 * 32];   // [sample-block][hi i 0..63 | lo i 0..63][32 samples]       64 KB
-  float w_hi[2][KK * 32];  // W^T: [o-block][i][32 o's]        GEMM 1 B operand        16 KB
-  float w_lo[2][KK * 32];  //                                                           16 KB
+  float w[2][128 * 32];    // W^T: [o-block][hi i 0..63 | lo i 0..63][32 o's]   GEMM 1 B    32 KB
   uint64_t ab_full, ab_empty, d1_full, d2_full;
   uint32_t tmem_base;
 };
@@ -480,7 +481,7 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 256);
-  stage_weights<true>(a.W + (int64_t)f * KK * KK, smem_u32(s.w_hi), smem_u32(s.w_lo), tid, kBwdThreads);
+  stage_weights<true>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid, kBwdThreads);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -562,6 +563,24 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
           }
         }
       }
+#ifdef CKB_TIMELINE
+      // experiments: bit 6 = never reload (compute on stale registers), bit 3 = no math (the loads
+      // are consumed by a dummy reduction)
+      if (flags & 8) {
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch)
+            acc += L.x0[p][ch].x + L.x1[p][ch].y + L.y[p][ch].z + L.g[p][ch].w + L.x0[p][ch].w;
+        if (acc == 1234.5f) sts32(rhi, acc);
+        if (it + 1 < n_tiles) {
+          if (st.rows_left >= TM - warp * 8 - bsub) { bwd_load_pass<2>(L, st, 0); bwd_load_pass<2>(L, st, 1); }
+          else { bwd_load_pass<1>(L, st, 0); bwd_load_pass<1>(L, st, 1); }
+        }
+      } else if (flags & 64) bwd_transform<FAST, 0>(L, st, off, rhi, bsub);
+      else
+#endif
       if (it + 1 >= n_tiles) bwd_transform<FAST, 0>(L, st, off, rhi, bsub);
       else if (st.rows_left >= TM - warp * 8 - bsub) bwd_transform<FAST, 2>(L, st, off, rhi, bsub);
       else bwd_transform<FAST, 1>(L, st, off, rhi, bsub);
@@ -579,21 +598,20 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
           tc_fence_after_sync();
           if (it < 4) DBG(16 + it * 8 + 0);
           // GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
-          constexpr uint32_t idesc1 = make_idesc_tf32(TM, KK, 0, 0);
+          //   r_hi x [W_hi | W_lo]  (N = 128): main | correction;  r_lo x W_hi (N = 64): correction
+          constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
+          constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
           constexpr uint32_t kRlo = offsetof(BwdSmem, r_lo) - offsetof(BwdSmem, r_hi);
-          constexpr uint32_t kWhi = offsetof(BwdSmem, w_hi) - offsetof(BwdSmem, r_hi);
-          constexpr uint32_t kWlo = offsetof(BwdSmem, w_lo) - offsetof(BwdSmem, r_hi);
+          constexpr uint32_t kW = offsetof(BwdSmem, w) - offsetof(BwdSmem, r_hi);
+          const uint64_t d_r = make_desc(rhi, 16, 1024);
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {  // hi*hi | lo*hi, hi*lo
-            const uint32_t ab = rhi + (p == 1 ? kRlo : 0), wb = rhi + (p == 2 ? kWlo : kWhi);
-            const uint32_t d = tmem_base + (p == 0 ? 0 : KK);
+          for (int ks = 0; ks < 8; ++ks)  // 8 o's per step
+            mma_tf32(tmem_base, desc_at(d_r, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+                     desc_at(d_r, kW + (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n128, ks ? 1u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {  // 8 o's per step
-              const uint64_t da = make_desc(ab + (ks >> 2) * (TM * 128) + (ks & 3) * 32, 16, 1024);
-              const uint64_t db = make_desc(wb + (ks >> 2) * (KK * 128) + (ks & 3) * 32, 16, 1024);
-              mma_tf32(d, da, db, idesc1, (p == 2 || ks) ? 1u : 0u);
-            }
-          }
+          for (int ks = 0; ks < 8; ++ks)
+            mma_tf32(tmem_base + KK, desc_at(d_r, kRlo + (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+                     desc_at(d_r, kW + (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n64, 1u);
           mma_commit(&s.d1_full);
           mma_commit(&s.ab_empty);
           if (it < 4) DBG(16 + it * 8 + 1);
@@ -606,11 +624,13 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
           // GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
           constexpr uint32_t idesc2 = make_idesc_tf32(128, 128, 0, 0);
           constexpr uint32_t kRT = offsetof(BwdSmem, rT) - offsetof(BwdSmem, r_hi);
+          constexpr uint32_t kETo = offsetof(BwdSmem, eT) - offsetof(BwdSmem, r_hi);
+          const uint64_t d_r = make_desc(rhi, 16, 1024);
 #pragma unroll
           for (int ks = 0; ks < TM / 8; ++ks) {
             const uint32_t o = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
-            mma_tf32(tmem_base + kD2Col, make_desc(rhi + kRT + o, 16, 1024),
-                     make_desc(eT + o, 16, 1024), idesc2, (it || ks) ? 1u : 0u);
+            mma_tf32(tmem_base + kD2Col, desc_at(d_r, kRT + o), desc_at(d_r, kETo + o), idesc2,
+                     (it || ks) ? 1u : 0u);
           }
           mma_commit(&s.ab_empty);
           if (it + 1 == n_tiles) mma_commit(&s.d2_full);

@@ -126,6 +126,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// The descriptor of the tile `off_bytes` further on in shared memory (same LBO / SBO / swizzle):
+// a 32-bit add on the low word.  Shared addresses are below 2^18, so the 14-bit start-address
+// field cannot carry into its neighbours.
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t off_bytes) {
+  const uint32_t lo = (uint32_t)base + (off_bytes >> 4);
+  return (base & 0xFFFFFFFF00000000ull) | lo;
+}
+
 // Instruction descriptor, kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
