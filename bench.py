@@ -202,13 +202,9 @@ def run_b200(args):
     flat_grads = None
     launches = 0
 
-    def sync_grads():
-        # data-parallel replicas: gradients of the mean log-likelihood are averaged over ranks
-        if world > 1 and not args.no_grad_allreduce:
-            for p in leaves:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+    from cirkit_b200.distributed import BatchShardedCircuit, all_gather_rows
 
-    ll_all = torch.empty(world * B, dtype=torch.float32, device=dev) if world > 1 else None
+    sharded = BatchShardedCircuit(cc)  # this rank's replica: rows [rank*B, (rank+1)*B) of the job
 
     def step(x):
         nonlocal launches
@@ -216,13 +212,15 @@ def run_b200(args):
             p.grad = None
         ll = cc(x)
         n = cc.runtime.last_launches
-        loss = -ll.mean()
+        loss = -ll.sum() / (world * B)  # this rank's share of the global-batch mean NLL
         loss.backward()
         launches = n + cc.runtime.last_launches
         if world > 1:
-            # the one collective of the data path: all-gather of the root log-densities
-            dist.all_gather_into_tensor(ll_all, ll.detach().reshape(-1))
-            sync_grads()
+            # the one collective of the data path: all-gather of the root log-densities ...
+            all_gather_rows(ll, world * B)
+            # ... and, for single-GPU gradient parity, the sum of the replicas' leaf gradients
+            if not args.no_grad_allreduce:
+                sharded.sync_gradients()
         return loss
 
     def barrier():
@@ -276,22 +274,25 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (rank 0, live, CUDA events around each step's launches)
     prof = profile_steps(cc.runtime, dev_x[0], leaves, iters=5)
     peak, peak_src = peaks()
+    # the dominant KERNEL: the step/direction with the largest time per launch (a step that is
+    # two kernels, like the fused table+dense one, is not a single roofline point)
     best = None
     for r in prof:
         for d in ("fwd", "bwd"):
             t = r.get(f"{d}_ms")
             if t is None:
                 continue
-            if best is None or t > best[0]:
-                best = (t, r, d)
-    t, r, d = best
+            per_launch = t / max(r.get(f"{d}_launches", 1), 1)
+            if best is None or per_launch > best[3]:
+                best = (t, r, d, per_launch)
+    t, r, d, _ = best
     nbytes = r[f"{d}_bytes"]
     achieved = nbytes / (t * 1e-3) / 1e9
     step_ms_sum = sum(q.get("fwd_ms", 0) + q.get("bwd_ms", 0) for q in prof)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None,
-        "kernel": f"step {r['step']} {r['kind']} {d} (F={r.get('F')})",
+        "traffic": ncu_traffic(f"{args.workload} B={B} {r['kind']} {d} F={r.get('F')}"),
+        "kernel": f"step {r['step']} {r['kind']} {d} (F={r.get('F')}, {r.get(d + '_launches', 1)} launch)",
         "kernel_ms": t, "kernel_share_of_step": t / step_ms_sum, "peak_source": peak_src,
         "algorithmic_bytes": nbytes,
         "whole_step": {
@@ -311,7 +312,7 @@ def run_b200(args):
         "config": {
             "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
             "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
-            "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, avg)"),
+            "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
             "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
             "leaves": "seeded N(0,1), seed 1234",
         },
@@ -326,6 +327,20 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel `key` names, from
+    the committed `ncu --set full` captures (profiles/*_traffic.json, written by
+    scripts/ncu_traffic.py); None when that kernel/shape has not been captured."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*_traffic.json")), reverse=True):
+        with open(path) as fh:
+            table = json.load(fh)
+        if key in table:
+            return table[key]["dram_bytes"]
+    return None
 
 
 def main():

@@ -492,8 +492,17 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
                                        int64_t n, int splits) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
+    // fixed left-to-right order (deterministic), but 16 independent loads in flight at a time
     float s = 0.f;
-    for (int j = 0; j < splits; ++j) s += partial[(int64_t)j * n + i];
+    int j = 0;
+    for (; j + 16 <= splits; j += 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldg(partial + (int64_t)(j + u) * n + i);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
+    }
+    for (; j < splits; ++j) s += __ldg(partial + (int64_t)j * n + i);
     out[i] = s;
   }
 }

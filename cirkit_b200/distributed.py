@@ -1,0 +1,136 @@
+"""Batch-sharded evaluation of one circuit on several GPUs.
+
+Every operation of a circuit is independent across samples, so the multi-GPU scheme is plain
+replication: each rank (one process per GPU, `torch.distributed`) holds the same plan and the same
+parameters, evaluates a contiguous block of the rows of `x`, and the only exchange on the data
+path is ONE all-gather of the root log-densities (4 bytes per sample and output).  For training,
+the leaf gradients of the replicas are summed with one all-reduce per parameter tensor so that
+every rank ends up with the gradient of the global-batch loss (single-GPU parity).
+
+The reference has no multi-device support (it evaluates wherever its tensors live,
+cirkit/backend/torch/circuits.py:242-278); this module is what a user of it would otherwise write
+around `DistributedDataParallel`.  It is backend-agnostic (nccl on GPUs, gloo in the CPU tests) and
+wraps any module mapping x:(B, D) -> (B, O, K).
+"""
+
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+
+def shard_rows(num_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous row block [begin, end) of `rank`: the first `num_rows % world_size` ranks get
+    one extra row, so blocks differ by at most one row and concatenate in rank order."""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError(f"invalid rank {rank} for world size {world_size}")
+    base, extra = divmod(num_rows, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def _world(group) -> tuple[int, int]:
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def all_gather_rows(local: Tensor, num_rows: int, group=None) -> Tensor:
+    """Concatenate the row blocks of all ranks (the blocks of `shard_rows(num_rows, ...)`) into
+    the global (num_rows, ...) tensor, on every rank.  One collective; blocks that are one row
+    short are padded for the exchange and trimmed afterwards."""
+    world, rank = _world(group)
+    if world == 1:
+        if local.shape[0] != num_rows:
+            raise ValueError(f"expected {num_rows} rows, got {local.shape[0]}")
+        return local
+    begin, end = shard_rows(num_rows, world, rank)
+    if local.shape[0] != end - begin:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} rows, its block has {end - begin}")
+    rows_max = -(-num_rows // world)
+    tail = local.shape[1:]
+    send = local.detach().contiguous()
+    if send.shape[0] < rows_max:  # uneven split: pad to the common block size
+        send = torch.cat([send, send.new_zeros((rows_max - send.shape[0], *tail))])
+    recv = send.new_empty((world * rows_max, *tail))
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if num_rows == world * rows_max:
+        return recv
+    blocks = []
+    for r in range(world):
+        b, e = shard_rows(num_rows, world, r)
+        blocks.append(recv[r * rows_max : r * rows_max + (e - b)])
+    return torch.cat(blocks)
+
+
+def all_reduce_gradients(params: Iterable[Tensor], *, average: bool = False, group=None) -> int:
+    """Sum (or average) `.grad` of every parameter over the ranks, in place.  Parameters without
+    a gradient on this rank contribute zeros, so all ranks issue the same collectives.  Returns
+    the number of bytes reduced."""
+    world, _ = _world(group)
+    total = 0
+    for p in params:
+        if not p.requires_grad:
+            continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        total += p.grad.numel() * p.grad.element_size()
+        if world > 1:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                p.grad.div_(world)
+    return total
+
+
+class BatchShardedCircuit(nn.Module):
+    """A replica of `circuit` that evaluates this rank's rows of a global batch.
+
+    forward(x_local)            -> local root log-densities (B_local, O, K), differentiable
+    log_likelihoods(x_local, B) -> all-gathered (B, O, K) on every rank (no gradient)
+    loss(x_local, B)            -> -sum(ll_local) / B: summing the gradients of this over the
+                                   ranks (sync_gradients) gives the gradient of the mean negative
+                                   log-likelihood of the global batch
+    """
+
+    def __init__(self, circuit: nn.Module, group=None) -> None:
+        super().__init__()
+        self.circuit = circuit
+        self.group = group
+
+    @property
+    def world_size(self) -> int:
+        return _world(self.group)[0]
+
+    @property
+    def rank(self) -> int:
+        return _world(self.group)[1]
+
+    def local_rows(self, num_rows: int) -> tuple[int, int]:
+        return shard_rows(num_rows, self.world_size, self.rank)
+
+    def shard(self, x_global: Tensor) -> Tensor:
+        begin, end = self.local_rows(x_global.shape[0])
+        return x_global[begin:end]
+
+    def forward(self, x_local: Tensor) -> Tensor:
+        return self.circuit(x_local)
+
+    def log_likelihoods(self, x_local: Tensor, num_rows: int) -> Tensor:
+        with torch.no_grad():
+            ll = self.circuit(x_local)
+        return all_gather_rows(ll, num_rows, self.group)
+
+    def loss(self, x_local: Tensor, num_rows: int) -> Tensor:
+        return -self.circuit(x_local).sum() / num_rows
+
+    def sync_gradients(self, *, average: bool = False) -> int:
+        return all_reduce_gradients(self.circuit.parameters(), average=average, group=self.group)
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Make every replica start from rank `src`'s parameters."""
+        if self.world_size > 1:
+            for p in self.circuit.parameters():
+                dist.broadcast(p.data, src=src, group=self.group)
