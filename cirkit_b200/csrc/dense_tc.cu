@@ -11,6 +11,7 @@
 // tiles in the K-major UMMA layout, so nothing but the layer's inputs and outputs touches HBM.
 #include "dense.cuh"
 #include "sm100.cuh"
+#include "tc_util.cuh"
 
 namespace ckb {
 using namespace sm100;
@@ -23,57 +24,6 @@ namespace {
 
 constexpr int TM = 128;  // samples per tile (UMMA M)
 constexpr int KK = 64;   // Ki = Ko
-
-__device__ __forceinline__ float4 ldg_stream(const float* p) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ float half_warp_max(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <bool FAST>
-__device__ __forceinline__ float exp_(float x) {
-  return FAST ? fast_exp(x) : expf(x);
-}
-// exp(d) for d <= 0, d possibly -inf: one clamp keeps the MUFU path finite (exp(-104) flushes to 0)
-template <bool FAST>
-__device__ __forceinline__ float exp_nonpos(float d) {
-  return FAST ? fast_exp_finite(fmaxf(d, -104.f)) : expf(d);
-}
-// exp(min(d, 88)): finite, so that a zero gradient times it stays zero
-template <bool FAST>
-__device__ __forceinline__ float exp_capped(float d) {
-  return FAST ? fast_exp_finite(fminf(d, 88.f)) : expf(fminf(d, 88.f));
-}
-// 16-byte streaming load that leaves zeros when `ok` is false (no divergent branch)
-__device__ __forceinline__ float4 ldg_stream_if(const float* p, bool ok) {
-  float4 v;
-  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
-      "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
-      "@q ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
-      : "l"(p), "r"((int)ok));
-  return v;
-}
-template <bool FAST>
-__device__ __forceinline__ float log_(float x) {
-  return FAST ? fast_log(x) : logf(x);
-}
-__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x);
-  split_tf32(v.y, hi.y, lo.y);
-  split_tf32(v.z, hi.z, lo.z);
-  split_tf32(v.w, hi.w, lo.w);
-}
 
 // Splits the fold's 64x64 weight slice into (hi, lo) swizzled K-major tiles, stacked per k-block
 // as 128 rows [hi rows 0..63 | lo rows 0..63] so that ONE N=128 instruction multiplies an A tile
@@ -331,21 +281,6 @@ struct __align__(1024) BwdSmem {
 };
 
 constexpr int kMaxCons = 4;  // consumer rows per fold the tensor-core path sums
-
-// 4x4 transpose across the 4 lanes that differ in their two low lane bits: on entry lane j holds
-// (row j, cols 0..3); on exit it holds (rows 0..3, col j).
-__device__ __forceinline__ float4 transpose4(float4 v, int j) {
-  const bool p = j & 1, q = j & 2;
-  float s0 = p ? v.x : v.y, s1 = p ? v.z : v.w;
-  float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-  if (p) { v.x = r0; v.z = r1; } else { v.y = r0; v.w = r1; }
-  s0 = q ? v.x : v.z;
-  s1 = q ? v.y : v.w;
-  r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
-  r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
-  if (q) { v.x = r0; v.y = r1; } else { v.z = r0; v.w = r1; }
-  return v;
-}
 
 struct BwdLoads {
   float4 x0[2][2], x1[2][2], y[2][2], g[2][2];  // [pass][column half]
@@ -742,13 +677,15 @@ static int g_tc_enabled = -1;
 static int g_tc_flags = 3;  // bit 0: MUFU exp, bit 1: MUFU log (both set: the fast-math kernels)
 void set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; }
 void set_tc_fast_math(int bits) { g_tc_flags = bits; }
-static bool tc_disabled() {
+bool tc_disabled() {
   if (g_tc_enabled < 0) {
     const char* e = getenv("CKB_DISABLE_TC");
     g_tc_enabled = (e && e[0] == '1') ? 0 : 1;
   }
   return g_tc_enabled == 0;
 }
+
+int tc_flags() { return g_tc_flags; }
 
 int debug_read(void* dst, size_t bytes) {
   if (bytes > sizeof(long long) * 512) bytes = sizeof(long long) * 512;
