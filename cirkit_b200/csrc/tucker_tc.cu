@@ -16,16 +16,32 @@
 // The tensor core truncates when it folds a product group into the fp32 accumulator (~0.6 ulp low
 // per accumulating instruction, measured).  Over the 512 k-steps of a Ki^2 = 4096 reduction that
 // would bias log S by ~1e-5 per layer, all with the same sign, so the forward accumulates in TMEM
-// only over chunks of 8 k-steps and folds the chunks into fp32 registers with round-to-nearest
-// adds (the same 8-step depth as the Ki = 64 sum-product block of dense_tc.cu).
-#include <type_traits>
-
+// only over chunks of 16 k-steps and folds the chunks into fp32 registers with round-to-nearest
+// adds; the two small correction products have their own accumulator.
 #include "dense.cuh"
 #include "sm100.cuh"
 #include "tc_util.cuh"
 
 namespace ckb {
 using namespace sm100;
+
+// Debug timeline (built with -DCKB_TIMELINE): CTA (0,0) of the forward kernel records clock64()
+// at pipeline events of its first k-blocks; read back with ckb_debug_read when bit 8 of
+// CKB_OPT_TC_FAST_MATH is set.
+__device__ long long g_dbg_tk[512];
+int tucker_debug_read(void* dst, size_t bytes) {
+  if (bytes > sizeof(long long) * 512) bytes = sizeof(long long) * 512;
+  CKB_CUDA_CHECK(cudaMemcpyFromSymbol(dst, g_dbg_tk, bytes));
+  return CKB_OK;
+}
+#ifdef CKB_TIMELINE
+#define TKDBG(kb, slot)                                                                    \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 24) g_dbg_tk[16 + (kb) * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TKDBG(kb, slot) do { } while (0)
+#endif
 
 namespace {
 
@@ -40,41 +56,61 @@ __device__ __forceinline__ float4 ldg_nc(const float* p) {
 }
 __device__ __forceinline__ float max4(const float4& v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
 
+// TMEM budget and shared-memory traffic shape all three kernels: a tf32 tcgen05.mma reads 32 bytes
+// of every operand row per instruction, so with both operands in shared memory (v1 of this file)
+// the 128 B/clk of the shared-memory crossbar, not the tensor pipe, set the pace (27 % pipe
+// utilisation measured).  The operand that is generated on the fly (the Kronecker rows, r, P^T)
+// is therefore written to TMEM with tcgen05.st and consumed as the A operand from there; only the
+// weight-side tiles travel through shared memory.
+//
 // ==========================================================================================
-// Forward.  CTA = (fold, 256 samples).  Warps 0-7: producers (one thread per sample row: the
-// Kronecker operand tile and a share of the weight tile per k-block of 32 reduction indices),
-// warps 8-15: chunk accumulation (TMEM -> registers) and the log epilogue.  Lane 0 of producer
-// warp 0 issues the MMAs of a k-block right after its own share of the tile (a 17th warp would
-// cap the kernel at 96 registers per thread: 5 warps on one scheduler's register file).
+// Forward.  CTA = (fold, 128 samples).  The reduction runs over 64 ring slots, one per index i of
+// the first input (64 reduction indices (i, j = 0..63) = 8 k-steps per slot).
+//   warps 0-7  : A producers; thread = (sample row, column half): e1[b,i] * e2[b,j] for its 32 j's
+//                -> (hi, lo) -> TMEM slot (tcgen05.st)
+//   warp 8     : weight loader: one 32 KB bulk copy (TMA engine) per slot of the pre-split image
+//                tucker_split_w_kernel wrote (splitting W inside every CTA, 16 per fold, made the
+//                weight producers the critical path: the generic->async proxy fence after their
+//                shared-memory stores also waits for the global loads they have in flight)
+//   warps 10-11: MMA issue.  Measured on B200: ~150 clk per mbarrier wait, ~80 per commit and
+//                ~50 per tcgen05.mma when one lane issues from a divergent branch, so the whole
+//                warp stays converged and the instructions are predicated on the elected lane
+//                (~25-35 clk per MMA), A and W share ONE full/empty barrier pair per slot, a
+//                k-step is two instructions: a_hi x [W_hi | W_lo] (N = 128: main | correction)
+//                and a_lo x W_hi (N = 64: correction), and the two warps take alternate chunks
+//   warps 12-15: chunk accumulation (TMEM -> fp32 registers every 16 k-steps) and the log epilogue
+// TMEM columns: (main | correction) accumulator pair x2 [0,256), A ring 2 x (hi 64 | lo 64) [256,512).
 // ==========================================================================================
-constexpr int kProdWarps = 8, kEpiWarps = 8;
-constexpr int kFwdThreads = (kProdWarps + kEpiWarps) * 32;  // 512
-constexpr int kChunkKb = 2;                          // k-blocks (of 4 k-steps) per TMEM chunk
-constexpr int kNumKb = KRED / 32;                    // 128
+constexpr int kFwdThreads = 512;
+constexpr int kNS = 2;            // ring depth
+constexpr int kChunkSlots = 2;    // slots (of 8 k-steps) per TMEM chunk
+constexpr uint32_t kColA = 256;
 
 struct __align__(1024) TkFwdSmem {
-  float a_hi[2][2][TM * 32];  // [stage][M tile][row][32] swizzled     64 KB
-  float a_lo[2][2][TM * 32];  //                                        64 KB
-  float w[2][128 * 32];       // [stage][hi o 0..63 | lo o 0..63][32]   32 KB
-  float msum[ROWS];
-  uint64_t full[2], empty[2], tfull[2], tempty[2];
+  float w[kNS][2][128 * 32];  // [slot][k-block][hi o 0..63 | lo o 0..63][32] swizzled   64 KB
+  float msum[TM];
+  uint64_t full[kNS], empty[kNS], mfull[2], mempty[2], turn[2];
   uint32_t tmem_base;
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(kFwdThreads, 1) tucker_tc_fwd_kernel(DenseArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1)
+tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
   extern __shared__ uint8_t smem_raw[];
   TkFwdSmem& s = *reinterpret_cast<TkFwdSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y;
-  const int64_t b0 = (int64_t)blockIdx.x * ROWS;
+  const int64_t b0 = (int64_t)blockIdx.x * TM;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.full[i], kProdWarps);
+    for (int i = 0; i < kNS; ++i) {
+      mbar_init(&s.full[i], 8 + 1);  // 8 A-producer warps + the weight copy (arrive.expect_tx)
       mbar_init(&s.empty[i], 1);
-      mbar_init(&s.tfull[i], 1);
-      mbar_init(&s.tempty[i], kEpiWarps * 32);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.mfull[i], 1);
+      mbar_init(&s.mempty[i], 128);
+      mbar_init(&s.turn[i], 1);
     }
     fence_barrier_init();
   }
@@ -84,139 +120,135 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tucker_tc_fwd_kernel(DenseArgs
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
 
-  if (warp < kProdWarps) {
-    // ================= producers =================
-    constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
-    constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
-    const uint64_t d_ahi = make_desc(smem_u32(s.a_hi), 16, 1024);
-    const uint64_t d_alo = make_desc(smem_u32(s.a_lo), 16, 1024);
-    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
-    const int p = tid;  // row inside the CTA
-    const int64_t b = b0 + p;
+  if (warp < 8) {
+    // ================= A producers =================
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int64_t b = b0 + row;
     const bool valid = b < a.B;
     const float* x1 = in_row(a, f, 0) + (valid ? b : 0) * KK;
     const float* x2 = in_row(a, f, 1) + (valid ? b : 0) * KK;
     float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) m1 = fmaxf(m1, max4(ldg_nc(x1 + 4 * c)));
-    m1 = clamp_max(m1);
-    float e2[KK];
-#pragma unroll
     for (int c = 0; c < 16; ++c) {
-      const float4 v = ldg_nc(x2 + 4 * c);
-      e2[4 * c] = v.x; e2[4 * c + 1] = v.y; e2[4 * c + 2] = v.z; e2[4 * c + 3] = v.w;
-      m2 = fmaxf(m2, max4(v));
+      m1 = fmaxf(m1, max4(ldg_nc(x1 + 4 * c)));
+      m2 = fmaxf(m2, max4(ldg_nc(x2 + 4 * c)));
     }
+    m1 = clamp_max(m1);
     m2 = clamp_max(m2);
+    float e2[32];  // [jh][16]: columns jh*32 + h*16 + c
 #pragma unroll
-    for (int j = 0; j < KK; ++j) e2[j] = valid ? exp_nonpos<FAST>(e2[j] - m2) : 0.f;
-    s.msum[p] = fmaxf(m1 + m2, -FLT_MAX);
-
-    // this thread's two 16-byte pieces of every weight k-block: rows o_a / o_a + 32, chunk wc
-    const int o_a = p >> 3, wc = p & 7;
-    const float* w0 = a.W + ((int64_t)f * KK + o_a) * KRED + wc * 4;
-    const float* w1 = w0 + (int64_t)32 * KRED;
-    const uint32_t w_off0 = (uint32_t)o_a * 128u + ((((uint32_t)wc ^ (uint32_t)o_a) & 7u) << 4);
-    const uint32_t w_off1 = w_off0 + 32u * 128u;  // (o_a + 32) & 7 == o_a & 7
-    const uint32_t r = (uint32_t)p & 127u, t = (uint32_t)p >> 7;
-    const uint32_t a_row = t * kTile + r * 128u;
-    const uint32_t ahi = smem_u32(s.a_hi), alo = smem_u32(s.a_lo), wsm = smem_u32(s.w);
-
-    float4 wn0 = ldg_stream(w0), wn1 = ldg_stream(w1);
+    for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = ldg_nc(x2 + jh * 32 + h * 16 + 4 * c);
+        e2[jh * 16 + 4 * c] = valid ? exp_nonpos<FAST>(v.x - m2) : 0.f;
+        e2[jh * 16 + 4 * c + 1] = valid ? exp_nonpos<FAST>(v.y - m2) : 0.f;
+        e2[jh * 16 + 4 * c + 2] = valid ? exp_nonpos<FAST>(v.z - m2) : 0.f;
+        e2[jh * 16 + 4 * c + 3] = valid ? exp_nonpos<FAST>(v.w - m2) : 0.f;
+      }
+    if (h == 0) s.msum[row] = fmaxf(m1 + m2, -FLT_MAX);
+    const uint32_t abase = tmem_base + ((uint32_t)(q * 32) << 16) + kColA + h * 16;
     float x1n = __ldg(x1);
-    auto body = [&](const int kb, auto JH, const float a1) {
-      constexpr int jh = decltype(JH)::value;
-      const float4 wc0 = wn0, wc1 = wn1;
-      if (kb + 1 < kNumKb) {
-        wn0 = ldg_stream(w0 + (kb + 1) * 32);
-        wn1 = ldg_stream(w1 + (kb + 1) * 32);
-      }
-      const uint32_t stage = (uint32_t)kb & 1u;
-      mbar_wait(&s.empty[stage], ((kb >> 1) & 1) ^ 1);
-      const uint32_t abase = stage * (2 * kTile) + a_row;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 pr, hi, lo;
-        pr.x = a1 * e2[jh * 32 + 4 * c];
-        pr.y = a1 * e2[jh * 32 + 4 * c + 1];
-        pr.z = a1 * e2[jh * 32 + 4 * c + 2];
-        pr.w = a1 * e2[jh * 32 + 4 * c + 3];
-        split4(pr, hi, lo);
-        const uint32_t off = abase + ((((uint32_t)c ^ r) & 7u) << 4);
-        sts128(ahi + off, hi);
-        sts128(alo + off, lo);
-      }
-      {
-        float4 hi, lo;
-        const uint32_t wb = wsm + stage * kTile;
-        split4(wc0, hi, lo);
-        sts128(wb + w_off0, hi);
-        sts128(wb + w_off0 + 64 * 128, lo);
-        split4(wc1, hi, lo);
-        sts128(wb + w_off1, hi);
-        sts128(wb + w_off1 + 64 * 128, lo);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.full[stage]);
-      if (warp == 0) {
-        if (lane == 0) {
-          // ---- MMA issue for this k-block
-          const int chunk = kb / kChunkKb, buf = chunk & 1;
-          const bool first = (kb % kChunkKb) == 0;
-          if (first) mbar_wait(&s.tempty[buf], ((chunk >> 1) & 1) ^ 1);
-          mbar_wait(&s.full[stage], (kb >> 1) & 1);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int tt = 0; tt < 2; ++tt) {
-            const uint32_t d = tmem_base + tt * 256 + buf * 128;
-            const uint32_t aoff = stage * (2 * kTile) + tt * kTile;
-            //   e_hi x [W_hi | W_lo]  (N = 128): main | correction;  e_lo x W_hi (N = 64): correction
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_tf32(d, desc_at(d_ahi, aoff + ks * 32), desc_at(d_w, stage * kTile + ks * 32),
-                       idesc_n128, (first && ks == 0) ? 0u : 1u);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_tf32(d + KK, desc_at(d_alo, aoff + ks * 32), desc_at(d_w, stage * kTile + ks * 32),
-                       idesc_n64, 1u);
-          }
-          mma_commit(&s.empty[stage]);
-          if ((kb % kChunkKb) == kChunkKb - 1) mma_commit(&s.tfull[buf]);
-        }
-        __syncwarp();
-      }
-    };
     for (int i = 0; i < KK; ++i) {
       const float a1 = exp_nonpos<FAST>(x1n - m1);
       if (i + 1 < KK) x1n = __ldg(x1 + i + 1);
-      body(2 * i, std::integral_constant<int, 0>{}, a1);
-      body(2 * i + 1, std::integral_constant<int, 1>{}, a1);
+      const uint32_t sl = (uint32_t)i & (kNS - 1);
+      // the products are ready before the slot is: only the TMEM stores sit behind the wait
+      float hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) split_tf32(a1 * e2[c], hi[c], lo[c]);
+      if (tid == 0) TKDBG(i, 3);
+      mbar_wait(&s.empty[sl], ((i / kNS) & 1) ^ 1);
+      tc_fence_after_sync();
+      if (tid == 0) TKDBG(i, 4);
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        tmem_st16(abase + sl * 128 + jh * 32, hi + jh * 16);
+        tmem_st16(abase + sl * 128 + 64 + jh * 32, lo + jh * 16);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[sl]);
+      if (tid == 0) TKDBG(i, 5);
     }
-  } else {
+  } else if (warp == 8) {
+    // ================= weight loader: one bulk copy (TMA engine) per slot =================
+    // wimg holds, per fold and slot i, the two stacked [W_hi | W_lo] swizzled k-block tiles exactly
+    // as the MMA reads them (tucker_split_w_kernel), so a slot is 32 contiguous KB
+    if (lane == 0) {
+      const float* src = wimg + (int64_t)f * KK * (2 * 128 * 32);
+      for (int i = 0; i < KK; ++i) {
+        const uint32_t sl = (uint32_t)i & (kNS - 1);
+        mbar_wait(&s.empty[sl], ((i / kNS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&s.full[sl], 2 * kTile);
+        bulk_g2s(&s.w[sl][0][0], src + (int64_t)i * (2 * 128 * 32), 2 * kTile, &s.full[sl]);
+      }
+    }
+  } else if (warp == 10 || warp == 11) {
+    // ================= MMA issuers (whole warp converged, instructions on the elected lane) =====
+    // Two issuer warps take alternate chunks (each chunk has its own accumulator pair), so the
+    // ~150-clock barrier waits and ~80-clock commits of one overlap the MMA issue of the other.
+    constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
+    constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
+    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+    const int buf = warp - 10;
+    const uint32_t d = tmem_base + buf * 128;
+    for (int chunk = buf; chunk < KK / kChunkSlots; chunk += 2) {
+      // A parity wait can only tell two consecutive phases of a barrier apart, and the slots'
+      // previous phases were consumed by the other issuer: wait until it has seen all of them.
+      const int n = chunk >> 1;
+      if (chunk > 0) mbar_wait(&s.turn[buf], buf ? (n & 1) : ((n - 1) & 1));
+      mbar_wait(&s.mempty[buf], (n & 1) ^ 1);
+#pragma unroll
+      for (int u = 0; u < kChunkSlots; ++u) {
+        const int i = chunk * kChunkSlots + u;
+        const uint32_t sl = (uint32_t)i & (kNS - 1);
+        if (lane == 0) TKDBG(i, 0);
+        mbar_wait(&s.full[sl], (i / kNS) & 1);
+        // hand the ring over: the other issuer may start waiting for the next chunk's slots
+        if (u == kChunkSlots - 1 && lane == 0) mbar_arrive(&s.turn[buf ^ 1]);
+        tc_fence_after_sync();
+        if (lane == 0) TKDBG(i, 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a_hi = tmem_base + kColA + sl * 128 + ks * 8, a_lo = a_hi + 64;
+          const uint64_t b_w = desc_at(d_w, (sl * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
+          mma_tf32_ts_warp(d, a_hi, b_w, idesc_n128, (u == 0 && ks == 0) ? 0u : 1u);
+          mma_tf32_ts_warp(d + KK, a_lo, b_w, idesc_n64, 1u);
+        }
+        if (lane == 0) TKDBG(i, 10);
+        mma_commit_warp(&s.empty[sl]);
+        if (u == kChunkSlots - 1) mma_commit_warp(&s.mfull[buf]);
+        if (lane == 0) TKDBG(i, 2);
+      }
+    }
+  } else if (warp >= 12) {
     // ================= chunk accumulation + epilogue =================
-    const int q = warp & 3, t = (warp - kProdWarps) >> 2;
-    const int row = t * TM + q * 32 + lane;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float acc[KK];
 #pragma unroll
     for (int j = 0; j < KK; ++j) acc[j] = 0.f;
-    constexpr int kChunks = kNumKb / kChunkKb;
+    constexpr int kChunks = KK / kChunkSlots;
     for (int c = 0; c < kChunks; ++c) {
       const int buf = c & 1;
-      mbar_wait_relaxed(&s.tfull[buf], (c >> 1) & 1);
+      mbar_wait_relaxed(&s.mfull[buf], (c >> 1) & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256 + buf * 128;
+      if (tid == 12 * 32) TKDBG(c * kChunkSlots + kChunkSlots - 1, 7);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         float v[16], w[16];
-        tmem_ld16(taddr + cc * 16, v);
-        tmem_ld16(taddr + KK + cc * 16, w);
+        tmem_ld16(lane_base + buf * 128 + cc * 16, v);
+        tmem_ld16(lane_base + buf * 128 + KK + cc * 16, w);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[cc * 16 + j] += v[j] + w[j];
       }
       tc_fence_before_sync();
-      mbar_arrive(&s.tempty[buf]);
+      mbar_arrive(&s.mempty[buf]);
     }
     const int64_t b = b0 + row;
     if (b < a.B) {
@@ -243,12 +275,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) tucker_tc_fwd_kernel(DenseArgs
 
 // ==========================================================================================
 // Backward, part 1 (d/dx1, d/dx2 and the operands of part 2).  CTA = (fold, 256 samples).
-// 16 worker warps; thread = (sample row, column half).  Prologue: row maxes, e2, r = g/S as
-// (hi, lo) A tiles [sample][o]; the transposed, split r and the raw e1, e2 go to a scratch block
-// per 32 samples, already in the swizzled image part 2 multiplies from.  Main loop over i:
-// the 64x64 slice W[:, i, :] is staged transposed ([j][o], so that o is the K axis), GEMM
-// T_i[b, j] = sum_o r[b,o] W[o,i,j] (K = 64: 8 k-steps, no long accumulation), and the workers
-// fold T_i into d/dx1[b,i] (dot with e2) and d/dx2[b,:] (axpy with e1[b,i]).
+// 16 worker warps; thread = (sample row, column half).  Prologue: row maxes, e2, r = g/S, written
+// as (hi, lo) to TMEM (the A operand of every GEMM of this CTA); the transposed, split r and the
+// raw e1, e2 also go to a scratch block per 32 samples, already in the swizzled image part 2
+// multiplies from.  Main loop over i: the 64x64 slice W[:, i, :] is staged transposed ([j][o], so
+// that o is the K axis), GEMM T_i[b, j] = sum_o r[b,o] W[o,i,j] (K = 64; the three 3xTF32
+// products share one accumulator: a 2^-22 relative bias is irrelevant for gradients), and the
+// workers fold T_i into d/dx1[b,i] (dot with e2) and d/dx2[b,:] (axpy with e1[b,i]).
+// TMEM columns: T accumulators [tile][buffer] x 64 -> [0,256); r (hi | lo) per tile -> [256,512).
 // ==========================================================================================
 constexpr int kDxWorkers = 16;
 constexpr int kDxThreads = kDxWorkers * 32;  // 512; lane 0 of worker 0 issues the MMAs
@@ -262,9 +296,7 @@ __device__ __forceinline__ int blk_off(int unit, int bcol) {
 }
 
 struct __align__(1024) TkDxSmem {
-  float r_hi[2][2][TM * 32];  // [M tile][o half][row][32]                        64 KB
-  float r_lo[2][2][TM * 32];  //                                                   64 KB
-  float w[2][2][128 * 32];    // [stage][o half][hi j 0..63 | lo j 0..63][32 o]    64 KB
+  float w[2][2][128 * 32];  // [stage][o half][hi j 0..63 | lo j 0..63][32 o]    64 KB
   float part[2][ROWS];
   uint64_t wfull[2], wempty[2], tfull[2], tempty[2];
   uint32_t tmem_base;
@@ -302,6 +334,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
     const int64_t bsafe = valid ? b : 0;
     const float* x1 = in_row(a, f, 0) + bsafe * KK;
     const float* x2 = in_row(a, f, 1) + bsafe * KK;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
@@ -336,7 +369,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
         blk[kBlkE1 + blk_off(u + 3, lane)] = valid ? exp_nonpos<FAST>(v.w - m1) : 0.f;
       }
     }
-    // r = g * exp(m1 + m2 - y) for this thread's 32 outputs
+    // r = g * exp(m1 + m2 - y) for this thread's 32 outputs -> TMEM columns o (hi) and 64 + o (lo)
     {
       const float* yrow = a.y + ((int64_t)f * a.B + bsafe) * KK + 32 * ch;
       int cbeg = 0, cend = 0;
@@ -344,39 +377,38 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
         cbeg = a.gs.cons_ptr[f];
         cend = a.gs.cons_ptr[f + 1];
       }
-      const uint32_t rhi = smem_u32(s.r_hi) + (uint32_t)(t * 2 + ch) * kTile;
-      const uint32_t rlo = smem_u32(s.r_lo) + (uint32_t)(t * 2 + ch) * kTile;
-      const uint32_t rr = (uint32_t)(q * 32 + lane);
+      const uint32_t rbase = lane_base + 256 + t * 128 + ch * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = cbeg; k < cend; ++k) {
-          const float4 z = *reinterpret_cast<const float4*>(a.gs.garena + a.gs.B * a.gs.cons_rows[k] +
-                                                            b * KK + 32 * ch + 4 * c);
-          g.x += z.x; g.y += z.y; g.z += z.z; g.w += z.w;
+      for (int hh = 0; hh < 2; ++hh) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = hh * 16 + 4 * c;
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = cbeg; k < cend; ++k) {
+            const float4 z = *reinterpret_cast<const float4*>(
+                a.gs.garena + a.gs.B * a.gs.cons_rows[k] + b * KK + 32 * ch + col);
+            g.x += z.x; g.y += z.y; g.z += z.z; g.w += z.w;
+          }
+          const float4 yv = ldg_nc(yrow + col);
+          split_tf32(g.x * exp_capped<FAST>(ms - yv.x), hi[4 * c], lo[4 * c]);
+          split_tf32(g.y * exp_capped<FAST>(ms - yv.y), hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32(g.z * exp_capped<FAST>(ms - yv.z), hi[4 * c + 2], lo[4 * c + 2]);
+          split_tf32(g.w * exp_capped<FAST>(ms - yv.w), hi[4 * c + 3], lo[4 * c + 3]);
         }
-        const float4 yv = ldg_nc(yrow + 4 * c);
-        float4 rv, hi, lo;
-        rv.x = g.x * exp_capped<FAST>(ms - yv.x);
-        rv.y = g.y * exp_capped<FAST>(ms - yv.y);
-        rv.z = g.z * exp_capped<FAST>(ms - yv.z);
-        rv.w = g.w * exp_capped<FAST>(ms - yv.w);
-        split4(rv, hi, lo);
-        const uint32_t off = rr * 128u + ((((uint32_t)c ^ rr) & 7u) << 4);
-        sts128(rhi + off, hi);
-        sts128(rlo + off, lo);
+        tmem_st16(rbase + hh * 16, hi);
+        tmem_st16(rbase + 64 + hh * 16, lo);
         if (blk) {
-          const int o = 32 * ch + 4 * c;
-          blk[blk_off(o, lane)] = hi.x;
-          blk[blk_off(o + 1, lane)] = hi.y;
-          blk[blk_off(o + 2, lane)] = hi.z;
-          blk[blk_off(o + 3, lane)] = hi.w;
-          blk[blk_off(64 + o, lane)] = lo.x;
-          blk[blk_off(64 + o + 1, lane)] = lo.y;
-          blk[blk_off(64 + o + 2, lane)] = lo.z;
-          blk[blk_off(64 + o + 3, lane)] = lo.w;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int o = 32 * ch + hh * 16 + c;
+            blk[blk_off(o, lane)] = hi[c];
+            blk[blk_off(64 + o, lane)] = lo[c];
+          }
         }
       }
+      tmem_st_wait();
+      tc_fence_before_sync();
     }
 
     // weight staging: unit u = 2*warp + n: rows o0..o0+3 of W[:, i, j0..j0+31], transposed on the fly
@@ -413,11 +445,8 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.wfull[st]);
     };
-    constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
     constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
-    const uint64_t d_rhi = make_desc(smem_u32(s.r_hi), 16, 1024);
-    const uint64_t d_rlo = make_desc(smem_u32(s.r_lo), 16, 1024);
-    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+    const uint64_t d_w = make_desc(wsm, 16, 1024);
     auto issue_mma = [&](int i) {  // worker 0: T_i = r W[:, i, :] for both M tiles
       if (warp == 0) {
         if (lane == 0) {
@@ -427,16 +456,16 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
           tc_fence_after_sync();
 #pragma unroll
           for (int tt = 0; tt < 2; ++tt) {
-            const uint32_t d = tmem_base + tt * 256 + buf * 128;
+            const uint32_t d = tmem_base + tt * 128 + buf * 64;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_tf32(d, desc_at(d_rhi, (tt * 2 + (ks >> 2)) * kTile + (ks & 3) * 32),
-                       desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32), idesc_n128,
-                       ks ? 1u : 0u);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_tf32(d + KK, desc_at(d_rlo, (tt * 2 + (ks >> 2)) * kTile + (ks & 3) * 32),
-                       desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32), idesc_n64, 1u);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t a_hi = tmem_base + 256 + tt * 128 + ks * 8, a_lo = a_hi + 64;
+              const uint64_t b_hi = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
+              const uint64_t b_lo = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + 64 * 128 + (ks & 3) * 32);
+              mma_tf32_ts(d, a_hi, b_hi, idesc_n64, ks ? 1u : 0u);
+              mma_tf32_ts(d, a_hi, b_lo, idesc_n64, 1u);
+              mma_tf32_ts(d, a_lo, b_hi, idesc_n64, 1u);
+            }
           }
           mma_commit(&s.wempty[st]);
           mma_commit(&s.tfull[buf]);
@@ -462,19 +491,17 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
       const int buf = i & 1;
       mbar_wait(&s.tfull[buf], (i >> 1) & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256 + buf * 128 + ch * 32;
+      const uint32_t taddr = lane_base + t * 128 + buf * 64 + ch * 32;
       float dot = 0.f;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float v[8], w[8];
-        tmem_ld8(taddr + h * 8, v);
-        tmem_ld8(taddr + KK + h * 8, w);
+      for (int h = 0; h < 2; ++h) {
+        float v[16];
+        tmem_ld16(taddr + h * 16, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float T = v[j] + w[j];
-          dot = fmaf(T, e2[h * 8 + j], dot);
-          acc2[h * 8 + j] = fmaf(T, e1i, acc2[h * 8 + j]);
+        for (int j = 0; j < 16; ++j) {
+          dot = fmaf(v[j], e2[h * 16 + j], dot);
+          acc2[h * 16 + j] = fmaf(v[j], e1i, acc2[h * 16 + j]);
         }
       }
       tc_fence_before_sync();
@@ -503,27 +530,26 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
 // ==========================================================================================
 // Backward, part 2 (d/dW).  CTA = (fold, 256 consecutive reduction indices n = (i, j): four i's),
 // loops over ALL samples in blocks of 32 (the K axis of this GEMM):
-//   dW[o, n] = sum_b r[b,o] P[b,n],  P[b,(i,j)] = e1[b,i] e2[b,j]
-// A = stacked [r_hi^T ; r_lo^T] (128 x 32 per block, bulk-copied as written by part 1),
-// B = P_hi^T / P_lo^T (256 x 32), formed by 256 producer threads (one per n) from the raw e1 / e2
-// rows of the block.  Two M128 x N256 accumulators (A x P_hi, A x P_lo) fill the 512 TMEM columns;
-// dW = D0[o] + D0[64 + o] + D1[o]  (the r_lo x P_lo quadrant is dropped).
+//   dW^T[n, o] = sum_b P[b,n] r[b,o],  P[b,(i,j)] = e1[b,i] e2[b,j]
+// A = P^T (two M tiles of 128 n; one producer thread per n forms the 32 products of a block from
+// the raw e1 / e2 rows and writes (hi, lo) to a TMEM ring), B = stacked [r_hi^T ; r_lo^T]
+// (128 x 32 per block, bulk-copied as part 1 wrote it).  One accumulator per tile takes all three
+// 3xTF32 products.  TMEM columns: dW^T accumulators [0,128), A ring [stage][tile] x 64 [128,512).
 // ==========================================================================================
 constexpr int kDwProdWarps = 8;
 constexpr int kDwTmaWarp = 8, kDwMmaWarp = 9;
 constexpr int kDwThreads = 10 * 32;
 constexpr int NCH = 256;  // reduction indices per CTA
+constexpr int kNR = 4;    // raw ring (shared memory)
+constexpr int kNP = 3;    // P ring (TMEM)
 
 struct __align__(1024) TkDwSmem {
-  float rstack[2][128 * 32];  // 32 KB
-  float p_hi[2][NCH * 32];    // 64 KB
-  float p_lo[2][NCH * 32];    // 64 KB
-  float e2raw[2][64 * 32];    // 16 KB
-  float e1raw[2][4 * 32];     //  1 KB
-  uint64_t raw_full[2], p_full[2], empty[2], done;
+  float rstack[kNR][128 * 32];  // 64 KB
+  float e2raw[kNR][64 * 32];    // 32 KB
+  float e1raw[kNR][4 * 32];     //  2 KB
+  uint64_t raw_full[kNR], raw_empty[kNR], p_full[kNP], p_empty[kNP], done;
   uint32_t tmem_base;
 };
-static_assert(NCH * (KK + 1) * 4 <= 2 * sizeof(float) * 2 * NCH * 32, "exchange buffer fits p_hi + p_lo");
 
 __global__ void __launch_bounds__(kDwThreads, 1)
 tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int nblk, float* dW) {
@@ -534,10 +560,13 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
   const int i0 = 4 * blockIdx.x, n0 = NCH * blockIdx.x;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNR; ++i) {
       mbar_init(&s.raw_full[i], 1);
+      mbar_init(&s.raw_empty[i], 1);
+    }
+    for (int i = 0; i < kNP; ++i) {
       mbar_init(&s.p_full[i], kDwProdWarps);
-      mbar_init(&s.empty[i], 1);
+      mbar_init(&s.p_empty[i], 1);
     }
     mbar_init(&s.done, 1);
     fence_barrier_init();
@@ -552,99 +581,93 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
   if (warp == kDwTmaWarp) {
     if (lane == 0) {
       for (int kb = 0; kb < nblk; ++kb) {
-        const int st = kb & 1;
-        mbar_wait(&s.empty[st], ((kb >> 1) & 1) ^ 1);
+        const int sr = kb & (kNR - 1);
+        mbar_wait(&s.raw_empty[sr], ((kb / kNR) & 1) ^ 1);
         const float* blk = fblk + (int64_t)kb * kBlkFloats;
-        mbar_arrive_expect_tx(&s.raw_full[st], 128 * 128 + 64 * 128 + 4 * 128);
-        bulk_g2s(s.rstack[st], blk, 128 * 128, &s.raw_full[st]);
-        bulk_g2s(s.e2raw[st], blk + kBlkE2, 64 * 128, &s.raw_full[st]);
-        bulk_g2s(s.e1raw[st], blk + kBlkE1 + i0 * 32, 4 * 128, &s.raw_full[st]);
+        mbar_arrive_expect_tx(&s.raw_full[sr], 128 * 128 + 64 * 128 + 4 * 128);
+        bulk_g2s(s.rstack[sr], blk, 128 * 128, &s.raw_full[sr]);
+        bulk_g2s(s.e2raw[sr], blk + kBlkE2, 64 * 128, &s.raw_full[sr]);
+        bulk_g2s(s.e1raw[sr], blk + kBlkE1 + i0 * 32, 4 * 128, &s.raw_full[sr]);
       }
     }
   } else if (warp == kDwMmaWarp) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, NCH, 0, 0);
+      constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
       const uint64_t d_r = make_desc(smem_u32(s.rstack), 16, 1024);
-      const uint64_t d_ph = make_desc(smem_u32(s.p_hi), 16, 1024);
-      const uint64_t d_pl = make_desc(smem_u32(s.p_lo), 16, 1024);
+      int sp = 0, php = 0;
       for (int kb = 0; kb < nblk; ++kb) {
-        const uint32_t st = kb & 1;
-        mbar_wait(&s.raw_full[st], (kb >> 1) & 1);
-        mbar_wait(&s.p_full[st], (kb >> 1) & 1);
+        const uint32_t sr = kb & (kNR - 1);
+        mbar_wait(&s.raw_full[sr], (kb / kNR) & 1);
+        mbar_wait(&s.p_full[sp], php);
         tc_fence_after_sync();
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t da = desc_at(d_r, st * (128 * 128) + ks * 32);
-          mma_tf32(tmem_base, da, desc_at(d_ph, st * (NCH * 128) + ks * 32), idesc, (kb | ks) ? 1u : 0u);
-          mma_tf32(tmem_base + NCH, da, desc_at(d_pl, st * (NCH * 128) + ks * 32), idesc,
-                   (kb | ks) ? 1u : 0u);
+        for (int tt = 0; tt < 2; ++tt) {
+          const uint32_t d = tmem_base + tt * 64;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = tmem_base + 128 + (sp * 2 + tt) * 64 + ks * 8, a_lo = a_hi + 32;
+            const uint64_t b_hi = desc_at(d_r, sr * kTile + ks * 32);
+            const uint64_t b_lo = desc_at(d_r, sr * kTile + 64 * 128 + ks * 32);
+            mma_tf32_ts(d, a_hi, b_hi, idesc_n64, (kb | ks) ? 1u : 0u);
+            mma_tf32_ts(d, a_hi, b_lo, idesc_n64, 1u);
+            mma_tf32_ts(d, a_lo, b_hi, idesc_n64, 1u);
+          }
         }
-        mma_commit(&s.empty[st]);
+        mma_commit(&s.raw_empty[sr]);
+        mma_commit(&s.p_empty[sp]);
+        if (++sp == kNP) { sp = 0; php ^= 1; }
       }
       mma_commit(&s.done);
     }
   } else {
-    // ================= producers: P^T tiles =================
-    const int n = tid;                 // row of the P^T tile: (i0 + il, j)
+    // ================= producers: P^T rows into TMEM =================
+    const int q = warp & 3, t = warp >> 2;
+    const int n = tid;  // row of the P^T operand: (i0 + il, j); n = t*128 + q*32 + lane
     const int il = n >> 6, j = n & 63;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t e1row = (uint32_t)il * 128u, e1key = (uint32_t)(i0 + il) & 7u;
     const uint32_t e2row = (uint32_t)j * 128u, e2key = (uint32_t)j & 7u;
-    const uint32_t prow = (uint32_t)n * 128u, pkey = (uint32_t)n & 7u;
     const uint32_t e1s = smem_u32(s.e1raw), e2s = smem_u32(s.e2raw);
-    const uint32_t phs = smem_u32(s.p_hi), pls = smem_u32(s.p_lo);
+    int sp = 0, php = 0;
     for (int kb = 0; kb < nblk; ++kb) {
-      const uint32_t st = kb & 1;
-      mbar_wait(&s.raw_full[st], (kb >> 1) & 1);
+      const uint32_t sr = kb & (kNR - 1);
+      mbar_wait(&s.raw_full[sr], (kb / kNR) & 1);
+      mbar_wait(&s.p_empty[sp], php ^ 1);
+      tc_fence_after_sync();
+      const uint32_t abase = lane_base + 128 + (sp * 2 + t) * 64;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 u = lds128(e1s + st * (4 * 128) + e1row + ((((uint32_t)c ^ e1key) & 7u) << 4));
-        const float4 v = lds128(e2s + st * (64 * 128) + e2row + ((((uint32_t)c ^ e2key) & 7u) << 4));
-        float4 pr, hi, lo;
-        pr.x = u.x * v.x; pr.y = u.y * v.y; pr.z = u.z * v.z; pr.w = u.w * v.w;
-        split4(pr, hi, lo);
-        const uint32_t off = st * (NCH * 128) + prow + ((((uint32_t)c ^ pkey) & 7u) << 4);
-        sts128(phs + off, hi);
-        sts128(pls + off, lo);
+      for (int hh = 0; hh < 2; ++hh) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t cc = (uint32_t)(hh * 4 + c);
+          const float4 u = lds128(e1s + sr * (4 * 128) + e1row + (((cc ^ e1key) & 7u) << 4));
+          const float4 v = lds128(e2s + sr * (64 * 128) + e2row + (((cc ^ e2key) & 7u) << 4));
+          split_tf32(u.x * v.x, hi[4 * c], lo[4 * c]);
+          split_tf32(u.y * v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32(u.z * v.z, hi[4 * c + 2], lo[4 * c + 2]);
+          split_tf32(u.w * v.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        tmem_st16(abase + hh * 16, hi);
+        tmem_st16(abase + 32 + hh * 16, lo);
       }
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.p_full[st]);
+      if (lane == 0) mbar_arrive(&s.p_full[sp]);
+      if (++sp == kNP) { sp = 0; php ^= 1; }
     }
-    // ================= epilogue =================
+    // ================= epilogue: dW[o][n0 + n] = D[n][o] =================
     mbar_wait_relaxed(&s.done, 0);
     tc_fence_after_sync();
-    const int q = warp & 3, half = warp >> 2;  // TMEM lane quadrant; 128-column half
-    const uint32_t xch = smem_u32(s.p_hi);     // [256 columns][64 + 1] exchange buffer over p_hi | p_lo (dead)
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
-    if (q >= 2) {
-      const int o = (q - 2) * 32 + lane;
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        float v[16];
-        tmem_ld16(taddr + cc * 16, v);
-        tmem_ld_wait();
+    float* out = dW + (int64_t)f * KK * KRED + n0 + n;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          sts32(xch + (uint32_t)((half * 128 + cc * 16 + jj) * (KK + 1) + o) * 4u, v[jj]);
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kDwProdWarps * 32) : "memory");
-    if (q < 2) {
-      const int o = q * 32 + lane;
-      float* out = dW + ((int64_t)f * KK + o) * KRED + n0 + half * 128;
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        float v[16], w[16];
-        tmem_ld16(taddr + cc * 16, v);
-        tmem_ld16(taddr + NCH + cc * 16, w);
-        tmem_ld_wait();
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[16];
+      tmem_ld16(lane_base + t * 64 + cc * 16, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          v[jj] += w[jj] + lds32(xch + (uint32_t)((half * 128 + cc * 16 + jj) * (KK + 1) + o) * 4u);
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 4)
-          *reinterpret_cast<float4*>(out + cc * 16 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
-      }
+      for (int jj = 0; jj < 16; ++jj) out[(int64_t)(cc * 16 + jj) * KRED] = v[jj];
     }
   }
   tc_fence_before_sync();
@@ -652,6 +675,24 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
   if (warp == kDwMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// W (F, 64, 4096) -> per (fold, slot i, k-block): stacked [W_hi rows o | W_lo rows o][32 j] tiles,
+// 128-byte swizzled: the shared-memory image of the forward's B operand.
+__global__ void tucker_split_w_kernel(const float* __restrict__ W, float* __restrict__ img, int64_t n16) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n16;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx enumerates 16-byte pieces of W in memory order: (f, o, i, kbi, c)
+    const int c = (int)(idx & 7), kbi = (int)((idx >> 3) & 1), i = (int)((idx >> 4) & 63);
+    const int o = (int)((idx >> 10) & 63);
+    const int64_t f = idx >> 16;
+    const float4 v = ldg_stream(W + idx * 4);
+    float4 hi, lo;
+    split4(v, hi, lo);
+    float* dst = img + ((f * KK + i) * 2 + kbi) * (128 * 32) + o * 32 + (((c ^ o) & 7) << 2);
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + 64 * 32) = lo;
   }
 }
 
@@ -667,9 +708,16 @@ bool tucker_tc_ok(const ckb_step_desc_t& d) {
   return !tc_disabled() && d.arity == 2 && d.k_in == KK && d.k_out == KK;
 }
 
-size_t tucker_tc_ws(const ckb_step_desc_t& d, int64_t B) {
+static size_t tucker_tc_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
   const int64_t nblk = (B + ROWS - 1) / ROWS * (ROWS / 32);
   return (size_t)d.num_folds * nblk * kBlkFloats * 4;
+}
+static size_t tucker_tc_fwd_ws(const ckb_step_desc_t& d) {
+  return (size_t)d.num_folds * KK * 2 * 128 * 32 * 4;  // split weight image, 2 MB per fold
+}
+size_t tucker_tc_ws(const ckb_step_desc_t& d, int64_t B) {
+  const size_t a = tucker_tc_bwd_ws(d, B), b = tucker_tc_fwd_ws(d);
+  return a > b ? a : b;
 }
 
 static DenseArgs tucker_tc_args(const ckb_step_desc_t& d, Ctx& c) {
@@ -696,11 +744,20 @@ int tucker_tc_fwd(const ckb_step_desc_t& d, Ctx& c) {
     attr = true;
   }
   const DenseArgs a = tucker_tc_args(d, c);
-  dim3 grid(ceil_div(c.B, ROWS), d.num_folds);
+  if (c.ws_bytes < tucker_tc_fwd_ws(d)) {
+    set_error("tucker_fwd: workspace too small (%zu < %zu)", c.ws_bytes, tucker_tc_fwd_ws(d));
+    return CKB_ERR_WORKSPACE;
+  }
+  float* wimg = (float*)c.ws;
+  const int64_t n16 = (int64_t)d.num_folds * KK * KRED / 4;
+  tucker_split_w_kernel<<<(int)min64((n16 + 255) / 256, 16 * kNumSMs), 256, 0, c.stream>>>(a.W, wimg, n16);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  dim3 grid(ceil_div(c.B, TM), d.num_folds);
   if ((tc_flags() & 3) == 3)
-    tucker_tc_fwd_kernel<true><<<grid, kFwdThreads, smem, c.stream>>>(a);
+    tucker_tc_fwd_kernel<true><<<grid, kFwdThreads, smem, c.stream>>>(a, wimg);
   else
-    tucker_tc_fwd_kernel<false><<<grid, kFwdThreads, smem, c.stream>>>(a);
+    tucker_tc_fwd_kernel<false><<<grid, kFwdThreads, smem, c.stream>>>(a, wimg);
   CKB_LAUNCH_CHECK();
   c.launches++;
   return CKB_OK;
@@ -722,8 +779,8 @@ int tucker_tc_bwd(const ckb_step_desc_t& d, Ctx& c) {
   float* scratch = nullptr;
   const int nblk_alloc = ceil_div(c.B, ROWS) * (ROWS / 32);
   if (dW) {
-    if (c.ws_bytes < tucker_tc_ws(d, c.B)) {
-      set_error("tucker_bwd: workspace too small (%zu < %zu)", c.ws_bytes, tucker_tc_ws(d, c.B));
+    if (c.ws_bytes < tucker_tc_bwd_ws(d, c.B)) {
+      set_error("tucker_bwd: workspace too small (%zu < %zu)", c.ws_bytes, tucker_tc_bwd_ws(d, c.B));
       return CKB_ERR_WORKSPACE;
     }
     scratch = (float*)c.ws;

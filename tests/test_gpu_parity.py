@@ -102,7 +102,7 @@ def test_known_answers(dev):
         assert math.isclose(ym[3].exp().item(), 44.0, rel_tol=2e-6)
 
 
-@pytest.mark.parametrize("name", [n for n in SEEDED if "tucker" not in n])
+@pytest.mark.parametrize("name", SEEDED)
 def test_benchmark_circuits_vs_reference(name, dev):
     """Benchmark-size circuits (QuadTree 28x28, K=32/64): outputs and gradient summaries of the
     real reference (float64) on leaves re-drawn from the fixture seed."""
