@@ -304,7 +304,7 @@ struct __align__(1024) TkDxSmem {
 
 template <bool FAST>
 __global__ void __launch_bounds__(kDxThreads, 1)
-tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
+tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __restrict__ wimg) {
   extern __shared__ uint8_t smem_raw[];
   TkDxSmem& s = *reinterpret_cast<TkDxSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -313,7 +313,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.wfull[i], kDxWorkers);
+      mbar_init(&s.wfull[i], 1);
       mbar_init(&s.wempty[i], 1);
       mbar_init(&s.tfull[i], 1);
       mbar_init(&s.tempty[i], kDxWorkers * 32);
@@ -411,68 +411,46 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk) {
       tc_fence_before_sync();
     }
 
-    // weight staging: unit u = 2*warp + n: rows o0..o0+3 of W[:, i, j0..j0+31], transposed on the fly
-    const float* wsrc[2];
-    uint32_t wdst[2];
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const int u = 2 * warp + n;
-      const int o0 = 4 * (u & 15), j0 = 32 * (u >> 4);
-      wsrc[n] = a.W + ((int64_t)f * KK + o0 + (lane & 3)) * KRED + j0 + 4 * (lane >> 2);
-      const uint32_t j = (uint32_t)(j0 + lane);
-      wdst[n] = (uint32_t)(o0 >> 5) * kTile + j * 128u + (((((uint32_t)o0 & 31u) >> 2) ^ j) & 7u) * 16u;
-    }
-    const uint32_t wsm = smem_u32(s.w);
-    float4 wn[2];
-    wn[0] = ldg_stream(wsrc[0]);
-    wn[1] = ldg_stream(wsrc[1]);
-    auto stage_w = [&](int i) {  // writes W[:, i, :] (held in wn) and fetches slice i + 1
-      const uint32_t st = (uint32_t)i & 1u;
-      mbar_wait(&s.wempty[st], ((i >> 1) & 1) ^ 1);
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        float4 hi, lo;
-        split4(transpose4(wn[n], lane & 3), hi, lo);
-        const uint32_t dst = wsm + st * (2 * kTile) + wdst[n];
-        sts128(dst, hi);
-        sts128(dst + 64 * 128, lo);
+    // weight staging: the transposed, split slice W[:, i, :]^T ([hi j | lo j] rows x o) comes as ONE
+    // 32 KB bulk copy per i from the image tucker_split_wt_kernel wrote (no proxy fence, no
+    // register staging in this kernel)
+    const float* wsrc = wimg + (int64_t)f * KK * (2 * 128 * 32);
+    auto stage_w = [&](int i) {
+      if (tid == 32) {  // lane 0 of worker 1
+        const uint32_t st = (uint32_t)i & 1u;
+        mbar_wait(&s.wempty[st], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&s.wfull[st], 2 * kTile);
+        bulk_g2s(&s.w[st][0][0], wsrc + (int64_t)i * (2 * 128 * 32), 2 * kTile, &s.wfull[st]);
       }
-      if (i + 1 < KK) {
-        wn[0] = ldg_stream(wsrc[0] + (i + 1) * KK);
-        wn[1] = ldg_stream(wsrc[1] + (i + 1) * KK);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.wfull[st]);
     };
     constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
-    const uint64_t d_w = make_desc(wsm, 16, 1024);
-    auto issue_mma = [&](int i) {  // worker 0: T_i = r W[:, i, :] for both M tiles
+    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+    auto issue_mma = [&](int i) {  // worker 0 (whole warp, elected lane): T_i = r W[:, i, :]
       if (warp == 0) {
-        if (lane == 0) {
-          const uint32_t st = i & 1, buf = i & 1;
-          mbar_wait(&s.tempty[buf], ((i >> 1) & 1) ^ 1);
-          mbar_wait(&s.wfull[st], (i >> 1) & 1);
-          tc_fence_after_sync();
+        const uint32_t st = i & 1, buf = i & 1;
+        mbar_wait(&s.tempty[buf], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&s.wfull[st], (i >> 1) & 1);
+        tc_fence_after_sync();
 #pragma unroll
-          for (int tt = 0; tt < 2; ++tt) {
-            const uint32_t d = tmem_base + tt * 128 + buf * 64;
+        for (int tt = 0; tt < 2; ++tt) {
+          const uint32_t d = tmem_base + tt * 128 + buf * 64;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint32_t a_hi = tmem_base + 256 + tt * 128 + ks * 8, a_lo = a_hi + 64;
-              const uint64_t b_hi = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
-              const uint64_t b_lo = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + 64 * 128 + (ks & 3) * 32);
-              mma_tf32_ts(d, a_hi, b_hi, idesc_n64, ks ? 1u : 0u);
-              mma_tf32_ts(d, a_hi, b_lo, idesc_n64, 1u);
-              mma_tf32_ts(d, a_lo, b_hi, idesc_n64, 1u);
-            }
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a_hi = tmem_base + 256 + tt * 128 + ks * 8, a_lo = a_hi + 64;
+            const uint64_t b_hi = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
+            const uint64_t b_lo = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + 64 * 128 + (ks & 3) * 32);
+            mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, ks ? 1u : 0u);
+            mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
+            mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
           }
-          mma_commit(&s.wempty[st]);
-          mma_commit(&s.tfull[buf]);
         }
-        __syncwarp();
+        mma_commit_warp(&s.wempty[st]);
+        mma_commit_warp(&s.tfull[buf]);
       }
     };
+    // every worker's r is in TMEM before the first MMA
+    asm volatile("bar.sync 9, %0;" ::"n"(kDxThreads) : "memory");
+    tc_fence_after_sync();
     stage_w(0);
     issue_mma(0);
 
@@ -591,34 +569,33 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
       }
     }
   } else if (warp == kDwMmaWarp) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
-      const uint64_t d_r = make_desc(smem_u32(s.rstack), 16, 1024);
-      int sp = 0, php = 0;
-      for (int kb = 0; kb < nblk; ++kb) {
-        const uint32_t sr = kb & (kNR - 1);
-        mbar_wait(&s.raw_full[sr], (kb / kNR) & 1);
-        mbar_wait(&s.p_full[sp], php);
-        tc_fence_after_sync();
+    // whole warp converged, instructions on the elected lane (see the forward kernel)
+    constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
+    const uint64_t d_r = make_desc(smem_u32(s.rstack), 16, 1024);
+    int sp = 0, php = 0;
+    for (int kb = 0; kb < nblk; ++kb) {
+      const uint32_t sr = kb & (kNR - 1);
+      mbar_wait(&s.raw_full[sr], (kb / kNR) & 1);
+      mbar_wait(&s.p_full[sp], php);
+      tc_fence_after_sync();
 #pragma unroll
-        for (int tt = 0; tt < 2; ++tt) {
-          const uint32_t d = tmem_base + tt * 64;
+      for (int tt = 0; tt < 2; ++tt) {
+        const uint32_t d = tmem_base + tt * 64;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = tmem_base + 128 + (sp * 2 + tt) * 64 + ks * 8, a_lo = a_hi + 32;
-            const uint64_t b_hi = desc_at(d_r, sr * kTile + ks * 32);
-            const uint64_t b_lo = desc_at(d_r, sr * kTile + 64 * 128 + ks * 32);
-            mma_tf32_ts(d, a_hi, b_hi, idesc_n64, (kb | ks) ? 1u : 0u);
-            mma_tf32_ts(d, a_hi, b_lo, idesc_n64, 1u);
-            mma_tf32_ts(d, a_lo, b_hi, idesc_n64, 1u);
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t a_hi = tmem_base + 128 + (sp * 2 + tt) * 64 + ks * 8, a_lo = a_hi + 32;
+          const uint64_t b_hi = desc_at(d_r, sr * kTile + ks * 32);
+          const uint64_t b_lo = desc_at(d_r, sr * kTile + 64 * 128 + ks * 32);
+          mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, (kb | ks) ? 1u : 0u);
+          mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
+          mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
         }
-        mma_commit(&s.raw_empty[sr]);
-        mma_commit(&s.p_empty[sp]);
-        if (++sp == kNP) { sp = 0; php ^= 1; }
       }
-      mma_commit(&s.done);
+      mma_commit_warp(&s.raw_empty[sr]);
+      mma_commit_warp(&s.p_empty[sp]);
+      if (++sp == kNP) { sp = 0; php ^= 1; }
     }
+    mma_commit_warp(&s.done);
   } else {
     // ================= producers: P^T rows into TMEM =================
     const int q = warp & 3, t = warp >> 2;
@@ -696,6 +673,31 @@ __global__ void tucker_split_w_kernel(const float* __restrict__ W, float* __rest
   }
 }
 
+// W (F, 64, 4096) -> per (fold, i, o half): stacked [W_hi[o, i, j] rows j | W_lo rows j][32 o] tiles,
+// 128-byte swizzled: the shared-memory image of the backward's B operand (o is the K axis there).
+__global__ void __launch_bounds__(256) tucker_split_wt_kernel(const float* __restrict__ W,
+                                                             float* __restrict__ img) {
+  __shared__ float T[KK][KK + 1];
+  const int i = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const float* src = W + (int64_t)f * KK * KRED + i * KK;
+  for (int idx = tid; idx < KK * KK / 4; idx += 256) {
+    const int o = idx >> 4, c = idx & 15;
+    const float4 v = ldg_stream(src + (int64_t)o * KRED + 4 * c);
+    T[o][4 * c] = v.x; T[o][4 * c + 1] = v.y; T[o][4 * c + 2] = v.z; T[o][4 * c + 3] = v.w;
+  }
+  __syncthreads();
+  float* dst = img + ((int64_t)f * KK + i) * (2 * 128 * 32);
+  for (int idx = tid; idx < 2 * KK * 8; idx += 256) {
+    const int kb = idx >> 9, j = (idx >> 3) & 63, c = idx & 7;
+    const int o = kb * 32 + c * 4;
+    float4 v = make_float4(T[o][j], T[o + 1][j], T[o + 2][j], T[o + 3][j]), hi, lo;
+    split4(v, hi, lo);
+    float* p = dst + kb * (128 * 32) + j * 32 + (((c ^ j) & 7) << 2);
+    *reinterpret_cast<float4*>(p) = hi;
+    *reinterpret_cast<float4*>(p + 64 * 32) = lo;
+  }
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   CKB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -708,12 +710,16 @@ bool tucker_tc_ok(const ckb_step_desc_t& d) {
   return !tc_disabled() && d.arity == 2 && d.k_in == KK && d.k_out == KK;
 }
 
-static size_t tucker_tc_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
+static size_t tucker_tc_img_bytes(const ckb_step_desc_t& d) {
+  return (size_t)d.num_folds * KK * 2 * 128 * 32 * 4;  // split weight image, 2 MB per fold
+}
+static size_t tucker_tc_scratch_bytes(const ckb_step_desc_t& d, int64_t B) {
   const int64_t nblk = (B + ROWS - 1) / ROWS * (ROWS / 32);
   return (size_t)d.num_folds * nblk * kBlkFloats * 4;
 }
-static size_t tucker_tc_fwd_ws(const ckb_step_desc_t& d) {
-  return (size_t)d.num_folds * KK * 2 * 128 * 32 * 4;  // split weight image, 2 MB per fold
+static size_t tucker_tc_fwd_ws(const ckb_step_desc_t& d) { return tucker_tc_img_bytes(d); }
+static size_t tucker_tc_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
+  return tucker_tc_img_bytes(d) + tucker_tc_scratch_bytes(d, B);  // image first, then the scratch
 }
 size_t tucker_tc_ws(const ckb_step_desc_t& d, int64_t B) {
   const size_t a = tucker_tc_bwd_ws(d, B), b = tucker_tc_fwd_ws(d);
@@ -778,18 +784,21 @@ int tucker_tc_bwd(const ckb_step_desc_t& d, Ctx& c) {
   float* dW = c.grads[d.slot[0]];
   float* scratch = nullptr;
   const int nblk_alloc = ceil_div(c.B, ROWS) * (ROWS / 32);
-  if (dW) {
-    if (c.ws_bytes < tucker_tc_bwd_ws(d, c.B)) {
-      set_error("tucker_bwd: workspace too small (%zu < %zu)", c.ws_bytes, tucker_tc_bwd_ws(d, c.B));
-      return CKB_ERR_WORKSPACE;
-    }
-    scratch = (float*)c.ws;
+  const size_t need = dW ? tucker_tc_bwd_ws(d, c.B) : tucker_tc_img_bytes(d);
+  if (c.ws_bytes < need) {
+    set_error("tucker_bwd: workspace too small (%zu < %zu)", c.ws_bytes, need);
+    return CKB_ERR_WORKSPACE;
   }
+  float* wimg = (float*)c.ws;
+  if (dW) scratch = (float*)(c.ws + tucker_tc_img_bytes(d));
+  tucker_split_wt_kernel<<<dim3(KK, d.num_folds), 256, 0, c.stream>>>(a.W, wimg);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
   dim3 grid(ceil_div(c.B, ROWS), d.num_folds);
   if ((tc_flags() & 3) == 3)
-    tucker_tc_bwd_dx_kernel<true><<<grid, kDxThreads, smem_dx, c.stream>>>(a, scratch, nblk_alloc);
+    tucker_tc_bwd_dx_kernel<true><<<grid, kDxThreads, smem_dx, c.stream>>>(a, scratch, nblk_alloc, wimg);
   else
-    tucker_tc_bwd_dx_kernel<false><<<grid, kDxThreads, smem_dx, c.stream>>>(a, scratch, nblk_alloc);
+    tucker_tc_bwd_dx_kernel<false><<<grid, kDxThreads, smem_dx, c.stream>>>(a, scratch, nblk_alloc, wimg);
   CKB_LAUNCH_CHECK();
   c.launches++;
   if (dW) {
