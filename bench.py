@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "samples/sec (fwd+bwd log-lik) QuadTree 28x28 K=64"
+METRIC = "samples/sec (fwd+bwd log-lik) QuadTree 28x28 K=64"  # BASELINE.json metric
 UNIT = "samples/s"
 WORKLOADS = {
     "qt28_cp_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=64",
@@ -46,6 +46,16 @@ def peaks():
         p = json.load(open(path))
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    """Dense bf16 tensor throughput the driver measured (sustained: the kernel runs inside a long
+    step); kind::tf32 runs at half of it."""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained; tf32 = half)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained bf16; tf32 = half)"
 
 
 class ClockSampler(threading.Thread):
@@ -289,18 +299,37 @@ def run_b200(args):
     nbytes = r[f"{d}_bytes"]
     achieved = nbytes / (t * 1e-3) / 1e9
     step_ms_sum = sum(q.get("fwd_ms", 0) + q.get("bwd_ms", 0) for q in prof)
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    whole = {
+        "algorithmic_bytes": plan.algorithmic_bytes(B),
+        "achieved_gbs": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9,
+        "frac": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9 / peak,
+    }
+    common = {
         "traffic": ncu_traffic(f"{args.workload} B={B} {r['kind']} {d} F={r.get('F')}"),
         "kernel": f"step {r['step']} {r['kind']} {d} (F={r.get('F')}, {r.get(d + '_launches', 1)} launch)",
-        "kernel_ms": t, "kernel_share_of_step": t / step_ms_sum, "peak_source": peak_src,
-        "algorithmic_bytes": nbytes,
-        "whole_step": {
-            "algorithmic_bytes": plan.algorithmic_bytes(B),
-            "achieved_gbs": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9,
-            "frac": plan.algorithmic_bytes(B) / (ms / args.steps * 1e-3) / 1e9 / peak,
-        },
+        "kernel_ms": t, "kernel_share_of_step": t / step_ms_sum,
+        "algorithmic_bytes": nbytes, "whole_step": whole,
     }
+    if r["kind"] == "tucker":
+        # the Tucker contraction is tensor-pipe bound: 2*Ko*Ki^2 flop per (fold, sample) forward,
+        # twice that backward; the kernels run it as 3xTF32 (three tf32 MMAs per product)
+        tf_peak, tf_src = tensor_peak()
+        flops = r[f"{d}_flops"]
+        tfs = flops / (t * 1e-3) / 1e12
+        total_flops = sum(q.get("fwd_flops", 0) + q.get("bwd_flops", 0) for q in prof)
+        roofline = {
+            "bound": "tensor", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
+            "peak_source": tf_src, "algorithmic_flops": flops,
+            "tensor_core_flops_executed": 3 * flops, "executed_frac_of_tf32_peak": 3 * tfs / (tf_peak / 2),
+            "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src},
+            **common,
+        }
+        roofline["whole_step"]["algorithmic_flops"] = total_flops
+        roofline["whole_step"]["achieved_tflops"] = total_flops / (ms / args.steps * 1e-3) / 1e12
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, **common}
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump(prof, fh, indent=1)

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
 
   if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    {  // whole warp converged; the instructions are predicated on the elected lane (a single
+       // lane in a divergent branch pays ~55 clocks per tcgen05.mma instead of ~25)
       constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
       constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
       const uint64_t d_ahi = make_desc(smem_u32(s.a_hi), 16, 1024);
@@ -125,14 +126,14 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
         const uint32_t d = tmem_base + buf * 128;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          mma_tf32(d, desc_at(d_ahi, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+          mma_tf32_warp(d, desc_at(d_ahi, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
                    desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n128, ks ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          mma_tf32(d + KK, desc_at(d_alo, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+          mma_tf32_warp(d + KK, desc_at(d_alo, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
                    desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n64, 1u);
-        mma_commit(&s.a_empty);
-        mma_commit(&s.tmem_full[buf]);
+        mma_commit_warp(&s.a_empty);
+        mma_commit_warp(&s.tmem_full[buf]);
       }
     }
   } else if (warp < kTransformWarps) {
@@ -528,10 +529,10 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
       // registers per thread): lane 0 of worker 0 issues GEMM 1 and lane 0 of worker 1 GEMM 2
       // once every worker has arrived; both workers would be waiting for GEMM 1 anyway.
       if (warp == kGemm1Warp) {
-        if (lane == 0) {
+        {
           mbar_wait(&s.ab_full, it & 1);
           tc_fence_after_sync();
-          if (it < 4) DBG(16 + it * 8 + 0);
+          if (it < 4 && lane == 0) DBG(16 + it * 8 + 0);
           // GEMM 1: T[b,i] = sum_o r[b,o] W[o,i]
           //   r_hi x [W_hi | W_lo]  (N = 128): main | correction;  r_lo x W_hi (N = 64): correction
           constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
@@ -541,19 +542,19 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
           const uint64_t d_r = make_desc(rhi, 16, 1024);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // 8 o's per step
-            mma_tf32(tmem_base, desc_at(d_r, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+            mma_tf32_warp(tmem_base, desc_at(d_r, (ks >> 2) * (TM * 128) + (ks & 3) * 32),
                      desc_at(d_r, kW + (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n128, ks ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            mma_tf32(tmem_base + KK, desc_at(d_r, kRlo + (ks >> 2) * (TM * 128) + (ks & 3) * 32),
+            mma_tf32_warp(tmem_base + KK, desc_at(d_r, kRlo + (ks >> 2) * (TM * 128) + (ks & 3) * 32),
                      desc_at(d_r, kW + (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n64, 1u);
-          mma_commit(&s.d1_full);
-          mma_commit(&s.ab_empty);
-          if (it < 4) DBG(16 + it * 8 + 1);
+          mma_commit_warp(&s.d1_full);
+          mma_commit_warp(&s.ab_empty);
+          if (it < 4 && lane == 0) DBG(16 + it * 8 + 1);
         }
         __syncwarp();
       } else if (warp == kGemm2Warp && want_dw) {
-        if (lane == 0) {
+        {
           mbar_wait(&s.ab_full, it & 1);
           tc_fence_after_sync();
           // GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]   (stacked hi/lo rows, 8 samples per step)
@@ -564,11 +565,11 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
 #pragma unroll
           for (int ks = 0; ks < TM / 8; ++ks) {
             const uint32_t o = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
-            mma_tf32(tmem_base + kD2Col, desc_at(d_r, kRT + o), desc_at(d_r, kETo + o), idesc2,
+            mma_tf32_warp(tmem_base + kD2Col, desc_at(d_r, kRT + o), desc_at(d_r, kETo + o), idesc2,
                      (it || ks) ? 1u : 0u);
           }
-          mma_commit(&s.ab_empty);
-          if (it + 1 == n_tiles) mma_commit(&s.d2_full);
+          mma_commit_warp(&s.ab_empty);
+          if (it + 1 == n_tiles) mma_commit_warp(&s.d2_full);
         }
         __syncwarp();
       }

@@ -223,6 +223,76 @@ __global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
   }
 }
 
+// Long rows (the (Ko, Ki^2) weights of Tucker layers: 4096 columns): one block per row, the row
+// stays in registers as 16-byte vectors, so every element is read once and written once.
+template <bool BWD, int NV>
+__global__ void __launch_bounds__(256) softmax_wide_kernel(const float* __restrict__ a,
+                                                          const float* __restrict__ g,
+                                                          float* __restrict__ out, int cols) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t base = (int64_t)blockIdx.x * cols;
+  float4 v[NV], w[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+    const int c = (n * 256 + tid) * 4;
+    v[n] = *reinterpret_cast<const float4*>(a + base + c);
+    if (BWD) w[n] = *reinterpret_cast<const float4*>(g + base + c);
+  }
+  auto block_reduce = [&](float x, bool is_max) {
+    x = is_max ? warp_max(x) : warp_sum(x);
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+    return r;
+  };
+  if (!BWD) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) mx = fmaxf(mx, fmaxf(fmaxf(v[n].x, v[n].y), fmaxf(v[n].z, v[n].w)));
+    mx = block_reduce(mx, true);
+    float z = 0.f;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      v[n].x = expf(v[n].x - mx); v[n].y = expf(v[n].y - mx);
+      v[n].z = expf(v[n].z - mx); v[n].w = expf(v[n].w - mx);
+      z += (v[n].x + v[n].y) + (v[n].z + v[n].w);
+    }
+    const float inv = 1.f / block_reduce(z, false);
+#pragma unroll
+    for (int n = 0; n < NV; ++n)
+      *reinterpret_cast<float4*>(out + base + (n * 256 + tid) * 4) =
+          make_float4(v[n].x * inv, v[n].y * inv, v[n].z * inv, v[n].w * inv);
+  } else {
+    float dot = 0.f;
+#pragma unroll
+    for (int n = 0; n < NV; ++n)
+      dot += fmaf(v[n].x, w[n].x, v[n].y * w[n].y) + fmaf(v[n].z, w[n].z, v[n].w * w[n].w);
+    dot = block_reduce(dot, false);
+#pragma unroll
+    for (int n = 0; n < NV; ++n)
+      *reinterpret_cast<float4*>(out + base + (n * 256 + tid) * 4) =
+          make_float4(v[n].x * (w[n].x - dot), v[n].y * (w[n].y - dot), v[n].z * (w[n].z - dot),
+                      v[n].w * (w[n].w - dot));
+  }
+}
+
+template <bool BWD>
+static bool softmax_wide(const float* a, const float* g, float* out, int64_t rows, int cols, Ctx& c) {
+  if (rows <= 0 || rows > 0x7fffffff) return false;
+  switch (cols) {
+    case 1024: softmax_wide_kernel<BWD, 1><<<(unsigned)rows, 256, 0, c.stream>>>(a, g, out, cols); break;
+    case 2048: softmax_wide_kernel<BWD, 2><<<(unsigned)rows, 256, 0, c.stream>>>(a, g, out, cols); break;
+    case 4096: softmax_wide_kernel<BWD, 4><<<(unsigned)rows, 256, 0, c.stream>>>(a, g, out, cols); break;
+    default: return false;
+  }
+  c.launches++;
+  return true;
+}
+
 // Runs every CKB_POP_SOFTMAX op of `ops` (forward, or backward when `bwd`); returns how many
 // launches it made through c.launches.
 int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
@@ -249,10 +319,18 @@ int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
         set_error("softmax op: gradient of slot %d requested but slot %d has none", op.src, op.dst);
         return CKB_ERR_INVALID;
       }
+      if (softmax_wide<true>(c.tensors[op.dst], c.grads[op.dst], c.grads[op.src], op.rows, op.cols, c)) {
+        CKB_LAUNCH_CHECK();
+        continue;
+      }
       m.a[m.n] = c.tensors[op.dst];
       m.b[m.n] = c.grads[op.dst];
       m.out[m.n] = c.grads[op.src];
     } else {
+      if (softmax_wide<false>(c.tensors[op.src], nullptr, c.tensors[op.dst], op.rows, op.cols, c)) {
+        CKB_LAUNCH_CHECK();
+        continue;
+      }
       m.a[m.n] = c.tensors[op.src];
       m.b[m.n] = nullptr;
       m.out[m.n] = c.tensors[op.dst];

@@ -28,9 +28,9 @@ using namespace sm100;
 // Debug timeline (built with -DCKB_TIMELINE): CTA (0,0) of the forward kernel records clock64()
 // at pipeline events of its first k-blocks; read back with ckb_debug_read when bit 8 of
 // CKB_OPT_TC_FAST_MATH is set.
-__device__ long long g_dbg_tk[512];
+__device__ long long g_dbg_tk[1024];
 int tucker_debug_read(void* dst, size_t bytes) {
-  if (bytes > sizeof(long long) * 512) bytes = sizeof(long long) * 512;
+  if (bytes > sizeof(long long) * 1024) bytes = sizeof(long long) * 1024;
   CKB_CUDA_CHECK(cudaMemcpyFromSymbol(dst, g_dbg_tk, bytes));
   return CKB_OK;
 }
@@ -39,8 +39,13 @@ int tucker_debug_read(void* dst, size_t bytes) {
   do {                                                                                     \
     if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 24) g_dbg_tk[16 + (kb) * 16 + (slot)] = clock64(); \
   } while (0)
+#define DXDBG(i, slot)                                                                     \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= 8 && (i) < 32) g_dbg_tk[512 + ((i) - 8) * 16 + (slot)] = clock64(); \
+  } while (0)
 #else
 #define TKDBG(kb, slot) do { } while (0)
+#define DXDBG(i, slot) do { } while (0)
 #endif
 
 namespace {
@@ -285,7 +290,9 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
 // TMEM columns: T accumulators [tile][buffer] x 64 -> [0,256); r (hi | lo) per tile -> [256,512).
 // ==========================================================================================
 constexpr int kDxWorkers = 16;
-constexpr int kDxThreads = kDxWorkers * 32;  // 512; lane 0 of worker 0 issues the MMAs
+constexpr int kDxNW = 4;  // weight ring depth (32 KB slots)
+constexpr int kDxThreads = (kDxWorkers + 3) * 32;  // 608: warps 16 / 17 issue the MMAs of M tile 0 / 1,
+                                                   // warp 18 runs the weight copies
 
 // scratch block of 32 samples (floats): r stacked [hi o 0..63 | lo o 0..63][32 b] | e1 [i][32 b] |
 // e2 [j][32 b]; every [unit][32] row is 128 bytes with its 16-byte chunks xor-swizzled by unit & 7
@@ -296,9 +303,9 @@ __device__ __forceinline__ int blk_off(int unit, int bcol) {
 }
 
 struct __align__(1024) TkDxSmem {
-  float w[2][2][128 * 32];  // [stage][o half][hi j 0..63 | lo j 0..63][32 o]    64 KB
+  float w[kDxNW][2][128 * 32];  // [slot][o half][hi j 0..63 | lo j 0..63][32 o]   128 KB
   float part[2][ROWS];
-  uint64_t wfull[2], wempty[2], tfull[2], tempty[2];
+  uint64_t wfull[kDxNW], wempty[kDxNW], tfull[2][2], tempty[2][2];  // t*: [M tile][buffer]
   uint32_t tmem_base;
 };
 
@@ -312,12 +319,15 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
   const int64_t b0 = (int64_t)blockIdx.x * ROWS;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kDxNW; ++i) {
       mbar_init(&s.wfull[i], 1);
-      mbar_init(&s.wempty[i], 1);
-      mbar_init(&s.tfull[i], 1);
-      mbar_init(&s.tempty[i], kDxWorkers * 32);
+      mbar_init(&s.wempty[i], 2);  // one commit per tile issuer
     }
+    for (int i = 0; i < 2; ++i)
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(&s.tfull[t][i], 1);
+        mbar_init(&s.tempty[t][i], (kDxWorkers / 2) * 32);
+      }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 512);
@@ -326,7 +336,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
 
-  {
+  if (warp < kDxWorkers) {
     const int q = warp & 3, t = (warp >> 2) & 1, ch = warp >> 3;
     const int p = t * TM + q * 32 + lane;  // row inside the CTA
     const int64_t b = b0 + p;
@@ -411,48 +421,8 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
       tc_fence_before_sync();
     }
 
-    // weight staging: the transposed, split slice W[:, i, :]^T ([hi j | lo j] rows x o) comes as ONE
-    // 32 KB bulk copy per i from the image tucker_split_wt_kernel wrote (no proxy fence, no
-    // register staging in this kernel)
-    const float* wsrc = wimg + (int64_t)f * KK * (2 * 128 * 32);
-    auto stage_w = [&](int i) {
-      if (tid == 32) {  // lane 0 of worker 1
-        const uint32_t st = (uint32_t)i & 1u;
-        mbar_wait(&s.wempty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&s.wfull[st], 2 * kTile);
-        bulk_g2s(&s.w[st][0][0], wsrc + (int64_t)i * (2 * 128 * 32), 2 * kTile, &s.wfull[st]);
-      }
-    };
-    constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
-    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
-    auto issue_mma = [&](int i) {  // worker 0 (whole warp, elected lane): T_i = r W[:, i, :]
-      if (warp == 0) {
-        const uint32_t st = i & 1, buf = i & 1;
-        mbar_wait(&s.tempty[buf], ((i >> 1) & 1) ^ 1);
-        mbar_wait(&s.wfull[st], (i >> 1) & 1);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int tt = 0; tt < 2; ++tt) {
-          const uint32_t d = tmem_base + tt * 128 + buf * 64;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t a_hi = tmem_base + 256 + tt * 128 + ks * 8, a_lo = a_hi + 64;
-            const uint64_t b_hi = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
-            const uint64_t b_lo = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + 64 * 128 + (ks & 3) * 32);
-            mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, ks ? 1u : 0u);
-            mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
-            mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
-          }
-        }
-        mma_commit_warp(&s.wempty[st]);
-        mma_commit_warp(&s.tfull[buf]);
-      }
-    };
     // every worker's r is in TMEM before the first MMA
     asm volatile("bar.sync 9, %0;" ::"n"(kDxThreads) : "memory");
-    tc_fence_after_sync();
-    stage_w(0);
-    issue_mma(0);
 
     float acc2[32];
 #pragma unroll
@@ -460,33 +430,37 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
     float* gin1 = a.gin + (((int64_t)f * 2 + 0) * a.B + bsafe) * KK;
     float x1n = __ldg(x1);
     for (int i = 0; i < KK; ++i) {
-      if (i + 1 < KK) {
-        stage_w(i + 1);
-        issue_mma(i + 1);
-      }
       const float e1i = valid ? exp_nonpos<FAST>(x1n - m1) : 0.f;
       if (i + 1 < KK) x1n = __ldg(x1 + i + 1);
       const int buf = i & 1;
-      mbar_wait(&s.tfull[buf], (i >> 1) & 1);
+      if (tid == 0) DXDBG(i, 5);
+      if (tid == 8 * 32) DXDBG(i, 9);
+      mbar_wait(&s.tfull[t][buf], (i >> 1) & 1);
       tc_fence_after_sync();
+      if (tid == 0) DXDBG(i, 6);
+      if (tid == 8 * 32) DXDBG(i, 10);
       const uint32_t taddr = lane_base + t * 128 + buf * 64 + ch * 32;
       float dot = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[16];
-        tmem_ld16(taddr + h * 16, v);
+      for (int h = 0; h < 4; ++h) {
+        float v[8];
+        tmem_ld8(taddr + h * 8, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          dot = fmaf(v[j], e2[h * 16 + j], dot);
-          acc2[h * 16 + j] = fmaf(v[j], e1i, acc2[h * 16 + j]);
+        for (int j = 0; j < 8; ++j) {
+          dot = fmaf(v[j], e2[h * 8 + j], dot);
+          acc2[h * 8 + j] = fmaf(v[j], e1i, acc2[h * 8 + j]);
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&s.tempty[buf]);
+      mbar_arrive(&s.tempty[t][buf]);
+      if (tid == 0) DXDBG(i, 7);
+      if (tid == 8 * 32) DXDBG(i, 11);
       if (ch == 1) s.part[buf][p] = dot;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 7)) : "memory");
       if (ch == 0 && valid) gin1[i] = e1i * (dot + s.part[buf][p]);
+      if (tid == 0) DXDBG(i, 8);
+      if (tid == 8 * 32) DXDBG(i, 12);
     }
     if (valid) {
       float* gin2 = a.gin + (((int64_t)f * 2 + 1) * a.B + b) * KK + 32 * ch;
@@ -495,6 +469,51 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
         *reinterpret_cast<float4*>(gin2 + 4 * c) =
             make_float4(e2[4 * c] * acc2[4 * c], e2[4 * c + 1] * acc2[4 * c + 1],
                         e2[4 * c + 2] * acc2[4 * c + 2], e2[4 * c + 3] * acc2[4 * c + 3]);
+    }
+  } else if (warp == kDxWorkers + 2) {
+    // ================= weight loader =================
+    // the transposed, split slice W[:, i, :]^T ([hi j | lo j] rows x o) comes as ONE 32 KB bulk
+    // copy per i from the image tucker_split_wt_kernel wrote
+    asm volatile("bar.sync 9, %0;" ::"n"(kDxThreads) : "memory");
+    if (lane == 0) {
+      const float* wsrc = wimg + (int64_t)f * KK * (2 * 128 * 32);
+      for (int i = 0; i < KK; ++i) {
+        const uint32_t st = (uint32_t)i & (kDxNW - 1);
+        mbar_wait(&s.wempty[st], ((i / kDxNW) & 1) ^ 1);
+        mbar_arrive_expect_tx(&s.wfull[st], 2 * kTile);
+        bulk_g2s(&s.w[st][0][0], wsrc + (int64_t)i * (2 * 128 * 32), 2 * kTile, &s.wfull[st]);
+      }
+    }
+  } else {
+    // ================= MMA issuers: warp 16 -> M tile 0, warp 17 -> M tile 1 =================
+    // whole warp converged, instructions on the elected lane (see the forward kernel)
+    const int t = warp - kDxWorkers;
+    constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
+    const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+    asm volatile("bar.sync 9, %0;" ::"n"(kDxThreads) : "memory");  // r is in TMEM
+    tc_fence_after_sync();
+    for (int i = 0; i < KK; ++i) {
+      const uint32_t st = i & (kDxNW - 1), buf = i & 1;
+      if (lane == 0 && t == 0) DXDBG(i, 0);
+      mbar_wait(&s.tempty[t][buf], ((i >> 1) & 1) ^ 1);
+      if (lane == 0 && t == 0) DXDBG(i, 1);
+      mbar_wait(&s.wfull[st], (i / kDxNW) & 1);
+      tc_fence_after_sync();
+      if (lane == 0 && t == 0) DXDBG(i, 2);
+      const uint32_t d = tmem_base + t * 128 + buf * 64;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t a_hi = tmem_base + 256 + t * 128 + ks * 8, a_lo = a_hi + 64;
+        const uint64_t b_hi = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + (ks & 3) * 32);
+        const uint64_t b_lo = desc_at(d_w, (st * 2 + (ks >> 2)) * kTile + 64 * 128 + (ks & 3) * 32);
+        mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, ks ? 1u : 0u);
+        mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
+        mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
+      }
+      if (lane == 0 && t == 0) DXDBG(i, 3);
+      mma_commit_warp(&s.wempty[st]);
+      mma_commit_warp(&s.tfull[t][buf]);
+      if (lane == 0 && t == 0) DXDBG(i, 4);
     }
   }
   tc_fence_before_sync();
@@ -515,8 +534,8 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
 // 3xTF32 products.  TMEM columns: dW^T accumulators [0,128), A ring [stage][tile] x 64 [128,512).
 // ==========================================================================================
 constexpr int kDwProdWarps = 8;
-constexpr int kDwTmaWarp = 8, kDwMmaWarp = 9;
-constexpr int kDwThreads = 10 * 32;
+constexpr int kDwTmaWarp = 8, kDwMmaWarp = 9;  // warps 9 and 10 issue the MMAs of M tile 0 / 1
+constexpr int kDwThreads = 11 * 32;
 constexpr int NCH = 256;  // reduction indices per CTA
 constexpr int kNR = 4;    // raw ring (shared memory)
 constexpr int kNP = 3;    // P ring (TMEM)
@@ -540,13 +559,13 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
   if (tid == 0) {
     for (int i = 0; i < kNR; ++i) {
       mbar_init(&s.raw_full[i], 1);
-      mbar_init(&s.raw_empty[i], 1);
+      mbar_init(&s.raw_empty[i], 2);  // one commit per tile issuer
     }
     for (int i = 0; i < kNP; ++i) {
       mbar_init(&s.p_full[i], kDwProdWarps);
-      mbar_init(&s.p_empty[i], 1);
+      mbar_init(&s.p_empty[i], 2);
     }
-    mbar_init(&s.done, 1);
+    mbar_init(&s.done, 2);
     fence_barrier_init();
   }
   if (warp == kDwMmaWarp) tmem_alloc(&s.tmem_base, 512);
@@ -568,10 +587,13 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
         bulk_g2s(s.e1raw[sr], blk + kBlkE1 + i0 * 32, 4 * 128, &s.raw_full[sr]);
       }
     }
-  } else if (warp == kDwMmaWarp) {
-    // whole warp converged, instructions on the elected lane (see the forward kernel)
+  } else if (warp >= kDwMmaWarp) {
+    // whole warp converged, instructions on the elected lane (see the forward kernel); one issuer
+    // warp per M tile so that their barrier waits and commits overlap
     constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
     const uint64_t d_r = make_desc(smem_u32(s.rstack), 16, 1024);
+    const int tt = warp - kDwMmaWarp;
+    const uint32_t d = tmem_base + tt * 64;
     int sp = 0, php = 0;
     for (int kb = 0; kb < nblk; ++kb) {
       const uint32_t sr = kb & (kNR - 1);
@@ -579,17 +601,13 @@ tucker_tc_bwd_dw_kernel(const float* __restrict__ scratch, int nblk_alloc, int n
       mbar_wait(&s.p_full[sp], php);
       tc_fence_after_sync();
 #pragma unroll
-      for (int tt = 0; tt < 2; ++tt) {
-        const uint32_t d = tmem_base + tt * 64;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t a_hi = tmem_base + 128 + (sp * 2 + tt) * 64 + ks * 8, a_lo = a_hi + 32;
-          const uint64_t b_hi = desc_at(d_r, sr * kTile + ks * 32);
-          const uint64_t b_lo = desc_at(d_r, sr * kTile + 64 * 128 + ks * 32);
-          mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, (kb | ks) ? 1u : 0u);
-          mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
-          mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
-        }
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a_hi = tmem_base + 128 + (sp * 2 + tt) * 64 + ks * 8, a_lo = a_hi + 32;
+        const uint64_t b_hi = desc_at(d_r, sr * kTile + ks * 32);
+        const uint64_t b_lo = desc_at(d_r, sr * kTile + 64 * 128 + ks * 32);
+        mma_tf32_ts_warp(d, a_hi, b_hi, idesc_n64, (kb | ks) ? 1u : 0u);
+        mma_tf32_ts_warp(d, a_hi, b_lo, idesc_n64, 1u);
+        mma_tf32_ts_warp(d, a_lo, b_hi, idesc_n64, 1u);
       }
       mma_commit_warp(&s.raw_empty[sr]);
       mma_commit_warp(&s.p_empty[sp]);

@@ -614,6 +614,31 @@ class _PlanFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- per-step timing
+def _exec_step_flops(rt: PlanRuntime, es: ExecStep, batch: int) -> tuple[int, int]:
+    """Algorithmic floating-point operations (2 per multiply-add of the contraction the reference
+    layer states) of the forward and backward launches of one step; the backward of
+    a sum-product contraction is two contractions of the same size (input and weight gradients).
+    The 3xTF32 kernels execute three tensor-core products per algorithmic product."""
+    s = rt.plan.steps[es.out_sid]
+    if s.is_input:
+        return 0, 0
+    F, H, Ki, Ko = s.num_folds, s.arity, s.num_input_units, s.num_output_units
+    if s.kind == "tucker":
+        red = Ki ** H
+    elif s.kind == "sum":
+        red = H * Ki
+    elif s.kind == "cpt":
+        red = Ki
+    else:
+        return 0, 0
+    units = batch
+    if es.kind == STEP_TABLE_DENSE:
+        first = rt.plan.steps[es.sids[0]]
+        units = int(first.config.get("num_categories", first.config.get("num_states", 0)))
+    fwd = 2 * F * units * Ko * red
+    return fwd, 2 * fwd
+
+
 def _exec_step_bytes(rt: PlanRuntime, es: ExecStep, batch: int) -> tuple[int, int]:
     """Algorithmic HBM bytes of the forward and of the backward launches of one execution step:
     every tensor the step must read or write counted once, fp32 (see DESIGN.md "Kernels")."""
@@ -692,8 +717,10 @@ def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: i
         for i, es in enumerate(steps):
             t, n = timed(fwd, i, i + 1, 0)
             fb, bb = _exec_step_bytes(rt, es, B)
+            ff, bf = _exec_step_flops(rt, es, B)
             res.append({"step": es.label, "kind": es.label.split(":")[1], "F": plan.steps[es.out_sid].num_folds,
-                        "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb})
+                        "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb,
+                        "fwd_flops": ff, "bwd_flops": bf})
         for i in reversed(range(S)):
             t, n = timed(bwd, i, i + 1, 0)
             res[i + 1]["bwd_ms"] = t
