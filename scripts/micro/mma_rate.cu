@@ -14,7 +14,8 @@ __device__ __forceinline__ void mma_ss_elect(uint32_t d, uint64_t a, uint64_t b,
   asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__global__ void __launch_bounds__(128, 1) k(long long* out, int n_cols, int ts, int reps) {
+template <int ts>
+__global__ void __launch_bounds__(128, 1) k(long long* out, int n_cols, int reps) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -78,19 +79,20 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int n_cols, int ts, 
 
 int main() {
   long long* d; cudaMalloc(&d, 64);
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int reps = 512;
-  for (int ts = 2; ts < 6; ++ts)
+  void (*kern[6])(long long*, int, int) = {k<0>, k<1>, k<2>, k<3>, k<4>, k<5>};
+  for (int ts = 0; ts < 6; ++ts)
     for (int n : {64, 128, 256}) {
       long long h[8];
+      cudaFuncSetAttribute(kern[ts], cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
       for (int it = 0; it < 2; ++it) {
-        k<<<1, 128, 64 * 1024>>>(d, n, ts, reps);
+        kern[ts]<<<1, 128, 64 * 1024>>>(d, n, reps);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
       cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
       printf("%s N=%3d: issue %.1f clk/mma, issue+drain %.1f clk/mma, commit %lld, drain %lld, try_wait(satisfied) %lld, fence.proxy.async %lld\n",
-             ts == 0 ? "SS" : ts == 1 ? "TS" : ts == 2 ? "SS-elect" : ts == 3 ? "TS-elect" : ts == 4 ? "TS-elect-const" : "SS-elect-const", n, (double)h[0] / reps, (double)(h[0] + h[1] + h[2]) / reps, h[1], h[2], h[3], h[4]);
+             ts == 0 ? "SS-lane0" : ts == 1 ? "TS-lane0" : ts == 2 ? "SS-elect" : ts == 3 ? "TS-elect" : ts == 4 ? "TS-elect-const" : "SS-elect-const", n, (double)h[0] / reps, (double)(h[0] + h[1] + h[2]) / reps, h[1], h[2], h[3], h[4]);
     }
   return 0;
 }
