@@ -140,7 +140,7 @@ int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
 // samples in ascending order -- and then each warp sums the gradient rows of whole buckets in
 // registers and writes each table row once.  No floating-point atomics: the result is
 // deterministic, and every g row is read exactly once as one contiguous segment.
-constexpr int kTableBwdThreads = 512;
+constexpr int kTableBwdThreads = 1024;
 constexpr int kTableMaxCons = 8;
 
 template <int NT>  // units per lane: a CTA covers 32*NT units
@@ -162,7 +162,6 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
   const int64_t b_begin = (int64_t)blockIdx.x * chunk;
   const int n = (int)(min64(B, b_begin + chunk) - b_begin);
 
-  for (int i = tid; i < V; i += blockDim.x) cnt[i] = 0;
   if (tid == 0) {
     // rows of the gradient arena this fold sums (its consumers), resolved once
     if (gs.cons_ptr == nullptr) {
@@ -175,18 +174,42 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
       for (int c = 0; c < nc && c < kTableMaxCons; ++c) grows[c] = gs.garena + gs.B * gs.cons_rows[c0 + c];
     }
   }
+  // Stable bucket sort of the samples by state, every warp on its own contiguous segment:
+  //   (1) per-warp histogram wcnt[warp][v] (match_any groups, no atomics),
+  //   (2) bucket offsets = exclusive scan over states of the totals; per-warp cursors inside a
+  //       bucket = prefix over the warps (lower segments first, so the order is the sample order),
+  //   (3) every warp fills its segment through its cursors.
+  int* wcnt = reinterpret_cast<int*>(list + chunk);      // [nwarps][V]
+  const int seg = ((n + nwarps - 1) / nwarps + 31) & ~31;  // samples per warp, multiple of 32
+  const int i_begin = warp * seg, i_end = min(n, i_begin + seg);
+  for (int i = tid; i < nwarps * V; i += blockDim.x) wcnt[i] = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int64_t b = b_begin + i;
+  for (int i0 = i_begin; i0 < i_end; i0 += 32) {
+    const int i = i0 + lane;
     int v = 0xFFFF;
-    if (!read_mask(maskT, mask_ld, var, b)) {
-      v = min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1);
-      atomicAdd(&cnt[v], 1);
+    if (i < i_end) {
+      const int64_t b = b_begin + i;
+      if (!read_mask(maskT, mask_ld, var, b))
+        v = min(max(read_state(xT, x_is_float, (int64_t)var * B + b), 0), V - 1);
+      xs[i] = (uint16_t)v;
     }
-    xs[i] = (uint16_t)v;
+    const bool valid = v != 0xFFFF;
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? v : 0x10000 + lane);
+    if (valid && lane == __ffs(same) - 1) wcnt[warp * V + v] += __popc(same);
+    __syncwarp();
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of the counts, then the stable fill
+  for (int v = tid; v < V; v += blockDim.x) {  // totals; wcnt becomes the prefix over the warps
+    int run = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const int c = wcnt[w * V + v];
+      wcnt[w * V + v] = run;
+      run += c;
+    }
+    cnt[v] = run;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the bucket sizes
     int carry = 0;
     for (int i0 = 0; i0 < V; i0 += 32) {
       const int i = i0 + lane;
@@ -197,30 +220,26 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (i < V) {
-        start[i] = carry + incl - c;
-        cnt[i] = carry + incl - c;  // becomes the fill cursor
-      }
+      if (i < V) start[i] = carry + incl - c;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) start[V] = carry;
+  }
+  __syncthreads();
+  for (int i0 = i_begin; i0 < i_end; i0 += 32) {
+    const int i = i0 + lane;
+    const int xv = i < i_end ? xs[i] : 0xFFFF;
+    const bool valid = xv != 0xFFFF;
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? xv : 0x10000 + lane);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    int base = 0;
+    if (valid) base = start[xv] + wcnt[warp * V + xv];
     __syncwarp();
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      const int xv = i < n ? xs[i] : 0xFFFF;
-      const bool valid = xv != 0xFFFF;
-      const int key = valid ? xv : 0x10000 + lane;
-      const unsigned same = __match_any_sync(0xffffffffu, key);
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      int base = 0;
-      if (valid) base = cnt[xv];
-      __syncwarp();
-      if (valid) {
-        list[base + rank] = (uint16_t)i;
-        if (rank == __popc(same) - 1) cnt[xv] = base + rank + 1;  // last lane of the group
-      }
-      __syncwarp();
+    if (valid) {
+      list[base + rank] = (uint16_t)i;
+      if (rank == __popc(same) - 1) wcnt[warp * V + xv] += rank + 1;  // last lane of the group
     }
+    __syncwarp();
   }
   __syncthreads();
   // sum whole buckets: warp per state, lanes over units, 8 rows (8*NT loads per lane) in flight
@@ -295,7 +314,7 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   int64_t chunk;
   table_bwd_config(d, c.B, splits, chunk);
   const int V = d.num_states;
-  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 4 + 16;
+  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 4 + (size_t)(kTableBwdThreads / 32) * V * 4 + 16;
   if (smem > 200 * 1024) {
     set_error("table_bwd: %d states do not fit shared memory", V);
     return CKB_ERR_UNSUPPORTED;
