@@ -101,3 +101,48 @@ def test_tucker_determinism_and_row_independence(plan64, dev):
         assert torch.equal(cc(x), y)
         assert torch.equal(cc(x[:7]), y[:7])
         assert torch.equal(cc(x[256:300]), y[256:300])
+
+
+def test_full_size_properties(dev):
+    """BASELINE.json configs[2] (QuadTree 28x28, Tucker, K=64, B=2048): size-independent properties
+    plus the reference's own values on the fixture rows embedded in the batch."""
+    from cirkit_b200 import B200Circuit, IntegrateQuery
+
+    g = Golden("qt28_tucker_k64")
+    cc = B200Circuit(g.plan)
+    with torch.no_grad():
+        for p, v in zip(cc.leaves, g.leaves(torch.float32)):
+            p.copy_(v)
+    cc = cc.to(dev)
+    B = 2048
+    x = torch.randint(0, 256, (B, 784), generator=torch.Generator().manual_seed(0))
+    n_fix = g.x().shape[0]
+    x[:n_fix] = g.x()
+    xd = x.to(dev)
+    y = cc(xd)
+    # (1) reference values (float64) of the fixture rows
+    ref = g.y()
+    err = (y[:n_fix].detach().double().cpu() - ref).abs()
+    assert bool((err <= FWD_RTOL * ref.abs() + FWD_ATOL).all()), f"forward err {err.max().item():.3e}"
+    # (2) run-to-run determinism
+    assert torch.equal(cc(xd), y)
+    # (3) a normalised circuit integrates to one
+    with torch.no_grad():
+        z = IntegrateQuery(cc)(xd[:64], integrate_vars=torch.ones(1, 784, dtype=torch.bool))
+    assert z.abs().max().item() < 1e-3
+    # (4) every row of d(theta) of a softmax-parameterised weight sums to zero
+    (-y.mean()).backward()
+    for p in cc.leaves:
+        assert torch.isfinite(p.grad).all()
+        assert p.grad.double().sum(dim=-1).abs().max().item() < 2e-6
+    # (5) the gradient of the mean log-likelihood is linear in the batch
+    grads = [p.grad.clone() for p in cc.leaves]
+    halves = []
+    for sl in (slice(0, B // 2), slice(B // 2, B)):
+        for p in cc.leaves:
+            p.grad = None
+        (-cc(xd[sl]).mean()).backward()
+        halves.append([p.grad.clone() for p in cc.leaves])
+    for ga, h0, h1 in zip(grads, *halves):
+        half = 0.5 * (h0.double() + h1.double())
+        assert (half - ga.double()).abs().max().item() <= max(2e-6, 1e-4 * ga.abs().max().item())
