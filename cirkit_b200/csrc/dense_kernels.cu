@@ -624,6 +624,10 @@ int dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
 int kronecker_into(const ckb_step_desc_t& d, Ctx& c, float* dst);
 int kronecker_bwd_from(const ckb_step_desc_t& d, Ctx& c, const float* gsrc);
 
+bool tucker_root_ok(const ckb_step_desc_t& d);
+size_t tucker_root_ws(const ckb_step_desc_t& d, int64_t B);
+int tucker_root_fwd(const ckb_step_desc_t& d, Ctx& c);
+int tucker_root_bwd(const ckb_step_desc_t& d, Ctx& c);
 bool tucker_tc_ok(const ckb_step_desc_t& d);
 size_t tucker_tc_ws(const ckb_step_desc_t& d, int64_t B);
 int tucker_tc_fwd(const ckb_step_desc_t& d, Ctx& c);
@@ -631,6 +635,7 @@ int tucker_tc_bwd(const ckb_step_desc_t& d, Ctx& c);
 
 size_t tucker_ws(const ckb_step_desc_t& d, int64_t B) {
   if (tucker_tc_ok(d)) return tucker_tc_ws(d, B) + 256;
+  if (tucker_root_ok(d)) return tucker_root_ws(d, B) + 256;
   const size_t kron = (size_t)d.num_folds * B * d.k_in * d.k_in * 4;
   return 2 * kron + run_dense_bwd_ws(d.num_folds, 1, d.k_out, d.k_in * d.k_in, B) + 256;
 }
@@ -661,6 +666,7 @@ static DenseArgs tucker_args(const ckb_step_desc_t& d, Ctx& c, float* kron) {
 int tucker_fwd(const ckb_step_desc_t& d, Ctx& c) {
   if (int rc = tucker_check(d)) return rc;
   if (tucker_tc_ok(d)) return tucker_tc_fwd(d, c);
+  if (tucker_root_ok(d)) return tucker_root_fwd(d, c);
   const size_t kron_bytes = (size_t)d.num_folds * c.B * d.k_in * d.k_in * 4;
   if (c.ws_bytes < kron_bytes) {
     set_error("tucker_fwd: workspace too small");
@@ -674,6 +680,7 @@ int tucker_fwd(const ckb_step_desc_t& d, Ctx& c) {
 int tucker_bwd(const ckb_step_desc_t& d, Ctx& c) {
   if (int rc = tucker_check(d)) return rc;
   if (tucker_tc_ok(d)) return tucker_tc_bwd(d, c);
+  if (tucker_root_ok(d)) return tucker_root_bwd(d, c);
   const size_t kron_bytes = ((size_t)d.num_folds * c.B * d.k_in * d.k_in * 4 + 255) & ~(size_t)255;
   if (c.ws_bytes < 2 * kron_bytes) {
     set_error("tucker_bwd: workspace too small");

@@ -499,6 +499,10 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
           }
         }
       }
+      // The next tile's rows are requested AFTER the proxy fence: fence.proxy.async also waits for
+      // the global loads the thread has in flight (measured: -6 % on the backward launches);
+      // bit 4 of CKB_OPT_TC_FAST_MATH restores the refill inside the transform for A/B runs.
+      const bool late = (flags & 16) == 0;
 #ifdef CKB_TIMELINE
       // experiments: bit 6 = never reload (compute on stale registers), bit 3 = no math (the loads
       // are consumed by a dummy reduction)
@@ -517,10 +521,6 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
       } else if (flags & 64) bwd_transform<FAST, 0>(L, st, off, rhi, bsub);
       else
 #endif
-      // The next tile's rows are requested AFTER the proxy fence: fence.proxy.async also waits for
-      // the global loads the thread has in flight (measured: -6 % on the backward launches);
-      // bit 4 of CKB_OPT_TC_FAST_MATH restores the refill inside the transform for A/B runs.
-      const bool late = (flags & 16) == 0;
       if (it + 1 >= n_tiles || late) bwd_transform<FAST, 0>(L, st, off, rhi, bsub);
       else if (st.rows_left >= TM - warp * 8 - bsub) bwd_transform<FAST, 2>(L, st, off, rhi, bsub);
       else bwd_transform<FAST, 1>(L, st, off, rhi, bsub);
