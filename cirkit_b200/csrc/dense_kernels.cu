@@ -241,6 +241,7 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
     const int rc = dense_tc_fwd(a, F, c);  // tensor-core path for the hot shape
     if (rc <= 0) return rc;
   }
+  if (dense32_ok(a)) return dense32_fwd(a, F, c);
   if (dense_ko1_ok(a)) {
     dim3 grid(dense_ko1_blocks(F, a.B), F);
     dense_ko1_fwd_kernel<<<grid, 256, 0, c.stream>>>(a);
@@ -506,6 +507,7 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
 static size_t run_dense_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
   if (Ko == 1 && Kred <= 32 * kKo1MaxPerLane) return (size_t)dense_ko1_blocks(F, B) * F * Kred * 4;
   const size_t tc = dense_tc_bwd_ws(F, H, Ko, Kred, B);
+  if (Ko == 32 && Kred == 32 && H <= 2) return dense32_bwd_ws(F, B);
   if (!dense_small_ok(H, Ko, Kred)) return tc;
   int SW, splits;
   int64_t chunk;
@@ -520,6 +522,7 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
     if (rc <= 0) return rc;
   }
   const size_t n = (size_t)F * a.Ko * a.Kred;
+  if (dense32_ok(a)) return dense32_bwd(a, F, dW, c, ws, ws_bytes);
   if (dense_ko1_ok(a)) {
     const int blocks = dense_ko1_blocks(F, a.B);
     a.dWp = dW;

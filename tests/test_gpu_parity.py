@@ -121,9 +121,12 @@ def test_benchmark_circuits_vs_reference(name, dev):
         tol = grad_tolerance(torch.tensor(float(gmax)), ll_max=ll_max, w_max=w_max)
         err = (flat[idx] - probe).abs().max().item()
         assert err <= tol, f"leaf {i} probe: {err:.3e} > {tol:.3e}"
-        # L1 norm of the whole tensor: relative 2e-3 plus the per-element fp32 rounding floor
+        # L1 norm of the whole tensor: relative 2e-3 plus the per-element fp32 rounding floor.  The
+        # floor is the one grad_tolerance derives (4 ulp(1) = 5e-7 per element): near the root all
+        # units of a layer agree to below fp32 resolution (ulp(4357) = 4.9e-4), so a root-weight
+        # gradient whose float64 value is 1.7e-7 per element may legitimately come out as exactly 0.
         got_abs = flat.abs().sum().item()
-        assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * 1e-7, f"leaf {i} abs-sum {got_abs} vs {gabs}"
+        assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * 5e-7, f"leaf {i} abs-sum {got_abs} vs {gabs}"
 
 
 @pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_tucker_k4", "rbt12_gaussian_k5"])
@@ -301,3 +304,39 @@ def test_state_dict_roundtrip(dev):
         assert not torch.equal(other(x), cc(x))
         other.load_state_dict(sd)
         assert torch.equal(other(x), cc(x))
+
+
+@pytest.mark.parametrize("name,batch", [("qt8_cp_k4", 131), ("qg8_cp_k4", 37), ("qt8x4_cpt_k5", 260)])
+def test_k32_kernels_vs_oracle(name, batch, dev):
+    """The dedicated Ki = Ko = 32 kernels (dense32_kernels.cu, BASELINE.json configs[1]): reference
+    structures resized to 32 units, ragged batches, against the float64 oracle."""
+    import dataclasses
+
+    from cirkit_b200 import B200Circuit
+    from cirkit_b200.plan import seeded_leaves
+    from oracle import OracleCircuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden(name)
+    k0 = g.plan.steps[0].num_output_units
+    plan = dataclasses.replace(g.plan, meta={"units": k0}).with_units(32)
+    cc = B200Circuit(plan, seed=5).to(dev)
+    oc = OracleCircuit(plan, dtype=torch.float64)
+    with torch.no_grad():
+        for q, v in zip(oc.leaves, seeded_leaves(plan, 5)):
+            q.copy_(v)
+    x = make_inputs(plan, batch, seed=batch)
+    y = cc(x.to(dev))
+    yo = oc(x)
+    _check_forward(y, yo.detach())
+    w = torch.randn(batch, 1, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    (y * w.to(dev, torch.float32)).sum().backward()
+    (yo * w).sum().backward()
+    ll_max = float(yo.detach().abs().max())
+    for i, (p, q) in enumerate(zip(cc.leaves, oc.leaves)):
+        gr = torch.zeros_like(q) if q.grad is None else q.grad
+        got = torch.zeros_like(p) if p.grad is None else p.grad
+        err = (got.double().cpu() - gr).abs().max().item()
+        tol = grad_tolerance(gr, gout_l1=float(w.abs().sum()), ll_max=ll_max,
+                             w_max=float(torch.softmax(q.detach(), dim=-1).max()))
+        assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
