@@ -14,12 +14,13 @@ namespace {
 
 constexpr int K32 = 32;
 constexpr int kWarps = 8;
-constexpr int kS = 4;  // samples per warp iteration
+constexpr int kS = 4;   // samples per warp iteration (backward)
+constexpr int kSF = 4;  // forward (8 in flight measured slower: 80 registers, one CTA fewer per SM)
 
 __device__ __forceinline__ float ldg_or(const float* p, bool ok, float other) { return ok ? __ldg(p) : other; }
 
 __global__ void __launch_bounds__(kWarps * 32) dense32_fwd_kernel(DenseArgs a) {
-  __shared__ __align__(16) float es[kWarps][kS][K32];
+  __shared__ __align__(16) float es[kWarps][kSF][K32];
   const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* x0 = in_row(a, f, 0);
   const float* x1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
@@ -33,22 +34,22 @@ __global__ void __launch_bounds__(kWarps * 32) dense32_fwd_kernel(DenseArgs a) {
     }
   }
   float* yf = a.y + (int64_t)f * a.B * K32;
-  for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + warp) * kS; b0 < a.B; b0 += (int64_t)gridDim.x * kWarps * kS) {
-    float u[kS], m[kS];
+  for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + warp) * kSF; b0 < a.B; b0 += (int64_t)gridDim.x * kWarps * kSF) {
+    float u[kSF], m[kSF];
 #pragma unroll
-    for (int s = 0; s < kS; ++s) {
+    for (int s = 0; s < kSF; ++s) {
       const bool ok = b0 + s < a.B;
       u[s] = ldg_or(x0 + (b0 + s) * K32 + lane, ok, 0.f);
       if (x1) u[s] += ldg_or(x1 + (b0 + s) * K32 + lane, ok, 0.f);
     }
 #pragma unroll
-    for (int s = 0; s < kS; ++s) {
+    for (int s = 0; s < kSF; ++s) {
       m[s] = clamp_max(warp_max(u[s]));
       es[warp][s][lane] = sm100::fast_exp(u[s] - m[s]);
     }
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < kS; ++s) {
+    for (int s = 0; s < kSF; ++s) {
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kWarps * 32) dense32_fwd_kernel(DenseArgs a) {
 }
 
 // backward: r = g * exp(m - y); du[i] = e[i] * sum_o r[o] W[o,i]; dW[o,i] += r[o] e[i]
-__global__ void __launch_bounds__(kWarps * 32) dense32_bwd_kernel(DenseArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 2) dense32_bwd_kernel(DenseArgs a) {
   __shared__ __align__(16) float es[kWarps][kS][K32];
   __shared__ __align__(16) float rs[kWarps][kS][K32];
   __shared__ float red[kWarps][K32][K32 + 1];
@@ -83,6 +84,13 @@ __global__ void __launch_bounds__(kWarps * 32) dense32_bwd_kernel(DenseArgs a) {
   const float* yf = a.y + (int64_t)f * a.B * K32;
   float* gin = a.gin + (int64_t)f * a.B * K32;
   const bool want_dw = a.dWp != nullptr;
+  // the usual case (a tree): one consumer row, resolved once instead of per sample
+  const float* grow = nullptr;
+  if (a.gs.cons_ptr == nullptr) {
+    grow = a.gs.garena + (int64_t)f * a.gs.B * K32;
+  } else if (a.gs.cons_ptr[f + 1] - a.gs.cons_ptr[f] == 1) {
+    grow = a.gs.garena + a.gs.B * a.gs.cons_rows[a.gs.cons_ptr[f]];
+  }
   for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + warp) * kS; b0 < a.B; b0 += (int64_t)gridDim.x * kWarps * kS) {
     float u[kS], yv[kS], g[kS];
 #pragma unroll
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(kWarps * 32) dense32_bwd_kernel(DenseArgs a) {
       u[s] = ldg_or(x0 + (b0 + s) * K32 + lane, ok, 0.f);
       if (x1) u[s] += ldg_or(x1 + (b0 + s) * K32 + lane, ok, 0.f);
       yv[s] = ldg_or(yf + (b0 + s) * K32 + lane, ok, 0.f);
-      g[s] = ok ? pull_grad(a.gs, f, b0 + s, K32, lane) : 0.f;
+      g[s] = !ok ? 0.f : (grow ? __ldg(grow + (b0 + s) * K32 + lane) : pull_grad(a.gs, f, b0 + s, K32, lane));
     }
     float e[kS];
 #pragma unroll
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(kWarps * 32) dense32_bwd_kernel(DenseArgs a) {
 }
 
 int dense32_splits(int F, int64_t B) {
-  return (int)max64(1, min64(ceil_div(B, kWarps * kS), ceil_div(8 * kNumSMs, F)));
+  return (int)max64(1, min64(ceil_div(B, kWarps * kSF), ceil_div(8 * kNumSMs, F)));
 }
 
 }  // namespace
