@@ -66,12 +66,45 @@ def all_gather_rows(local: Tensor, num_rows: int, group=None) -> Tensor:
     return torch.cat(blocks)
 
 
-def all_reduce_gradients(params: Iterable[Tensor], *, average: bool = False, group=None) -> int:
+def _flat_gradient(params: list, flat: Tensor | None) -> Tensor | None:
+    """`flat` if every gradient is a piece of that one buffer and together they fill it (the CUDA
+    runtime returns its parameter gradients as views of one flat tensor, `runtime.last_flat_grad`):
+    one collective instead of one per parameter tensor."""
+    if flat is None or flat.numel() == 0:
+        return None
+    lo = flat.data_ptr()
+    hi = lo + flat.numel() * flat.element_size()
+    covered, n = 0, 0
+    for p in params:
+        if not p.requires_grad:
+            continue
+        g = p.grad
+        if g is None or g.dtype != flat.dtype or g.device != flat.device or not g.is_contiguous():
+            return None
+        if not (lo <= g.data_ptr() and g.data_ptr() + g.numel() * g.element_size() <= hi):
+            return None
+        covered += g.numel()
+        n += 1
+    if covered + 4 * n < flat.numel():
+        return None  # the buffer holds more than these parameters' gradients
+    return flat
+
+
+def all_reduce_gradients(params: Iterable[Tensor], *, average: bool = False, group=None,
+                         flat: Tensor | None = None) -> int:
     """Sum (or average) `.grad` of every parameter over the ranks, in place.  Parameters without
     a gradient on this rank contribute zeros, so all ranks issue the same collectives.  Returns
     the number of bytes reduced."""
     world, _ = _world(group)
     total = 0
+    params = list(params)
+    flat = _flat_gradient(params, flat)
+    if flat is not None:
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.div_(world)
+        return flat.numel() * flat.element_size()
     for p in params:
         if not p.requires_grad:
             continue
@@ -127,7 +160,8 @@ class BatchShardedCircuit(nn.Module):
         return -self.circuit(x_local).sum() / num_rows
 
     def sync_gradients(self, *, average: bool = False) -> int:
-        return all_reduce_gradients(self.circuit.parameters(), average=average, group=self.group)
+        flat = getattr(getattr(self.circuit, "runtime", None), "last_flat_grad", None)
+        return all_reduce_gradients(self.circuit.parameters(), average=average, group=self.group, flat=flat)
 
     def broadcast_parameters(self, src: int = 0) -> None:
         """Make every replica start from rank `src`'s parameters."""

@@ -375,6 +375,7 @@ class PlanRuntime:
         self.last_launches = 0
         self.keep_arena = False
         self.last_arena: Tensor | None = None
+        self.last_flat_grad: Tensor | None = None  # flat buffer behind the last backward's gradients
 
     def step_output(self, sid: int, batch: int) -> Tensor:
         """(F, B, K) activations of plan step `sid` from the last forward pass (keep_arena=True)."""
@@ -529,11 +530,18 @@ def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Cal
 def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tuple[object, list]:
     grads = (C.c_void_p * rt.n_slots)()
     outs: list[Tensor | None] = []
-    for b, p, nd in zip(rt.bindings, P, need):
+    # all requested parameter gradients are views of ONE flat buffer (16-byte aligned pieces), so
+    # that a data-parallel wrapper can sum them over the ranks with a single all-reduce
+    sizes = [(-(-p.numel() // 4) * 4) if nd else 0 for p, nd in zip(P, need)]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=st.device) if sum(sizes) else None
+    rt.last_flat_grad = flat
+    off = 0
+    for b, p, nd, sz in zip(rt.bindings, P, need, sizes):
         if not nd:
             outs.append(None)
             continue
-        g = torch.empty_like(p)
+        g = flat[off : off + p.numel()].view(p.shape)
+        off += sz
         outs.append(g)
         grads[b.src_slot] = g.data_ptr()
         if b.native is not None:
