@@ -32,16 +32,40 @@ constexpr int KK = 64;   // Ki = Ko
 // TRANSPOSED = false: rows o, K = i  (forward:  S = e W^T)
 // TRANSPOSED = true : rows i, K = o  (backward: T = r W)
 constexpr uint32_t kWBlock = 128 * 128;  // bytes per k-block of the stacked weight tile
-template <bool TRANSPOSED>
-__device__ __forceinline__ void stage_weights(const float* Wf, uint32_t w, int tid, int nthreads) {
-  for (int idx = tid; idx < KK * KK; idx += nthreads) {
-    const int o = idx >> 6, i = idx & 63;
-    float hi, lo;
-    split_tf32(Wf[idx], hi, lo);
-    const int row = TRANSPOSED ? i : o, k = TRANSPOSED ? o : i;
-    const uint32_t off = (uint32_t)(k >> 5) * kWBlock + swz_off(row, k & 31);
-    sts32(w + off, hi);
-    sts32(w + off + KK * 128, lo);  // (row + 64) & 7 == row & 7: same swizzle
+template <bool TRANSPOSED, int NTHREADS>
+__device__ __forceinline__ void stage_weights(const float* Wf, uint32_t w, int tid) {
+  // All of this thread's 16-byte pieces are requested before the first one is used: the stores
+  // below are volatile asm, so a load inside their loop would be serialised behind them (one
+  // L2 / HBM round trip per piece; the CTA's set-up took 5 us that way).
+  constexpr int kPieces = KK * KK / 4;
+  constexpr int PER = (kPieces + NTHREADS - 1) / NTHREADS;
+  float4 v[PER];
+#pragma unroll
+  for (int n = 0; n < PER; ++n) {
+    const int p = tid + n * NTHREADS;
+    v[n] = p < kPieces ? __ldg(reinterpret_cast<const float4*>(Wf) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int n = 0; n < PER; ++n) {
+    const int p = tid + n * NTHREADS;
+    if (p < kPieces) {
+      const int o = p >> 4, i0 = (p & 15) * 4;
+      float4 hi, lo;
+      split4(v[n], hi, lo);
+      if (TRANSPOSED) {  // rows i0..i0+3, column o
+        const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t off = (uint32_t)(o >> 5) * kWBlock + swz_off(i0 + t, o & 31);
+          sts32(w + off, h[t]);
+          sts32(w + off + KK * 128, l[t]);  // (row + 64) & 7 == row & 7: same swizzle
+        }
+      } else {  // row o, columns i0..i0+3: one 16-byte chunk
+        const uint32_t off = (uint32_t)(i0 >> 5) * kWBlock + swz_off(o, i0 & 31);
+        sts128(w + off, hi);
+        sts128(w + off + KK * 128, lo);
+      }
+    }
   }
 }
 
@@ -96,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s.tmem_base, 256);
-  stage_weights<false>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid, kThreads);
+  stage_weights<false, kThreads>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -417,7 +441,7 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 256);
-  stage_weights<true>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid, kBwdThreads);
+  stage_weights<true, kBwdThreads>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
