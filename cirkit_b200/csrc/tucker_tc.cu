@@ -39,12 +39,20 @@ int tucker_debug_read(void* dst, size_t bytes) {
   do {                                                                                     \
     if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 24) g_dbg_tk[16 + (kb) * 16 + (slot)] = clock64(); \
   } while (0)
+#define TKMARK(slot)                                                                       \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0) g_dbg_tk[slot] = clock64();                    \
+  } while (0)
 #define DXDBG(i, slot)                                                                     \
   do {                                                                                     \
     if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= 8 && (i) < 32) g_dbg_tk[512 + ((i) - 8) * 16 + (slot)] = clock64(); \
   } while (0)
 #else
 #define TKDBG(kb, slot) do { } while (0)
+#define TKMARK(slot)                                                                       \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0) g_dbg_tk[slot] = clock64();                    \
+  } while (0)
 #define DXDBG(i, slot) do { } while (0)
 #endif
 
@@ -106,6 +114,7 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y;
   const int64_t b0 = (int64_t)blockIdx.x * TM;
+  if (tid == 0) TKMARK(0);
 
   if (tid == 0) {
     for (int i = 0; i < kNS; ++i) {
@@ -124,6 +133,7 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  if (tid == 0) TKMARK(1);
 
   if (warp < 8) {
     // ================= A producers =================
@@ -153,6 +163,7 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
         e2[jh * 16 + 4 * c + 3] = valid ? exp_nonpos<FAST>(v.w - m2) : 0.f;
       }
     if (h == 0) s.msum[row] = fmaxf(m1 + m2, -FLT_MAX);
+    if (tid == 0) TKMARK(2);
     const uint32_t abase = tmem_base + ((uint32_t)(q * 32) << 16) + kColA + h * 16;
     float x1n = __ldg(x1);
     for (int i = 0; i < KK; ++i) {
@@ -255,6 +266,7 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
       tc_fence_before_sync();
       mbar_arrive(&s.mempty[buf]);
     }
+    if (tid == 12 * 32) TKMARK(3);
     const int64_t b = b0 + row;
     if (b < a.B) {
       const float ms = s.msum[row];
@@ -272,9 +284,78 @@ tucker_tc_fwd_kernel(DenseArgs a, const float* __restrict__ wimg) {
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) TKMARK(4);
   if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (tid == 0) TKMARK(5);
+}
+
+// ==========================================================================================
+// Backward, part 0: e1 = exp(x1 - m1), e2 = exp(x2 - m2) and r = g / S = g exp(m1 + m2 - y) for
+// 32 samples of a fold per CTA, written as the scratch block parts 1 and 2 read: stacked
+// [r_hi | r_lo] rows, e1 rows, e2 rows, each [unit][32 samples], 16-byte chunks xor-swizzled.
+// HBM-bound streaming kernel (coalesced 16-byte loads, half-warp row maxima, transpose through
+// shared memory).
+// ==========================================================================================
+constexpr int kBlkFloats = 128 * 32 + 64 * 32 + 64 * 32;  // 8192 floats = 32 KB
+constexpr int kBlkE1 = 128 * 32, kBlkE2 = 128 * 32 + 64 * 32;
+__device__ __forceinline__ int blk_off(int unit, int bcol) {
+  return unit * 32 + ((((bcol >> 2) ^ unit) & 7) << 2) + (bcol & 3);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256) tucker_prep_kernel(DenseArgs a, float* scratch, int nblk) {
+  __shared__ float T[4][KK][33];  // r_hi, r_lo, e1, e2 as [unit][sample]
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const float* x1 = in_row(a, f, 0);
+  const float* x2 = in_row(a, f, 1);
+  const float* yf = a.y + (int64_t)f * a.B * KK;
+  const int cbeg = a.gs.cons_ptr[f], cend = a.gs.cons_ptr[f + 1];
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    const int idx4 = tid + n * 256;
+    const int row = idx4 >> 4, c4 = (idx4 & 15) * 4;  // 16 lanes per sample row
+    const int64_t b = b0 + row;
+    const bool valid = b < a.B;
+    const int64_t e = (valid ? b : 0) * KK + c4;
+    const float4 v1 = ldg_stream(x1 + e), v2 = ldg_stream(x2 + e), yv = ldg_stream(yf + e);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = cbeg; k < cend; ++k) {
+      const float4 z = ldg_stream(a.gs.garena + a.gs.B * a.gs.cons_rows[k] + e);
+      g.x += z.x; g.y += z.y; g.z += z.z; g.w += z.w;
+    }
+    const float m1 = clamp_max(half_warp_max(max4(v1)));
+    const float m2 = clamp_max(half_warp_max(max4(v2)));
+    const float ms = fmaxf(m1 + m2, -FLT_MAX);
+    const float z = valid ? 1.f : 0.f;
+    const float e1[4] = {z * exp_nonpos<FAST>(v1.x - m1), z * exp_nonpos<FAST>(v1.y - m1),
+                         z * exp_nonpos<FAST>(v1.z - m1), z * exp_nonpos<FAST>(v1.w - m1)};
+    const float e2[4] = {z * exp_nonpos<FAST>(v2.x - m2), z * exp_nonpos<FAST>(v2.y - m2),
+                         z * exp_nonpos<FAST>(v2.z - m2), z * exp_nonpos<FAST>(v2.w - m2)};
+    const float r[4] = {z * g.x * exp_capped<FAST>(ms - yv.x), z * g.y * exp_capped<FAST>(ms - yv.y),
+                        z * g.z * exp_capped<FAST>(ms - yv.z), z * g.w * exp_capped<FAST>(ms - yv.w)};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float hi, lo;
+      split_tf32(r[t], hi, lo);
+      T[0][c4 + t][row] = hi;
+      T[1][c4 + t][row] = lo;
+      T[2][c4 + t][row] = e1[t];
+      T[3][c4 + t][row] = e2[t];
+    }
+  }
+  __syncthreads();
+  float* blk = scratch + ((int64_t)f * nblk + blockIdx.x) * kBlkFloats;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int u = warp; u < 4 * KK; u += 8) {  // 256 rows of 32 samples: r_hi 64, r_lo 64, e1 64, e2 64
+    const int part = u >> 6, unit = u & 63;
+    // scratch row index inside its section: r rows are stacked (hi 0..63, lo 64..127)
+    const int sec = part < 2 ? 0 : (part == 2 ? kBlkE1 : kBlkE2);
+    const int urow = part == 1 ? 64 + unit : unit;
+    blk[sec + blk_off(urow, lane)] = T[part][unit][lane];
   }
 }
 
@@ -294,16 +375,11 @@ constexpr int kDxNW = 4;  // weight ring depth (32 KB slots)
 constexpr int kDxThreads = (kDxWorkers + 3) * 32;  // 608: warps 16 / 17 issue the MMAs of M tile 0 / 1,
                                                    // warp 18 runs the weight copies
 
-// scratch block of 32 samples (floats): r stacked [hi o 0..63 | lo o 0..63][32 b] | e1 [i][32 b] |
-// e2 [j][32 b]; every [unit][32] row is 128 bytes with its 16-byte chunks xor-swizzled by unit & 7
-constexpr int kBlkFloats = 128 * 32 + 64 * 32 + 64 * 32;  // 8192 floats = 32 KB
-constexpr int kBlkE1 = 128 * 32, kBlkE2 = 128 * 32 + 64 * 32;
-__device__ __forceinline__ int blk_off(int unit, int bcol) {
-  return unit * 32 + ((((bcol >> 2) ^ unit) & 7) << 2) + (bcol & 3);
-}
+// scratch block of 32 samples: see tucker_prep_kernel
 
 struct __align__(1024) TkDxSmem {
   float w[kDxNW][2][128 * 32];  // [slot][o half][hi j 0..63 | lo j 0..63][32 o]   128 KB
+  float stage[KK * ROWS];       // e1 as [i][row]                                         64 KB
   float part[2][ROWS];
   uint64_t wfull[kDxNW], wempty[kDxNW], tfull[2][2], tempty[2][2];  // t*: [M tile][buffer]
   uint32_t tmem_base;
@@ -317,6 +393,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.y;
   const int64_t b0 = (int64_t)blockIdx.x * ROWS;
+  if (tid == 0) TKMARK(8);
 
   if (tid == 0) {
     for (int i = 0; i < kDxNW; ++i) {
@@ -335,6 +412,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  if (tid == 0) TKMARK(9);
 
   if (warp < kDxWorkers) {
     const int q = warp & 3, t = (warp >> 2) & 1, ch = warp >> 3;
@@ -342,96 +420,46 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
     const int64_t b = b0 + p;
     const bool valid = b < a.B;
     const int64_t bsafe = valid ? b : 0;
-    const float* x1 = in_row(a, f, 0) + bsafe * KK;
-    const float* x2 = in_row(a, f, 1) + bsafe * KK;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m1 = -INFINITY, m2 = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      m1 = fmaxf(m1, max4(ldg_nc(x1 + 4 * c)));
-      m2 = fmaxf(m2, max4(ldg_nc(x2 + 4 * c)));
-    }
-    m1 = clamp_max(m1);
-    m2 = clamp_max(m2);
-    const float ms = fmaxf(m1 + m2, -FLT_MAX);
-    float* blk = scratch ? scratch + ((int64_t)f * nblk + (b0 + p) / 32) * kBlkFloats : nullptr;
-
-    // e2 (this thread's 32 columns)
+    // r (split), e1 and e2 of this CTA's samples were written by tucker_prep_kernel, transposed
+    // ([unit][32 samples] rows), so lanes = consecutive samples read them coalesced.  (A prologue
+    // that derived them here from x1, x2, y, g took 30 us of a 100 us CTA, serial on every SM.)
+    const float* blk = scratch + ((int64_t)f * nblk + (b0 + p) / 32) * kBlkFloats;
+    float* stg = s.stage;  // e1 as [i][row]
     float e2[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = ldg_nc(x2 + 32 * ch + 4 * c);
-      e2[4 * c] = valid ? exp_nonpos<FAST>(v.x - m2) : 0.f;
-      e2[4 * c + 1] = valid ? exp_nonpos<FAST>(v.y - m2) : 0.f;
-      e2[4 * c + 2] = valid ? exp_nonpos<FAST>(v.z - m2) : 0.f;
-      e2[4 * c + 3] = valid ? exp_nonpos<FAST>(v.w - m2) : 0.f;
-    }
-    if (blk) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) blk[kBlkE2 + blk_off(32 * ch + c, lane)] = e2[c];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = ldg_nc(x1 + 32 * ch + 4 * c);
-        const int u = 32 * ch + 4 * c;
-        blk[kBlkE1 + blk_off(u, lane)] = valid ? exp_nonpos<FAST>(v.x - m1) : 0.f;
-        blk[kBlkE1 + blk_off(u + 1, lane)] = valid ? exp_nonpos<FAST>(v.y - m1) : 0.f;
-        blk[kBlkE1 + blk_off(u + 2, lane)] = valid ? exp_nonpos<FAST>(v.z - m1) : 0.f;
-        blk[kBlkE1 + blk_off(u + 3, lane)] = valid ? exp_nonpos<FAST>(v.w - m1) : 0.f;
-      }
-    }
-    // r = g * exp(m1 + m2 - y) for this thread's 32 outputs -> TMEM columns o (hi) and 64 + o (lo)
+    for (int c = 0; c < 32; ++c) e2[c] = __ldg(blk + kBlkE2 + blk_off(32 * ch + c, lane));
     {
-      const float* yrow = a.y + ((int64_t)f * a.B + bsafe) * KK + 32 * ch;
-      int cbeg = 0, cend = 0;
-      if (valid) {
-        cbeg = a.gs.cons_ptr[f];
-        cend = a.gs.cons_ptr[f + 1];
-      }
       const uint32_t rbase = lane_base + 256 + t * 128 + ch * 32;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float hi[16], lo[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col = hh * 16 + 4 * c;
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int k = cbeg; k < cend; ++k) {
-            const float4 z = *reinterpret_cast<const float4*>(
-                a.gs.garena + a.gs.B * a.gs.cons_rows[k] + b * KK + 32 * ch + col);
-            g.x += z.x; g.y += z.y; g.z += z.z; g.w += z.w;
-          }
-          const float4 yv = ldg_nc(yrow + col);
-          split_tf32(g.x * exp_capped<FAST>(ms - yv.x), hi[4 * c], lo[4 * c]);
-          split_tf32(g.y * exp_capped<FAST>(ms - yv.y), hi[4 * c + 1], lo[4 * c + 1]);
-          split_tf32(g.z * exp_capped<FAST>(ms - yv.z), hi[4 * c + 2], lo[4 * c + 2]);
-          split_tf32(g.w * exp_capped<FAST>(ms - yv.w), hi[4 * c + 3], lo[4 * c + 3]);
+        for (int c = 0; c < 16; ++c) {
+          const int o = 32 * ch + hh * 16 + c;
+          hi[c] = __ldg(blk + blk_off(o, lane));
+          lo[c] = __ldg(blk + blk_off(64 + o, lane));
         }
         tmem_st16(rbase + hh * 16, hi);
         tmem_st16(rbase + 64 + hh * 16, lo);
-        if (blk) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int o = 32 * ch + hh * 16 + c;
-            blk[blk_off(o, lane)] = hi[c];
-            blk[blk_off(64 + o, lane)] = lo[c];
-          }
-        }
       }
-      tmem_st_wait();
-      tc_fence_before_sync();
     }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[(32 * ch + c) * ROWS + p] = __ldg(blk + kBlkE1 + blk_off(32 * ch + c, lane));
+    tmem_st_wait();
+    tc_fence_before_sync();
 
+    if (tid == 0) TKMARK(10);
     // every worker's r is in TMEM before the first MMA
     asm volatile("bar.sync 9, %0;" ::"n"(kDxThreads) : "memory");
+    if (tid == 0) TKMARK(11);
 
     float acc2[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc2[j] = 0.f;
     float* gin1 = a.gin + (((int64_t)f * 2 + 0) * a.B + bsafe) * KK;
-    float x1n = __ldg(x1);
     for (int i = 0; i < KK; ++i) {
-      const float e1i = valid ? exp_nonpos<FAST>(x1n - m1) : 0.f;
-      if (i + 1 < KK) x1n = __ldg(x1 + i + 1);
+      const float e1i = stg[i * ROWS + p];
       const int buf = i & 1;
       if (tid == 0) DXDBG(i, 5);
       if (tid == 8 * 32) DXDBG(i, 9);
@@ -462,6 +490,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
       if (tid == 0) DXDBG(i, 8);
       if (tid == 8 * 32) DXDBG(i, 12);
     }
+    if (tid == 0) TKMARK(12);
     if (valid) {
       float* gin2 = a.gin + (((int64_t)f * 2 + 1) * a.B + b) * KK + 32 * ch;
 #pragma unroll
@@ -518,6 +547,7 @@ tucker_tc_bwd_dx_kernel(DenseArgs a, float* scratch, int nblk, const float* __re
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) TKMARK(13);
   if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -800,15 +830,21 @@ int tucker_tc_bwd(const ckb_step_desc_t& d, Ctx& c) {
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
   a.gin = c.garena + c.B * d.gin_off;
   float* dW = c.grads[d.slot[0]];
-  float* scratch = nullptr;
   const int nblk_alloc = ceil_div(c.B, ROWS) * (ROWS / 32);
-  const size_t need = dW ? tucker_tc_bwd_ws(d, c.B) : tucker_tc_img_bytes(d);
+  const size_t need = tucker_tc_bwd_ws(d, c.B);
   if (c.ws_bytes < need) {
     set_error("tucker_bwd: workspace too small (%zu < %zu)", c.ws_bytes, need);
     return CKB_ERR_WORKSPACE;
   }
   float* wimg = (float*)c.ws;
-  if (dW) scratch = (float*)(c.ws + tucker_tc_img_bytes(d));
+  float* scratch = (float*)(c.ws + tucker_tc_img_bytes(d));
+  {
+    dim3 gridp(nblk_alloc, d.num_folds);
+    if ((tc_flags() & 3) == 3) tucker_prep_kernel<true><<<gridp, 256, 0, c.stream>>>(a, scratch, nblk_alloc);
+    else tucker_prep_kernel<false><<<gridp, 256, 0, c.stream>>>(a, scratch, nblk_alloc);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+  }
   tucker_split_wt_kernel<<<dim3(KK, d.num_folds), 256, 0, c.stream>>>(a.W, wimg);
   CKB_LAUNCH_CHECK();
   c.launches++;

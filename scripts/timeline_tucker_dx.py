@@ -29,3 +29,7 @@ t0 = a[512 + 5]
 for i in range(8, 20):
     base = 512 + (i - 8) * 16
     print(f"i {i:2d} " + " ".join(f"{n}=+{a[base+k]-t0}" for k, n in enumerate(names) if a[base + k] > 0))
+
+print("fwd kernel (last launch, CTA 0): start 0, setup +%d, prologue done +%d, last chunk ready +%d, all warps done +%d, end +%d" % tuple(a[k] - a[0] for k in (1, 2, 3, 4, 5)))
+print("dX kernel (last launch, CTA 0): start 0, setup +%d, prologue done +%d, r in TMEM +%d, loop done +%d, end +%d" % tuple(a[k] - a[8] for k in (9, 10, 11, 12, 13)))
+
