@@ -259,12 +259,15 @@ class CircuitPlan:
 
     # ---------------------------------------------------------------- utilities
     def with_units(self, k: int) -> "CircuitPlan":
-        """Return the same structure with every K-sized unit axis resized to ``k``.
+        """Return the same structure with every unit axis of size ``meta['units']`` resized to
+        ``k`` (layers with a single output unit, e.g. the root sum, keep it).
 
         The fold/gather structure a region graph compiles to does not depend on the number of
         units, so the committed structure fixtures (built from the reference at a small K) are
-        re-sized to the benchmark K here.  Only unit counts equal to ``meta['units']`` are
-        changed (the root sum keeps its single output unit).
+        re-sized to the benchmark K here.  Parameter shapes are re-derived from the layer kind
+        (`cirkit/backend/torch/layers/*`: Categorical/Embedding (F,K,V), Gaussian (F,K), sum
+        (F,Ko,H*Ki), CP-T (F,Ko,Ki), Tucker (F,Ko,Ki^H), mixing (F,K,H)), not matched by value, so
+        a fixture with K = 3 and an arity-3 layer resizes correctly.
         """
         k0 = self.meta.get("units")
         if k0 is None:
@@ -273,24 +276,39 @@ class CircuitPlan:
             return self
 
         def r(n: int) -> int:
-            if n == k0:
-                return k
-            if n == k0 * k0:
-                return k * k
-            return n
+            return k if n == k0 else n
 
-        leaves = [LeafSpec(tuple(r(d) if i else d for i, d in enumerate(l.shape)), l.init,
-                           l.requires_grad, l.name) for l in self.leaves]
-        steps = []
-        for s in self.steps:
-            params = {
-                n: ParamSpec(p.leaf, [(o, dict(a)) for o, a in p.ops],
-                             tuple(r(d) if i else d for i, d in enumerate(p.shape)), p.fold_idx)
-                for n, p in s.params.items()
-            }
-            steps.append(dataclasses.replace(
-                s, num_input_units=r(s.num_input_units) if not s.is_input else s.num_input_units,
-                num_output_units=r(s.num_output_units), params=params))
+        steps, leaf_shapes = [], {}
+        for sid, s in enumerate(self.steps):
+            ki = s.num_input_units if s.is_input else r(s.num_input_units)
+            ko = r(s.num_output_units)
+            params = {}
+            for n, p in s.params.items():
+                F = p.shape[0]
+                if s.kind in ("categorical", "embedding"):
+                    shape = (F, ko, p.shape[2])
+                elif s.kind in ("gaussian", "constant"):
+                    shape = (F, ko) + tuple(p.shape[2:])
+                elif s.kind == "sum":
+                    shape = (F, ko, s.arity * ki)
+                elif s.kind == "cpt":
+                    shape = (F, ko, ki)
+                elif s.kind == "tucker":
+                    shape = (F, ko, ki ** s.arity)
+                elif s.kind == "mixing":
+                    shape = (F, ko, s.arity)
+                else:
+                    shape = tuple(p.shape)
+                if len(shape) != len(p.shape):
+                    raise ValueError(f"step {sid} parameter {n!r}: cannot resize shape {p.shape}")
+                params[n] = ParamSpec(p.leaf, [(o, dict(a)) for o, a in p.ops], shape, p.fold_idx)
+                if p.leaf >= 0:
+                    new_leaf = (self.leaves[p.leaf].shape[0],) + shape[1:]
+                    if leaf_shapes.setdefault(p.leaf, new_leaf) != new_leaf:
+                        raise ValueError(f"leaf {p.leaf} is shared by layers of different shapes")
+            steps.append(dataclasses.replace(s, num_input_units=ki, num_output_units=ko, params=params))
+        leaves = [LeafSpec(tuple(leaf_shapes.get(i, l.shape)), l.init, l.requires_grad, l.name)
+                  for i, l in enumerate(self.leaves)]
         meta = dict(self.meta)
         meta["units"] = k
         plan = dataclasses.replace(self, steps=steps, leaves=leaves, meta=meta)

@@ -94,3 +94,32 @@ def test_two_ranks_match_single_process(tmp_path, name, batch):
             if p.requires_grad:
                 torch.testing.assert_close(gr, p.grad, rtol=1e-10, atol=1e-12)
         assert o["nbytes"] == sum(p.numel() * 8 for p in oc.leaves if p.requires_grad)
+
+
+def test_flat_gradient_detection():
+    """The CUDA runtime hands out parameter gradients as views of one flat buffer; the sharding
+    helper sums that buffer with ONE collective when (and only when) every gradient lives in it."""
+    from cirkit_b200.distributed import _flat_gradient, all_reduce_gradients
+
+    shapes = [(3, 4, 5), (7,), (2, 6)]
+    sizes = [-(-torch.Size(s).numel() // 4) * 4 for s in shapes]
+    flat = torch.arange(float(sum(sizes)))
+    params, off = [], 0
+    for s, sz in zip(shapes, sizes):
+        p = torch.nn.Parameter(torch.zeros(s, dtype=flat.dtype))
+        p.grad = flat[off : off + torch.Size(s).numel()].view(s)
+        off += sz
+        params.append(p)
+    assert _flat_gradient(params, flat) is flat
+    assert _flat_gradient(params, None) is None
+    assert _flat_gradient(params, torch.zeros(4)) is None  # some other buffer
+    before = [p.grad.clone() for p in params]
+    assert all_reduce_gradients(params, flat=flat) == flat.numel() * flat.element_size()  # world 1: no-op
+    for p, b in zip(params, before):
+        assert torch.equal(p.grad, b)
+    # a gradient that was re-allocated (e.g. accumulated out of place) disables the short cut
+    params[1].grad = params[1].grad.clone()
+    assert _flat_gradient(params, flat) is None
+    # ... and so does a buffer that holds more than these parameters' gradients
+    params[1].grad = flat[sizes[0] : sizes[0] + 7]
+    assert _flat_gradient(params[:2], flat) is None

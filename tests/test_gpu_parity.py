@@ -340,3 +340,40 @@ def test_k32_kernels_vs_oracle(name, batch, dev):
         tol = grad_tolerance(gr, gout_l1=float(w.abs().sum()), ll_max=ll_max,
                              w_max=float(torch.softmax(q.detach(), dim=-1).max()))
         assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("name,batch", [("qg8_cp_k4_densemix", 70), ("pd6_cp_k3_unopt", 45), ("rbt12_gaussian_k5", 129)])
+def test_k128_circuits_vs_oracle(name, batch, dev):
+    """K = 128, the unit count of BASELINE.json configs[3] (PoonDomingos, 8 GPUs): the reference's
+    QuadGraph (dense sum + mixing), PoonDomingos (Hadamard, mixing of arity up to 10, unoptimised)
+    and Gaussian-input structures resized to 128 units, against the float64 oracle.  These shapes
+    run on the FP32 SIMT kernels."""
+    import dataclasses
+
+    from cirkit_b200 import B200Circuit
+    from cirkit_b200.plan import seeded_leaves
+    from oracle import OracleCircuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden(name)
+    k0 = g.plan.steps[0].num_output_units
+    plan = dataclasses.replace(g.plan, meta={"units": k0}).with_units(128)
+    cc = B200Circuit(plan, seed=5).to(dev)
+    oc = OracleCircuit(plan, dtype=torch.float64)
+    with torch.no_grad():
+        for q, v in zip(oc.leaves, seeded_leaves(plan, 5)):
+            q.copy_(v)
+    x = make_inputs(plan, batch, seed=batch)
+    y = cc(x.to(dev))
+    yo = oc(x)
+    _check_forward(y, yo.detach())
+    w = torch.randn(batch, 1, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    (y * w.to(dev, torch.float32)).sum().backward()
+    (yo * w).sum().backward()
+    ll_max = float(yo.detach().abs().max())
+    for i, (p, q) in enumerate(zip(cc.leaves, oc.leaves)):
+        gr = torch.zeros_like(q) if q.grad is None else q.grad
+        got = torch.zeros_like(p) if p.grad is None else p.grad
+        err = (got.double().cpu() - gr).abs().max().item()
+        tol = grad_tolerance(gr, gout_l1=float(w.abs().sum()), ll_max=ll_max)
+        assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
