@@ -14,6 +14,46 @@ namespace ckb {
 
 constexpr int kMaxH = 64;  // inputs per fold the small kernels keep row pointers for
 
+// Pre-activations of SW consecutive samples, lane owning the reduction indices lane + 32 j
+// (-inf beyond Kred or beyond the batch).  All loads of one input row pointer are issued before
+// any of them is consumed.
+template <int SW, int NJ>
+__device__ __forceinline__ void gather_u(const DenseArgs& a, const float* const* rows, int64_t b0,
+                                         int lane, float (&uu)[SW][NJ]) {
+  if (!a.concat) {
+#pragma unroll
+    for (int s = 0; s < SW; ++s)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) uu[s][j] = (b0 + s < a.B && lane + 32 * j < a.Kred) ? 0.f : -INFINITY;
+    for (int h = 0; h < a.H; ++h) {
+      const float* r = rows[h] + b0 * a.Ki + lane;
+      float t[SW][NJ];
+#pragma unroll
+      for (int s = 0; s < SW; ++s)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          t[s][j] = (b0 + s < a.B && lane + 32 * j < a.Kred) ? __ldg(r + (int64_t)s * a.Ki + 32 * j) : 0.f;
+#pragma unroll
+      for (int s = 0; s < SW; ++s)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) uu[s][j] += t[s][j];
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < SW; ++s)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        float v = -INFINITY;
+        if (b0 + s < a.B && k < a.Kred) {
+          const int h = k / a.Ki;
+          v = __ldg(rows[h] + (b0 + s) * a.Ki + (k - h * a.Ki));
+        }
+        uu[s][j] = v;
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward, Kred <= 128 and Ko <= 128 ("small" = the whole weight slice fits in shared memory)
 // ------------------------------------------------------------------------------------------
@@ -43,15 +83,26 @@ __global__ void __launch_bounds__(256) dense_fwd_small(DenseArgs a) {
   for (int64_t b0 = ((int64_t)blockIdx.x * 8 + warp) * SW; b0 < a.B;
        b0 += (int64_t)gridDim.x * 8 * SW) {
     float m_reg[SW];
+    {
+      // the loads of all SW samples go out together (lane owns reduction indices lane + 32 j):
+      // one memory round trip per input instead of one per sample
+      float uu[SW][NO];
+      gather_u<SW, NO>(a, rows, b0, lane, uu);
 #pragma unroll
-    for (int s = 0; s < SW; ++s) {
-      const int64_t b = b0 + s;
-      float* es = e_w + s * KredP;
-      float m = 0.f;
-      if (b < a.B) m = load_u(a, rows, b, lane, es);
-      __syncwarp();
-      for (int k = lane; k < KredP; k += 32) es[k] = (b < a.B && k < a.Kred) ? expf(es[k] - m) : 0.f;
-      m_reg[s] = m;
+      for (int s = 0; s < SW; ++s) {
+        const bool valid = b0 + s < a.B;
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) m = fmaxf(m, uu[s][j]);
+        m = valid ? clamp_max(warp_max(m)) : 0.f;
+        float* es = e_w + s * KredP;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          const int k = lane + 32 * j;
+          if (k < KredP) es[k] = (valid && k < a.Kred) ? expf(uu[s][j] - m) : 0.f;
+        }
+        m_reg[s] = m;
+      }
     }
     __syncwarp();
     float acc[SW][NO];
@@ -321,28 +372,47 @@ __global__ void __launch_bounds__(256) dense_bwd_small(DenseArgs a) {
 
   float* r_w = r_all + warp * SW * LR;
   float* e_w = e_all + warp * SW * LE;
+  // the usual case (a tree): one consumer row, resolved once instead of per element
+  const float* grow = nullptr;
+  if (a.gs.cons_ptr == nullptr) grow = a.gs.garena + (int64_t)f * a.gs.B * a.Ko;
+  else if (a.gs.cons_ptr[f + 1] - a.gs.cons_ptr[f] == 1) grow = a.gs.garena + a.gs.B * a.gs.cons_rows[a.gs.cons_ptr[f]];
   const int64_t b_begin = (int64_t)blockIdx.x * a.chunk;
   const int64_t b_end = min(a.B, b_begin + a.chunk);
   for (int64_t t0 = b_begin; t0 < b_end; t0 += 8 * SW) {
     const int64_t b0 = t0 + warp * SW;
-    // ---- phase A: e and r of this warp's samples
+    // ---- phase A: e and r of this warp's samples, four samples at a time with all their loads
+    // (inputs, y, g) in flight together
+    static_assert(SW % 4 == 0, "sub-batches of 4 samples");
 #pragma unroll 1
-    for (int s = 0; s < SW; ++s) {
-      const int64_t b = b0 + s;
-      float* es = e_w + s * LE;
-      float* rs = r_w + s * LR;
-      const bool valid = b < b_end;
-      float m = 0.f;
-      if (valid) m = load_u(a, rows, b, lane, es);
-      __syncwarp();
-      for (int k = lane; k < LE; k += 32) es[k] = (valid && k < a.Kred) ? expf(es[k] - m) : 0.f;
-      for (int o = lane; o < LR; o += 32) {
-        float r = 0.f;
-        if (valid && o < a.Ko) {
-          const float g = pull_grad(a.gs, f, b, a.Ko, o);
-          r = (g == 0.f) ? 0.f : g * expf(m - a.y[((int64_t)f * a.B + b) * a.Ko + o]);
+    for (int s0 = 0; s0 < SW; s0 += 4) {
+      float uu[4][NI], yv[4][NI], gv[4][NI];
+      gather_u<4, NI>(a, rows, b0 + s0, lane, uu);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int64_t b = b0 + s0 + s;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int o = lane + 32 * j;
+          const bool ok = b < b_end && o < a.Ko;
+          yv[s][j] = ok ? __ldg(a.y + ((int64_t)f * a.B + b) * a.Ko + o) : 0.f;
+          gv[s][j] = !ok ? 0.f : (grow ? __ldg(grow + b * a.Ko + o) : pull_grad(a.gs, f, b, a.Ko, o));
         }
-        rs[o] = r;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const bool valid = b0 + s0 + s < b_end;
+        float* es = e_w + (s0 + s) * LE;
+        float* rs = r_w + (s0 + s) * LR;
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) m = fmaxf(m, uu[s][j]);
+        m = valid ? clamp_max(warp_max(m)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int k = lane + 32 * j;
+          if (k < LE) es[k] = (valid && k < a.Kred) ? expf(uu[s][j] - m) : 0.f;
+          if (k < LR) rs[k] = (valid && k < a.Ko && gv[s][j] != 0.f) ? gv[s][j] * expf(m - yv[s][j]) : 0.f;
+        }
       }
     }
     __syncwarp();
