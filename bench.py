@@ -31,7 +31,10 @@ WORKLOADS = {
     "qt28_cp_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=64",
     "qt28_cp_k32": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=32",
     "qt28_tucker_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, Tucker, K=64",
+    "pd32_cp_k128": "PoonDomingos 32x32x3, Categorical-256 inputs, CP (fold+optimize), K=128",
 }
+# workloads built by resizing a structure fixture: name -> (fixture, its units, units to run at)
+RESIZED = {"pd32_cp_k128": ("pd32_cp_k4", 4, 128)}
 
 
 def metric_name(workload):
@@ -40,12 +43,20 @@ def metric_name(workload):
     if workload == "qt28_cp_k64":
         return METRIC
     return "samples/sec (fwd+bwd log-lik) " + {"qt28_cp_k32": "QuadTree 28x28 K=32 (configs[1])",
-                                               "qt28_tucker_k64": "QuadTree 28x28 Tucker K=64 (configs[2])"}[workload]
+                                               "qt28_tucker_k64": "QuadTree 28x28 Tucker K=64 (configs[2])",
+                                               "pd32_cp_k128": "PoonDomingos 32x32x3 K=128 (configs[3])"}[workload]
 
 
 def load_plan(name):
+    import dataclasses
+
     from helpers import Golden
 
+    if name in RESIZED:
+        fixture, k0, k = RESIZED[name]
+        g = Golden(fixture)
+        g.plan = dataclasses.replace(g.plan, meta={"units": k0}).with_units(k)
+        return g
     return Golden(name)
 
 

@@ -66,48 +66,74 @@ def _lower_param(p, leaf_ids: dict[int, int], leaves: list, leaf_specs: list[Lea
     mods = [e.module for e in entries[:-1]]
     if not mods:
         return None
-    head = mods[0]
-    fold_idx = None
-    if isinstance(head, N.TorchPointerParameter):
-        fold_idx = None if head._fold_idx is None else head._fold_idx.cpu().numpy().astype(np.int64)
-        head = head.deref()
-    if not isinstance(head, N.TorchTensorParameter) or head._ptensor is None:
-        return None
-    ops: list[tuple[str, dict[str, Any]]] = []
-    for i, e in enumerate(entries[1:-1], start=1):
-        m = e.module
-        if type(m) not in op_names:
-            return None
-        # must consume exactly the previous node, un-permuted
-        if e.in_module_ids != [[i - 1]] or len(e.in_fold_idx) != 1:
-            return None
-        fi = e.in_fold_idx[0]
+
+    def identity(fi, n_folds: int) -> bool:
         if isinstance(fi, torch.Tensor):
-            if fi.tolist() != list(range(mods[i - 1].num_folds)):
+            return fi.tolist() == list(range(n_folds))
+        return fi == ()
+
+    def leaf_index(t) -> int:
+        key = id(t)
+        if key not in leaf_ids:
+            leaf_ids[key] = len(leaves)
+            leaves.append(t)
+            leaf_specs.append(LeafSpec(tuple(t.shape), "normal", bool(t.requires_grad), names.get(key, "")))
+        return leaf_ids[key]
+
+    def chain(i: int):
+        """(leaf tensor, fold_idx, ops) of node i, or None when the sub-graph is not a chain of
+        unary ops over one leaf with at most `matmul` nodes joining two such chains."""
+        m, e = mods[i], entries[i]
+        if isinstance(m, (N.TorchTensorParameter, N.TorchPointerParameter)):
+            fold_idx = None
+            if isinstance(m, N.TorchPointerParameter):
+                fold_idx = None if m._fold_idx is None else m._fold_idx.cpu().numpy().astype(np.int64)
+                m = m.deref()
+            if not isinstance(m, N.TorchTensorParameter) or m._ptensor is None:
                 return None
-        elif fi != ():
-            return None
-        attrs: dict[str, Any] = {}
-        if hasattr(m, "dim"):
-            attrs["dim"] = int(m.dim)
-        if isinstance(m, (N.TorchScaledSigmoidParameter, N.TorchClampParameter)):
-            attrs["vmin"] = None if m.vmin is None else float(m.vmin)
-            attrs["vmax"] = None if m.vmax is None else float(m.vmax)
-        ops.append((op_names[type(m)], attrs))
+            return m._ptensor, fold_idx, []
+        if type(m) in op_names:
+            # must consume exactly one earlier node, un-permuted
+            if len(e.in_module_ids) != 1 or len(e.in_module_ids[0]) != 1 or len(e.in_fold_idx) != 1:
+                return None
+            j = e.in_module_ids[0][0]
+            if not identity(e.in_fold_idx[0], mods[j].num_folds):
+                return None
+            sub = chain(j)
+            if sub is None:
+                return None
+            attrs: dict[str, Any] = {}
+            if hasattr(m, "dim"):
+                attrs["dim"] = int(m.dim)
+            if isinstance(m, (N.TorchScaledSigmoidParameter, N.TorchClampParameter)):
+                attrs["vmin"] = None if m.vmin is None else float(m.vmin)
+                attrs["vmax"] = None if m.vmax is None else float(m.vmax)
+            return sub[0], sub[1], sub[2] + [(op_names[type(m)], attrs)]
+        if isinstance(m, N.TorchMatMulParameter):
+            # SumCollapse (cirkit/backend/torch/optimization/layers.py:30-47): W = W1 @ W2
+            if len(e.in_module_ids) != 2 or any(len(ids) != 1 for ids in e.in_module_ids):
+                return None
+            (j1,), (j2,) = e.in_module_ids
+            if not identity(e.in_fold_idx[0], mods[j1].num_folds) or not identity(e.in_fold_idx[1], mods[j2].num_folds):
+                return None
+            lhs, rhs = chain(j1), chain(j2)
+            if lhs is None or rhs is None:
+                return None
+            rhs_spec = {"leaf": leaf_index(rhs[0]), "ops": [[o, a] for o, a in rhs[2]],
+                        "fold_idx": None if rhs[1] is None else [int(v) for v in rhs[1]]}
+            return lhs[0], lhs[1], lhs[2] + [("matmul", {"rhs": rhs_spec})]
+        return None
+
     last = entries[-1]
     if last.in_module_ids != [[len(mods) - 1]]:
         return None
     if last.in_fold_idx[0].tolist() != list(range(mods[-1].num_folds)):
         return None
-    key = id(head._ptensor)
-    if key not in leaf_ids:
-        leaf_ids[key] = len(leaves)
-        leaves.append(head._ptensor)
-        leaf_specs.append(
-            LeafSpec(tuple(head._ptensor.shape), "normal", bool(head._ptensor.requires_grad),
-                     names.get(key, ""))
-        )
-    return ParamSpec(leaf_ids[key], ops, (p.num_folds, *p.shape), fold_idx)
+    low = chain(len(mods) - 1)
+    if low is None:
+        return None
+    tensor, fold_idx, ops = low
+    return ParamSpec(leaf_index(tensor), ops, (p.num_folds, *p.shape), fold_idx)
 
 
 # --------------------------------------------------------------------------- layers

@@ -47,6 +47,9 @@ PARAM_OPS = (
     "softplus",  # nodes.py:730-738
     "clamp",  # nodes.py:702-727 (attrs: vmin, vmax)
     "mixing",  # TorchMixingWeightParameter nodes.py:847-862
+    # TorchMatMulParameter nodes.py:786-805 (SumCollapse): attrs {"rhs": {"leaf", "ops", "fold_idx"}},
+    # the right operand being another leaf -> op chain of the same plan
+    "matmul",
 )
 
 
@@ -156,9 +159,11 @@ class CircuitPlan:
             for name, p in s.params.items():
                 if p.leaf >= len(self.leaves):
                     raise ValueError(f"step {sid}: parameter {name} points past the leaf table")
-                for op, _ in p.ops:
+                for op, attrs in p.ops:
                     if op not in PARAM_OPS:
                         raise ValueError(f"step {sid}: parameter op {op!r} is not supported")
+                    if op == "matmul" and not 0 <= attrs["rhs"]["leaf"] < len(self.leaves):
+                        raise ValueError(f"step {sid}: matmul operand points past the leaf table")
 
     # ---------------------------------------------------------------- (de)serialisation
     def to_bytes(self) -> bytes:
@@ -279,6 +284,25 @@ class CircuitPlan:
             return k if n == k0 else n
 
         steps, leaf_shapes = [], {}
+
+        def resize_leaf(leaf: int, ops, eff_shape) -> None:
+            """New shape of a leaf from the op chain that leads from it to a layer parameter."""
+            old = self.leaves[leaf].shape
+            names = [o for o, _ in ops]
+            if names and names[-1] == "matmul":
+                # W1 @ W2 (SumCollapse): W1 is (F, Ko, K); W2 has its own chain
+                new = (old[0], r(old[1]), r(old[2]))
+                rhs = ops[-1][1]["rhs"]
+                resize_leaf(rhs["leaf"], [(o, a) for o, a in rhs["ops"]], None)
+            elif "mixing" in names:
+                new = (old[0], r(old[1])) + tuple(old[2:])  # mixing weights are (F, K, H)
+            elif eff_shape is not None:
+                new = (old[0],) + tuple(eff_shape[1:])
+            else:
+                new = (old[0],) + tuple(r(d) for d in old[1:])
+            if leaf_shapes.setdefault(leaf, new) != new:
+                raise ValueError(f"leaf {leaf} is shared by layers of different shapes")
+
         for sid, s in enumerate(self.steps):
             ki = s.num_input_units if s.is_input else r(s.num_input_units)
             ko = r(s.num_output_units)
@@ -303,9 +327,7 @@ class CircuitPlan:
                     raise ValueError(f"step {sid} parameter {n!r}: cannot resize shape {p.shape}")
                 params[n] = ParamSpec(p.leaf, [(o, dict(a)) for o, a in p.ops], shape, p.fold_idx)
                 if p.leaf >= 0:
-                    new_leaf = (self.leaves[p.leaf].shape[0],) + shape[1:]
-                    if leaf_shapes.setdefault(p.leaf, new_leaf) != new_leaf:
-                        raise ValueError(f"leaf {p.leaf} is shared by layers of different shapes")
+                    resize_leaf(p.leaf, p.ops, shape)
             steps.append(dataclasses.replace(s, num_input_units=ki, num_output_units=ko, params=params))
         leaves = [LeafSpec(tuple(leaf_shapes.get(i, l.shape)), l.init, l.requires_grad, l.name)
                   for i, l in enumerate(self.leaves)]

@@ -71,6 +71,20 @@ def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
     raise ValueError(f"unknown parameter op {op!r}")
 
 
+def eval_param_chain(leaves: Sequence[Tensor], spec: dict) -> Tensor:
+    """Host (PyTorch, differentiable) evaluation of a `leaf [-> fold slice] -> ops` chain given as
+    the plain dict a `matmul` op carries for its right operand."""
+    t = leaves[spec["leaf"]]
+    if spec.get("fold_idx") is not None:
+        t = t.index_select(0, torch.as_tensor(spec["fold_idx"], dtype=torch.int64, device=t.device))
+    for op, attrs in spec["ops"]:
+        if op == "matmul":
+            t = torch.matmul(t, eval_param_chain(leaves, attrs["rhs"]))
+        else:
+            t = apply_param_op(t, op, attrs)
+    return t
+
+
 @dataclass
 class _Binding:
     """One layer parameter: source tensor -> host prefix ops -> optional fused op -> slot."""
@@ -416,7 +430,10 @@ class PlanRuntime:
                     idx = torch.as_tensor(b.spec.fold_idx, dtype=torch.int64, device=t.device)
                     t = t.index_select(0, idx)
             for op, attrs in b.prefix:
-                t = apply_param_op(t, op, attrs)
+                if op == "matmul":  # W1 @ W2, the right operand is another leaf -> op chain
+                    t = torch.matmul(t, eval_param_chain(leaves, attrs["rhs"]))
+                else:
+                    t = apply_param_op(t, op, attrs)
             if t.dtype != torch.float32:
                 t = t.to(torch.float32)
             if tuple(t.shape) != b.src_shape:

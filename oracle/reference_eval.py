@@ -135,7 +135,24 @@ class OracleCircuit(nn.Module):
         if p.fold_idx is not None:
             t = t[torch.as_tensor(p.fold_idx, dtype=torch.int64)]  # nodes.py:277-279
         for op, attrs in p.ops:
-            t = apply_param_op(t, op, attrs)
+            if op == "matmul":
+                # TorchMatMulParameter.forward, parameters/nodes.py:802-805 (SumCollapse rule,
+                # optimization/layers.py:30-47): (F, d1, d2) @ (F, d2, d3)
+                t = torch.matmul(t, self._param_chain(attrs["rhs"]))
+            else:
+                t = apply_param_op(t, op, attrs)
+        return t
+
+    def _param_chain(self, spec: dict) -> Tensor:
+        """The right operand of a matmul node: another leaf -> [fold slice] -> op chain."""
+        t: Tensor = self.leaves[spec["leaf"]]
+        if spec.get("fold_idx") is not None:
+            t = t[torch.as_tensor(spec["fold_idx"], dtype=torch.int64)]
+        for op, attrs in spec["ops"]:
+            if op == "matmul":
+                t = torch.matmul(t, self._param_chain(attrs["rhs"]))
+            else:
+                t = apply_param_op(t, op, attrs)
         return t
 
     # ---------------------------------------------------------------- layers

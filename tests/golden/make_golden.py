@@ -240,7 +240,18 @@ def case_bench():
     write_seeded("qt28_tucker_k64", tc, x[:4], seed=1234, extra={"units": 64, "config": 2})
 
 
+def case_pd32():
+    """BASELINE.json configs[3] structure: PoonDomingos over 3x32x32 Categorical inputs, CP layers
+    (fold + optimize), built at K = 4 (the fold / gather structure does not depend on K; tests and
+    bench.py resize it with CircuitPlan.with_units)."""
+    torch.manual_seed(42)
+    x = torch.randint(0, 256, (4, 3 * 32 * 32))
+    _, tc = compile_ref(image_circuit((3, 32, 32), "poon-domingos", "cp", 4))
+    write_seeded("pd32_cp_k4", tc, x, seed=1234, extra={"units": 4, "config": 3})
+
+
 CASES = {
+    "pd32": case_pd32,
     "ka_categorical": case_ka_categorical,
     "ka_gaussian": case_ka_gaussian,
     "random_small": case_random_small,
