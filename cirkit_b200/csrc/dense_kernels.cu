@@ -20,7 +20,7 @@ constexpr int kMaxH = 64;  // inputs per fold the small kernels keep row pointer
 template <int SW, int NJ>
 __device__ __forceinline__ void gather_u(const DenseArgs& a, const float* const* rows, int64_t b0,
                                          int lane, float (&uu)[SW][NJ]) {
-  if (!a.concat) {
+  {  // summed inputs only (Hadamard-style); concatenating layers take the per-sample path
 #pragma unroll
     for (int s = 0; s < SW; ++s)
 #pragma unroll
@@ -38,19 +38,6 @@ __device__ __forceinline__ void gather_u(const DenseArgs& a, const float* const*
 #pragma unroll
         for (int j = 0; j < NJ; ++j) uu[s][j] += t[s][j];
     }
-  } else {
-#pragma unroll
-    for (int s = 0; s < SW; ++s)
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int k = lane + 32 * j;
-        float v = -INFINITY;
-        if (b0 + s < a.B && k < a.Kred) {
-          const int h = k / a.Ki;
-          v = __ldg(rows[h] + (b0 + s) * a.Ki + (k - h * a.Ki));
-        }
-        uu[s][j] = v;
-      }
   }
 }
 
@@ -83,7 +70,19 @@ __global__ void __launch_bounds__(256) dense_fwd_small(DenseArgs a) {
   for (int64_t b0 = ((int64_t)blockIdx.x * 8 + warp) * SW; b0 < a.B;
        b0 += (int64_t)gridDim.x * 8 * SW) {
     float m_reg[SW];
-    {
+    if (a.concat) {
+      // concatenating sums (rare, small): one sample at a time
+#pragma unroll 1
+      for (int s = 0; s < SW; ++s) {
+        const int64_t b = b0 + s;
+        float* es = e_w + s * KredP;
+        float m = 0.f;
+        if (b < a.B) m = load_u(a, rows, b, lane, es);
+        __syncwarp();
+        for (int k = lane; k < KredP; k += 32) es[k] = (b < a.B && k < a.Kred) ? expf(es[k] - m) : 0.f;
+        m_reg[s] = m;
+      }
+    } else {
       // the loads of all SW samples go out together (lane owns reduction indices lane + 32 j):
       // one memory round trip per input instead of one per sample
       float uu[SW][NO];
@@ -380,38 +379,61 @@ __global__ void __launch_bounds__(256) dense_bwd_small(DenseArgs a) {
   const int64_t b_end = min(a.B, b_begin + a.chunk);
   for (int64_t t0 = b_begin; t0 < b_end; t0 += 8 * SW) {
     const int64_t b0 = t0 + warp * SW;
-    // ---- phase A: e and r of this warp's samples, four samples at a time with all their loads
-    // (inputs, y, g) in flight together
+    // ---- phase A: e and r of this warp's samples
     static_assert(SW % 4 == 0, "sub-batches of 4 samples");
+    if (a.concat) {
+      // concatenating sums (rare, small): one sample at a time
 #pragma unroll 1
-    for (int s0 = 0; s0 < SW; s0 += 4) {
-      float uu[4][NI], yv[4][NI], gv[4][NI];
-      gather_u<4, NI>(a, rows, b0 + s0, lane, uu);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int64_t b = b0 + s0 + s;
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const int o = lane + 32 * j;
-          const bool ok = b < b_end && o < a.Ko;
-          yv[s][j] = ok ? __ldg(a.y + ((int64_t)f * a.B + b) * a.Ko + o) : 0.f;
-          gv[s][j] = !ok ? 0.f : (grow ? __ldg(grow + b * a.Ko + o) : pull_grad(a.gs, f, b, a.Ko, o));
+      for (int s = 0; s < SW; ++s) {
+        const int64_t b = b0 + s;
+        float* es = e_w + s * LE;
+        float* rs = r_w + s * LR;
+        const bool valid = b < b_end;
+        float m = 0.f;
+        if (valid) m = load_u(a, rows, b, lane, es);
+        __syncwarp();
+        for (int k = lane; k < LE; k += 32) es[k] = (valid && k < a.Kred) ? expf(es[k] - m) : 0.f;
+        for (int o = lane; o < LR; o += 32) {
+          float r = 0.f;
+          if (valid && o < a.Ko) {
+            const float g = pull_grad(a.gs, f, b, a.Ko, o);
+            r = (g == 0.f) ? 0.f : g * expf(m - a.y[((int64_t)f * a.B + b) * a.Ko + o]);
+          }
+          rs[o] = r;
         }
       }
+    } else {
+      // four samples at a time with all their loads (inputs, y, g) in flight together
+#pragma unroll 1
+      for (int s0 = 0; s0 < SW; s0 += 4) {
+        float uu[4][NI], yv[4][NI], gv[4][NI];
+        gather_u<4, NI>(a, rows, b0 + s0, lane, uu);
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const bool valid = b0 + s0 + s < b_end;
-        float* es = e_w + (s0 + s) * LE;
-        float* rs = r_w + (s0 + s) * LR;
-        float m = -INFINITY;
+        for (int s = 0; s < 4; ++s) {
+          const int64_t b = b0 + s0 + s;
 #pragma unroll
-        for (int j = 0; j < NI; ++j) m = fmaxf(m, uu[s][j]);
-        m = valid ? clamp_max(warp_max(m)) : 0.f;
+          for (int j = 0; j < NI; ++j) {
+            const int o = lane + 32 * j;
+            const bool ok = b < b_end && o < a.Ko;
+            yv[s][j] = ok ? __ldg(a.y + ((int64_t)f * a.B + b) * a.Ko + o) : 0.f;
+            gv[s][j] = !ok ? 0.f : (grow ? __ldg(grow + b * a.Ko + o) : pull_grad(a.gs, f, b, a.Ko, o));
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const int k = lane + 32 * j;
-          if (k < LE) es[k] = (valid && k < a.Kred) ? expf(uu[s][j] - m) : 0.f;
-          if (k < LR) rs[k] = (valid && k < a.Ko && gv[s][j] != 0.f) ? gv[s][j] * expf(m - yv[s][j]) : 0.f;
+        for (int s = 0; s < 4; ++s) {
+          const bool valid = b0 + s0 + s < b_end;
+          float* es = e_w + (s0 + s) * LE;
+          float* rs = r_w + (s0 + s) * LR;
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) m = fmaxf(m, uu[s][j]);
+          m = valid ? clamp_max(warp_max(m)) : 0.f;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            const int k = lane + 32 * j;
+            if (k < LE) es[k] = (valid && k < a.Kred) ? expf(uu[s][j] - m) : 0.f;
+            if (k < LR) rs[k] = (valid && k < a.Ko && gv[s][j] != 0.f) ? gv[s][j] * expf(m - yv[s][j]) : 0.f;
+          }
         }
       }
     }

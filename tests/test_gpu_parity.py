@@ -125,8 +125,12 @@ def test_benchmark_circuits_vs_reference(name, dev):
         # floor is the one grad_tolerance derives (4 ulp(1) = 5e-7 per element): near the root all
         # units of a layer agree to below fp32 resolution (ulp(4357) = 4.9e-4), so a root-weight
         # gradient whose float64 value is 1.7e-7 per element may legitimately come out as exactly 0.
+        # In deep circuits with large |ll| (PoonDomingos 3x32x32: 45 layers, |ll| = 18 000) the
+        # per-element bound of grad_tolerance (activation rounding, 8*eps32*|ll|*max W) exceeds that
+        # floor; the L1 check follows it up to 5e-6 per element.
         got_abs = flat.abs().sum().item()
-        assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * 5e-7, f"leaf {i} abs-sum {got_abs} vs {gabs}"
+        floor = min(max(5e-7, tol), 5e-6)
+        assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * floor, f"leaf {i} abs-sum {got_abs} vs {gabs}"
 
 
 @pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_tucker_k4", "rbt12_gaussian_k5"])
@@ -377,3 +381,41 @@ def test_k128_circuits_vs_oracle(name, batch, dev):
         err = (got.double().cpu() - gr).abs().max().item()
         tol = grad_tolerance(gr, gout_l1=float(w.abs().sum()), ll_max=ll_max)
         assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("H,K,Ko", [(2, 4, 4), (9, 4, 4), (13, 4, 4), (3, 40, 4), (5, 32, 32), (3, 64, 64)])
+def test_concatenating_sum_layers(H, K, Ko, dev):
+    """TorchSumLayer with arity H > 1 (cirkit/backend/torch/layers/inner.py:266-273): one LSE over
+    the concatenation of the H inputs, reduction lengths on both sides of 32 and of 128 (the
+    PoonDomingos circuit of BASELINE.json configs[3] has one of length 13*K)."""
+    import numpy as np
+
+    from cirkit_b200 import B200Circuit
+    from cirkit_b200.plan import CircuitPlan, LeafSpec, ParamSpec, StepSpec
+    from oracle import OracleCircuit
+
+    steps = [
+        StepSpec("categorical", H, 1, 1, K, params={"probs": ParamSpec(0, [("softmax", {"dim": 1})], (H, K, 16))},
+                 scope_idx=np.arange(H, dtype=np.int32), config={"num_categories": 16}),
+        StepSpec("sum", 1, H, K, Ko, params={"weight": ParamSpec(1, [("softmax", {"dim": 1})], (1, Ko, H * K))},
+                 in_step=np.zeros((1, H), np.int32), in_fold=np.arange(H, dtype=np.int32).reshape(1, H)),
+    ]
+    plan = CircuitPlan(steps, [LeafSpec((H, K, 16)), LeafSpec((1, Ko, H * K))], np.array([1], np.int32),
+                       np.array([0], np.int32), H, tuple(range(H)))
+    gen = torch.Generator().manual_seed(H * 100 + K)
+    vals = [torch.randn(l.shape, generator=gen) * (3.0 if i == 0 else 1.0) for i, l in enumerate(plan.leaves)]
+    cc, oc = B200Circuit(plan), OracleCircuit(plan, dtype=torch.float64)
+    with torch.no_grad():
+        for p, q, v in zip(cc.leaves, oc.leaves, vals):
+            p.copy_(v)
+            q.copy_(v.double())
+    cc = cc.to(dev)
+    x = torch.randint(0, 16, (37, H), generator=gen)
+    y, yo = cc(x.to(dev)), oc(x)
+    assert y.shape == yo.shape
+    assert (y.detach().double().cpu() - yo.detach()).abs().max().item() <= 5e-7 * yo.abs().max().item() + 1e-5
+    (-y.mean()).backward()
+    (-yo.mean()).backward()
+    for i, (p, q) in enumerate(zip(cc.leaves, oc.leaves)):
+        err = (p.grad.double().cpu() - q.grad).abs().max().item()
+        assert err <= grad_tolerance(q.grad), f"leaf {i}: {err:.3e}"
