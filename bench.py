@@ -423,12 +423,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qt28_cp_k64", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=2048, help="per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=256, help="batch of the bounded CPU sample")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="per-GPU batch (default 2048; 512 for pd32_cp_k128 = configs[3]: 4096 over 8 GPUs)")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="batch of the bounded CPU sample (default 256; 32 for pd32_cp_k128)")
     ap.add_argument("--no-grad-allreduce", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 512 if args.workload == "pd32_cp_k128" else 2048
+    if args.cpu_batch is None:
+        args.cpu_batch = 32 if args.workload == "pd32_cp_k128" else 256
     if args.impl == "reference":
         run_reference(args)  # bounded sample: --cpu-batch samples per step
     else:
