@@ -9,9 +9,10 @@
 //
 // The reference materialises nothing smaller than the einsum torch picks; its unfused route
 // (Kronecker layer + sum layer) writes the (F, B, Ki^2) product to memory.  Here the Kronecker
-// operand e1 (x) e2 is formed in registers and written straight into swizzled shared-memory MMA
-// tiles, so only x1, x2, y, g and W touch HBM.  All products are 3xTF32 (hi*hi + hi*lo + lo*hi,
-// see sm100.cuh), operand tiles are 128-byte-swizzled K-major.
+// operand e1 (x) e2 is formed in registers and written straight into TMEM (the A operand of the
+// MMAs), so only x1, x2, y, g, W and the per-step operand images derived from them touch HBM.
+// All products are 3xTF32 (hi*hi + hi*lo + lo*hi, see sm100.cuh); shared-memory operand tiles
+// (the weight side) are 128-byte-swizzled K-major.
 //
 // The tensor core truncates when it folds a product group into the fp32 accumulator (~0.6 ulp low
 // per accumulating instruction, measured).  Over the 512 k-steps of a Ki^2 = 4096 reduction that
@@ -49,10 +50,7 @@ int tucker_debug_read(void* dst, size_t bytes) {
   } while (0)
 #else
 #define TKDBG(kb, slot) do { } while (0)
-#define TKMARK(slot)                                                                       \
-  do {                                                                                     \
-    if (blockIdx.x == 0 && blockIdx.y == 0) g_dbg_tk[slot] = clock64();                    \
-  } while (0)
+#define TKMARK(slot) do { } while (0)
 #define DXDBG(i, slot) do { } while (0)
 #endif
 
