@@ -138,3 +138,28 @@ def test_integrate_query(reference):
         # all variables integrated out of a normalised circuit: log Z = 0
         got = oc(x, integrate_mask=torch.ones(1, 16, dtype=torch.bool))
     assert abs(got[0].item()) < 1e-9
+
+
+def test_sum_collapse_matmul_parameter_is_lowered(reference):
+    """The SumCollapse rule (cirkit/backend/torch/optimization/layers.py:30-47) turns sum∘sum into
+    one sum layer whose weight is `TorchMatMulParameter(W1, mixing(W2))`
+    (parameters/nodes.py:786-805).  The adapter lowers that graph into the plan (`matmul` op with
+    a second leaf chain) instead of leaving it to the host, so values AND gradients of both leaves
+    are the reference's."""
+    from cirkit.pipeline import PipelineContext
+
+    found = False
+    for shape in [(1, 6, 6), (1, 8, 8), (3, 8, 8)]:
+        sc = _image(reference, shape, "poon-domingos", "cp", 3)
+        tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+        D = shape[0] * shape[1] * shape[2]
+        with torch.enable_grad():
+            low = _compare(tc, torch.randint(0, 256, (4, D)))
+        assert not low.externals
+        ops = [o for s in low.plan.steps for p in s.params.values() for o, _ in p.ops]
+        found |= "matmul" in ops
+        # the plan (with the nested right-operand chain) survives serialisation
+        again = type(low.plan).load(low.plan.to_bytes())
+        assert [[o for o, _ in p.ops] for s in again.steps for p in s.params.values()] == \
+               [[o for o, _ in p.ops] for s in low.plan.steps for p in s.params.values()]
+    assert found, "none of the PoonDomingos circuits exercised the SumCollapse weight"
