@@ -1,12 +1,12 @@
 """Layer-by-layer report of the Tucker tcgen05 kernels against the float64 oracle (GPU box).
-usage: python scripts/debug_tucker.py [batch ...]"""
+usage: python tests/tools/debug_tucker.py [batch ...]"""
 import dataclasses
 import os
 import sys
 
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 

@@ -1,6 +1,6 @@
 """Focused check of concatenating sum layers (TorchSumLayer, arity H > 1) against the oracle."""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
 import numpy as np, torch
 from cirkit_b200 import B200Circuit

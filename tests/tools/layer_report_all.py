@@ -1,6 +1,6 @@
 """Layer-by-layer parity of a fixture: CUDA activations of every step vs the float64 oracle."""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
 import torch
 from helpers import Golden

@@ -1,7 +1,7 @@
 """clock64 timeline of stages 8.. of the Tucker backward-dX kernel (library built with
 CKB_NVCC_EXTRA=-DCKB_TIMELINE)."""
 import ctypes, dataclasses, os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
 import numpy as np, torch
 from helpers import Golden
