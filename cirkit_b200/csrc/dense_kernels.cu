@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(256) dense_fwd_small(DenseArgs a) {
   for (int64_t b0 = ((int64_t)blockIdx.x * 8 + warp) * SW; b0 < a.B;
        b0 += (int64_t)gridDim.x * 8 * SW) {
     float m_reg[SW];
-    if (a.concat) {
-      // concatenating sums (rare, small): one sample at a time
+    if (a.concat || a.Kred > 32 * NO) {
+      // concatenating sums, and reduction lengths beyond the register tile of the batched gather
+      // below (the tile is sized by Ko: 32 * NO indices) -- rare and small: one sample at a time
 #pragma unroll 1
       for (int s = 0; s < SW; ++s) {
         const int64_t b = b0 + s;
