@@ -61,6 +61,7 @@ def _lower_param(p, leaf_ids: dict[int, int], leaves: list, leaf_specs: list[Lea
         N.TorchSoftplusParameter: "softplus",
         N.TorchClampParameter: "clamp",
         N.TorchMixingWeightParameter: "mixing",
+        N.TorchConjugateParameter: "conj",
     }
     entries = list(p.address_book)
     mods = [e.module for e in entries[:-1]]
@@ -77,7 +78,8 @@ def _lower_param(p, leaf_ids: dict[int, int], leaves: list, leaf_specs: list[Lea
         if key not in leaf_ids:
             leaf_ids[key] = len(leaves)
             leaves.append(t)
-            leaf_specs.append(LeafSpec(tuple(t.shape), "normal", bool(t.requires_grad), names.get(key, "")))
+            leaf_specs.append(LeafSpec(tuple(t.shape), "normal", bool(t.requires_grad), names.get(key, ""),
+                                       "complex" if t.is_complex() else "float"))
         return leaf_ids[key]
 
     def chain(i: int):
@@ -137,8 +139,14 @@ def _lower_param(p, leaf_ids: dict[int, int], leaves: list, leaf_specs: list[Lea
 
 
 # --------------------------------------------------------------------------- layers
-def plan_from_torch(tc, *, allow_external_params: bool = True) -> LoweredCircuit:
-    """Lower a compiled `TorchCircuit` to a plan (see module docstring)."""
+def plan_from_torch(tc, *, allow_external_params: bool = True,
+                    semirings: tuple[str, ...] = ("lse-sum",)) -> LoweredCircuit:
+    """Lower a compiled `TorchCircuit` to a plan (see module docstring).
+
+    `semirings` lists the semirings the caller can execute.  The CUDA runtime implements
+    'lse-sum' only, so that is the default and anything else raises UnsupportedCircuitError;
+    the plan format itself also describes 'complex-lse-sum' circuits (complex64 leaves), which
+    the test oracle evaluates -- fixtures for the complex kernels are generated that way."""
     from cirkit.backend.torch.layers.inner import (
         TorchHadamardLayer,
         TorchKroneckerLayer,
@@ -151,7 +159,10 @@ def plan_from_torch(tc, *, allow_external_params: bool = True) -> LoweredCircuit
         TorchGaussianLayer,
     )
     from cirkit.backend.torch.layers.optimized import TorchCPTLayer, TorchTuckerLayer
-    from cirkit.backend.torch.semiring import LSESumSemiring
+    from cirkit.backend.torch.semiring import ComplexLSESumSemiring, LSESumSemiring
+
+    semiring_names = {LSESumSemiring: "lse-sum", ComplexLSESumSemiring: "complex-lse-sum"}
+    semiring = None
 
     names = {id(t): n for n, t in tc.named_parameters()}
     leaf_ids: dict[int, int] = {}
@@ -177,10 +188,13 @@ def plan_from_torch(tc, *, allow_external_params: bool = True) -> LoweredCircuit
 
     for sid, e in enumerate(entries[:-1]):
         m = e.module
-        if m.semiring is not LSESumSemiring:
+        if semiring_names.get(m.semiring) not in semirings:
             raise UnsupportedCircuitError(
                 f"semiring {m.semiring.__name__} has no CUDA path yet (lse-sum only)"
             )
+        if semiring not in (None, m.semiring):
+            raise UnsupportedCircuitError("layers of one circuit disagree on the semiring")
+        semiring = m.semiring
         F = m.num_folds
         params: dict[str, ParamSpec] = {}
         for name, p in m.params.items():
@@ -250,7 +264,7 @@ def plan_from_torch(tc, *, allow_external_params: bool = True) -> LoweredCircuit
         out_fold=out_fold.reshape(-1),
         num_variables=(max(scope) + 1) if scope else 0,
         scope=scope,
-        semiring="lse-sum",
+        semiring=semiring_names.get(semiring, "lse-sum"),
     )
     plan.validate()
     return LoweredCircuit(plan, leaves, externals)

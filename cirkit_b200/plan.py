@@ -50,7 +50,10 @@ PARAM_OPS = (
     # TorchMatMulParameter nodes.py:786-805 (SumCollapse): attrs {"rhs": {"leaf", "ops", "fold_idx"}},
     # the right operand being another leaf -> op chain of the same plan
     "matmul",
+    "conj",  # TorchConjugateParameter nodes.py (complex circuits: conjugate(c) shares c's leaves)
 )
+
+SEMIRINGS = ("lse-sum", "complex-lse-sum")  # cirkit/backend/torch/semiring.py:326-408, :410-476
 
 
 @dataclass
@@ -61,6 +64,7 @@ class LeafSpec:
     init: str = "normal"  # how reset_parameters() fills it ("normal" = nn.init.normal_)
     requires_grad: bool = True
     name: str = ""  # state_dict key of the tensor in the reference module, if known
+    dtype: str = "float"  # "float" | "complex" (complex64 leaves of 'complex-lse-sum' circuits)
 
 
 @dataclass
@@ -133,6 +137,13 @@ class CircuitPlan:
 
     # ---------------------------------------------------------------- validation
     def validate(self) -> None:
+        if self.semiring not in SEMIRINGS:
+            raise ValueError(f"unknown semiring {self.semiring!r}")
+        for lid, l in enumerate(self.leaves):
+            if l.dtype not in ("float", "complex"):
+                raise ValueError(f"leaf {lid}: unknown dtype {l.dtype!r}")
+            if l.dtype == "complex" and self.semiring != "complex-lse-sum":
+                raise ValueError(f"leaf {lid}: complex leaf in a {self.semiring!r} circuit")
         for sid, s in enumerate(self.steps):
             if s.kind not in ALL_KINDS:
                 raise ValueError(f"step {sid}: unknown kind {s.kind!r}")
@@ -162,6 +173,8 @@ class CircuitPlan:
                 for op, attrs in p.ops:
                     if op not in PARAM_OPS:
                         raise ValueError(f"step {sid}: parameter op {op!r} is not supported")
+                    if op == "conj" and self.semiring != "complex-lse-sum":
+                        raise ValueError(f"step {sid}: 'conj' outside a complex circuit")
                     if op == "matmul" and not 0 <= attrs["rhs"]["leaf"] < len(self.leaves):
                         raise ValueError(f"step {sid}: matmul operand points past the leaf table")
 
@@ -246,7 +259,8 @@ class CircuitPlan:
                 )
             )
         leaves = [
-            LeafSpec(tuple(l["shape"]), l["init"], l["requires_grad"], l.get("name", ""))
+            LeafSpec(tuple(l["shape"]), l["init"], l["requires_grad"], l.get("name", ""),
+                     l.get("dtype", "float"))
             for l in header["leaves"]
         ]
         plan = cls(

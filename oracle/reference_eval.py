@@ -9,7 +9,8 @@ is not installed (GPU box).  Gradients come from autograd, exactly as in the ref
 (no custom backward on the real-valued path).
 
 Parity status: pinned against the live reference in `tests/test_oracle_vs_reference.py` and
-against `tests/golden/*.npz`.
+against `tests/golden/*.npz` -- for the 'lse-sum' semiring and, ahead of the CUDA kernels for it,
+for 'complex-lse-sum' (semiring.py:410-476; fixtures of kind "complex").
 """
 
 from __future__ import annotations
@@ -44,6 +45,46 @@ def lse_apply_reduce(func, *xs: Tensor, dim: int = -1) -> Tensor:
     return torch.log(y) + functools.reduce(torch.add, max_xs)
 
 
+class _ComplexSafeLog(torch.autograd.Function):
+    """`csafelog`, cirkit/backend/torch/utils.py:32-50: complex log whose backward replaces the
+    NaN / inf of d log(z) = g / conj(z) at z = 0 by 0 / the largest finite values."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor) -> Tensor:
+        ctx.save_for_backward(z)
+        return torch.log(z)
+
+    @staticmethod
+    def backward(ctx, g: Tensor) -> Tensor:
+        (z,) = ctx.saved_tensors
+        return torch.nan_to_num(g / z.conj())
+
+
+def complex_cast(t: Tensor) -> Tensor:
+    """`ComplexLSESumSemiring.cast`, semiring.py:414-421."""
+    if t.is_complex():
+        return t
+    if t.is_floating_point():
+        return t.to(t.dtype.to_complex())
+    return t.to(torch.get_default_dtype().to_complex())
+
+
+def complex_lse_apply_reduce(func, *xs: Tensor, dim: int = -1) -> Tensor:
+    """`ComplexLSESumSemiring.apply_reduce`, semiring.py:440-476 (keepdim=True): as the real
+    block, with the shift taken over the REAL parts, complex exp, and the safe complex log."""
+    max_xs = [
+        torch.clamp(
+            torch.amax(xi.real, dim=dim, keepdim=True),
+            min=torch.finfo(xi.real.dtype).min,
+            max=torch.finfo(xi.real.dtype).max,
+        )
+        for xi in xs
+    ]
+    exp_xs = [torch.exp(xi - mi) for xi, mi in zip(xs, max_xs)]
+    y = func(*exp_xs)
+    return _ComplexSafeLog.apply(y) + functools.reduce(torch.add, max_xs)
+
+
 # --------------------------------------------------------------------------- parameters
 def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
     """One re-parameterisation node, cirkit/backend/torch/parameters/nodes.py (dim is given
@@ -67,6 +108,8 @@ def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
         return torch.nn.functional.softplus(t)
     if op == "clamp":
         return torch.clamp(t, min=attrs.get("vmin"), max=attrs.get("vmax"))
+    if op == "conj":
+        return torch.conj(t)  # TorchConjugateParameter, nodes.py:742-746
     if op == "mixing":
         # TorchMixingWeightParameter.forward, nodes.py:857-862: (F, K, H) -> (F, K, H*K)
         d = torch.vmap(torch.vmap(torch.diag, in_dims=1))(t)
@@ -80,12 +123,17 @@ class OracleCircuit(nn.Module):
 
     def __init__(self, plan: CircuitPlan, dtype: torch.dtype = torch.float32):
         super().__init__()
-        if plan.semiring != "lse-sum":
-            raise NotImplementedError("the oracle restates the 'lse-sum' semiring path")
+        if plan.semiring not in ("lse-sum", "complex-lse-sum"):
+            raise NotImplementedError(
+                "the oracle restates the 'lse-sum' and 'complex-lse-sum' semiring paths")
         plan.validate()
         self.plan = plan
+        # semiring.py:382-408 (real) / :440-476 (complex: activations are complex logs)
+        self.is_complex = plan.semiring == "complex-lse-sum"
+        self._reduce = complex_lse_apply_reduce if self.is_complex else lse_apply_reduce
         self.leaves = nn.ParameterList(
-            [nn.Parameter(torch.empty(l.shape, dtype=dtype), requires_grad=l.requires_grad)
+            [nn.Parameter(torch.empty(l.shape, dtype=dtype.to_complex() if l.dtype == "complex" else dtype),
+                          requires_grad=l.requires_grad)
              for l in plan.leaves]
         )
         self.reset_parameters()
@@ -122,7 +170,21 @@ class OracleCircuit(nn.Module):
 
     def reset_parameters(self) -> None:
         for t, spec in zip(self.leaves, self.plan.leaves):
-            init_leaf_(t.data, spec)
+            # complex leaves: real and imaginary parts drawn independently
+            init_leaf_(torch.view_as_real(t.data) if t.is_complex() else t.data, spec)
+
+    def _from_lse(self, y: Tensor) -> Tensor:
+        """`semiring.map_from(y, LSESumSemiring)`: identity / cast (semiring.py:511-514)."""
+        return complex_cast(y) if self.is_complex else y
+
+    def _from_linear(self, v: Tensor) -> Tensor:
+        """`semiring.map_from(v, SumProductSemiring)`: log (semiring.py:497-499) / the safe
+        complex log of the cast value (:506-508)."""
+        return _ComplexSafeLog.apply(complex_cast(v)) if self.is_complex else torch.log(v)
+
+    def _operand(self, w: Tensor) -> Tensor:
+        """`SemiringImpl.einsum` casts the weight operands, semiring.py:181-192."""
+        return complex_cast(w) if self.is_complex else w
 
     # ---------------------------------------------------------------- parameters
     def param(self, p: ParamSpec) -> Tensor:
@@ -162,7 +224,7 @@ class OracleCircuit(nn.Module):
             # TorchConstantValueLayer.forward, layers/input.py:739-743
             v = self.param(s.params["value"])
             v = v.unsqueeze(1).expand(F, batch, K)
-            return v if s.config.get("log_space", False) else torch.log(v)
+            return self._from_lse(v) if s.config.get("log_space", False) else self._from_linear(v)
         assert x is not None
         scope_idx = torch.as_tensor(s.scope_idx, dtype=torch.int64).view(F, 1)
         xs = x[..., scope_idx].permute(1, 0, 2)  # circuits.py:66 -> (F, B, 1)
@@ -176,7 +238,7 @@ class OracleCircuit(nn.Module):
             else:
                 logits = self.param(s.params["logits"])
             idx_fold = torch.arange(F)
-            return logits[idx_fold[:, None], :, xs]
+            return self._from_lse(logits[idx_fold[:, None], :, xs])
         if s.kind == "embedding":
             # TorchEmbeddingLayer.forward, layers/input.py:258-266 (+ log morphism semiring.py:499)
             if xs.is_floating_point():
@@ -184,7 +246,7 @@ class OracleCircuit(nn.Module):
             xs = xs.squeeze(2)
             w = self.param(s.params["weight"])
             idx_fold = torch.arange(F)
-            return torch.log(w[idx_fold[:, None], :, xs])
+            return self._from_linear(w[idx_fold[:, None], :, xs])
         if s.kind == "gaussian":
             # TorchGaussianLayer.log_unnormalized_likelihood, layers/input.py:661-670
             mean = self.param(s.params["mean"]).unsqueeze(1)
@@ -192,22 +254,23 @@ class OracleCircuit(nn.Module):
             lp = torch.distributions.Normal(loc=mean, scale=stddev).log_prob(xs)
             if "log_partition" in s.params:
                 lp = lp + self.param(s.params["log_partition"]).unsqueeze(1)
-            return lp
+            return self._from_lse(lp)
         raise ValueError(s.kind)
 
     def _integrate(self, s: StepSpec) -> Tensor:
         """`TorchInputLayer.integrate` for the layers on the path: layers/input.py:280-282,
         :414-421 (Categorical), :672-678 (Gaussian).  Shape (F, 1, K)."""
         F, K = s.num_folds, s.num_output_units
-        ref = self.leaves[0]
+        ref = next(iter(s.params.values()))
+        dtype = self.leaves[ref.leaf].dtype if ref.leaf >= 0 else self.leaves[0].dtype
         if s.kind == "categorical":
             if "probs" in s.params:
-                return torch.zeros(F, 1, K, dtype=ref.dtype)
-            return torch.logsumexp(self.param(s.params["logits"]), dim=2).unsqueeze(1)
+                return self._from_lse(torch.zeros(F, 1, K, dtype=dtype))
+            return self._from_lse(torch.logsumexp(self.param(s.params["logits"]), dim=2).unsqueeze(1))
         if s.kind == "gaussian":
             if "log_partition" in s.params:
-                return self.param(s.params["log_partition"]).unsqueeze(1)
-            return torch.zeros(F, 1, K, dtype=ref.dtype)
+                return self._from_lse(self.param(s.params["log_partition"]).unsqueeze(1))
+            return self._from_lse(torch.zeros(F, 1, K, dtype=dtype))
         raise TypeError(f"integration is not supported for {s.kind} layers")
 
     def _inner_layer(self, s: StepSpec, x: Tensor) -> Tensor:
@@ -226,17 +289,18 @@ class OracleCircuit(nn.Module):
             w = self.param(s.params["weight"])
             if s.kind == "mixing":
                 w = apply_param_op(w, "mixing", {})
+            w = self._operand(w)
             xf = x.permute(0, 2, 1, 3).flatten(start_dim=2)
-            return lse_apply_reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w), xf)
+            return self._reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w), xf)
         if s.kind == "cpt":
             # TorchCPTLayer.forward, layers/optimized.py:171-178
-            w = self.param(s.params["weight"])
+            w = self._operand(self.param(s.params["weight"]))
             u = x.sum(dim=1)
-            return lse_apply_reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w), u)
+            return self._reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w), u)
         if s.kind == "tucker":
             # TorchTuckerLayer.forward, layers/optimized.py:89-103 (einsum spec :62-66)
             H, Ki, Ko = s.arity, s.num_input_units, s.num_output_units
-            w = self.param(s.params["weight"]).view(-1, Ko, *([Ki] * H))
+            w = self._operand(self.param(s.params["weight"])).view(-1, Ko, *([Ki] * H))
             spec = (
                 tuple((0, 1, i + 2) for i in range(H))
                 + ((0, H + 2, *tuple(i + 2 for i in range(H))),)
@@ -249,7 +313,7 @@ class OracleCircuit(nn.Module):
                     args += [t, list(sub)]
                 return torch.einsum(*args, list(spec[-1]))
 
-            return lse_apply_reduce(f, *x.unbind(dim=1))
+            return self._reduce(f, *x.unbind(dim=1))
         raise ValueError(s.kind)
 
     # ---------------------------------------------------------------- executor

@@ -50,8 +50,8 @@ from cirkit_b200.plan import seeded_leaves  # noqa: E402
 PROBE = 64  # gradient entries kept per leaf in seeded fixtures
 
 
-def compile_ref(sc, fold=True, optimize=True):
-    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=fold, optimize=optimize)
+def compile_ref(sc, fold=True, optimize=True, semiring="lse-sum"):
+    ctx = PipelineContext(backend="torch", semiring=semiring, fold=fold, optimize=optimize)
     return ctx, ctx.compile(sc)
 
 
@@ -64,14 +64,16 @@ def ref_forward_backward(tc, leaves, x):
         p.grad = None
     with torch.enable_grad():
         y = tc(x)
-        (-y.mean()).backward()
+        # complex circuits: the gradient of the real part (the SoS loss is 2 Re c(x) - Re Z,
+        # notebooks/sum-of-squares-circuits.ipynb cell 32)
+        (-(y.real if y.is_complex() else y).mean()).backward()
     return y.detach(), [
         (torch.zeros_like(p) if p.grad is None else p.grad.detach().clone()) for p in leaves
     ]
 
 
-def write_full(name, tc, x, *, masks=None, extra=None):
-    low = plan_from_torch(tc, allow_external_params=False)
+def write_full(name, tc, x, *, masks=None, extra=None, kind="full"):
+    low = plan_from_torch(tc, allow_external_params=False, semirings=("lse-sum", "complex-lse-sum"))
     y, grads = ref_forward_backward(tc, low.leaves, x)
     out = {"plan": plan_array(low.plan), "x": x.numpy(), "y": y.numpy()}
     for i, (p, g) in enumerate(zip(low.leaves, grads)):
@@ -82,7 +84,7 @@ def write_full(name, tc, x, *, masks=None, extra=None):
         with torch.no_grad():
             out["mask"] = masks.numpy()
             out["y_mask"] = q(x, integrate_vars=masks).numpy()
-    meta = {"kind": "full", "steps": [s.kind for s in low.plan.steps]}
+    meta = {"kind": kind, "steps": [s.kind for s in low.plan.steps]}
     meta.update(extra or {})
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
@@ -250,7 +252,43 @@ def case_pd32():
     write_seeded("pd32_cp_k4", tc, x, seed=1234, extra={"units": 4, "config": 3})
 
 
+def case_complex():
+    """'complex-lse-sum' circuits (BASELINE.json configs[4] structure at small size; SURVEY §8 a7,
+    a16): complex Embedding inputs and complex sum weights, real part and imaginary part uniform
+    in [0, 1) as in notebooks/sum-of-squares-circuits.ipynb cell 12.  Fixture kind "complex": the
+    CUDA runtime has no kernels for this semiring yet, the oracle is pinned here ahead of them."""
+    B = 16
+    torch.manual_seed(42)
+    cplx = utils.Parameterization(dtype="complex", initialization="uniform")
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=16,
+        input_layers={"name": "embedding", "args": {
+            "num_states": 16, "weight_factory": utils.parameterization_to_factory(cplx)}},
+        num_input_units=4, sum_product_layer="cp-t", num_sum_units=4, sum_weight_param=cplx)
+    ctx, tc = compile_ref(sc, semiring="complex-lse-sum")
+    x = torch.randint(0, 16, (B, 16))
+    write_full("rbt16_cpt_k4_complex", tc, x, kind="complex")
+    # the conjugate circuit shares c's leaves through `conj` parameter nodes
+    tcc = ctx.compile(SF.conjugate(sc))
+    write_full("rbt16_cpt_k4_complex_conj", tcc, x, kind="complex")
+    # Tucker, un-optimised CP (sum / hadamard / mixing layers) and a circuit with real-valued
+    # Categorical inputs under complex sum weights (map_from(LSE) = cast, semiring.py:511-514)
+    emb = {"name": "embedding", "args": {
+        "num_states": 16, "weight_factory": utils.parameterization_to_factory(cplx)}}
+    cat = {"name": "categorical", "args": {"num_categories": 16}}
+    for name, layers, spl, K, D, optimize in [
+            ("rbt8_tucker_k3_complex", emb, "tucker", 3, 8, True),
+            ("rbt12_cp_k3_complex_unopt", emb, "cp", 3, 12, False),
+            ("rbt8_cpt_k4_complex_categorical", cat, "cp-t", 4, 8, True)]:
+        sc = data_modalities.tabular_data(
+            "random-binary-tree", num_features=D, input_layers=layers, num_input_units=K,
+            sum_product_layer=spl, num_sum_units=K, sum_weight_param=cplx)
+        _, tc = compile_ref(sc, optimize=optimize, semiring="complex-lse-sum")
+        write_full(name, tc, torch.randint(0, 16, (B, D)), kind="complex")
+
+
 CASES = {
+    "complex": case_complex,
     "pd32": case_pd32,
     "ka_categorical": case_ka_categorical,
     "ka_gaussian": case_ka_gaussian,

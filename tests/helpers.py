@@ -29,7 +29,8 @@ class Golden:
     def leaves(self, dtype=torch.float64) -> list[torch.Tensor]:
         if self.kind == "seeded":
             return [t.to(dtype) for t in seeded_leaves(self.plan, self.meta["seed"])]
-        return [torch.from_numpy(self.z[f"leaf_{i}"]).to(dtype) for i in range(len(self.plan.leaves))]
+        vals = [torch.from_numpy(self.z[f"leaf_{i}"]) for i in range(len(self.plan.leaves))]
+        return [v.to(dtype.to_complex() if v.is_complex() else dtype) for v in vals]
 
     def x(self) -> torch.Tensor | None:
         return torch.from_numpy(self.z["x"]) if "x" in self.z else None

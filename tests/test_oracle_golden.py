@@ -9,6 +9,7 @@ from oracle import OracleCircuit
 
 FULL = golden_names("full")
 SEEDED = golden_names("seeded")
+COMPLEX = golden_names("complex")
 FP64_RTOL, FP64_ATOL = 1e-8, 1e-12  # the reference's own tolerances, tests/floats.py:5-6
 
 
@@ -31,6 +32,56 @@ def test_forward_and_gradients_match_reference(name):
     for p, gr in zip(oc.leaves, g.grads()):
         got = torch.zeros_like(p) if p.grad is None else p.grad
         torch.testing.assert_close(got, gr, rtol=1e-7, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", COMPLEX)
+def test_complex_semiring_matches_reference(name):
+    """'complex-lse-sum' circuits (semiring.py:440-476, csafelog utils.py:32-50):
+    complex128 outputs and the gradients of -mean(Re y) against the reference's."""
+    g = Golden(name)
+    assert g.plan.semiring == "complex-lse-sum"
+    oc = _oracle(g)
+    y = oc(g.x())
+    assert y.is_complex() and y.shape == g.y().shape
+    torch.testing.assert_close(y, g.y(), rtol=FP64_RTOL, atol=FP64_ATOL)
+    (-y.real.mean()).backward()
+    for p, gr in zip(oc.leaves, g.grads()):
+        got = torch.zeros_like(p) if p.grad is None else p.grad
+        assert got.dtype == gr.dtype
+        torch.testing.assert_close(got, gr, rtol=1e-7, atol=1e-13)
+    # fp32 leaves -> complex64 activations, the dtype a CUDA path would compute in
+    oc32 = _oracle(g, torch.float32)
+    with torch.no_grad():
+        y32 = oc32(g.x())
+    assert y32.dtype == torch.complex64
+    # compare through exp: the imaginary part is a phase (test_compile_circuit_operators.py:236-238)
+    torch.testing.assert_close(torch.exp(y32 - g.y().real.to(torch.complex64)),
+                               torch.exp(g.y() - g.y().real).to(torch.complex64), rtol=2e-4, atol=2e-4)
+
+
+def test_complex_safe_log_gradient_is_finite_at_zero():
+    """tests/backend/torch/test_semiring.py:29-38: the gradient of the safe complex log at 0."""
+    from oracle.reference_eval import _ComplexSafeLog
+
+    z = torch.zeros(5, dtype=torch.complex64)
+    z.real[2] = z.imag[2] = 1.0
+    z.requires_grad = True
+    _ComplexSafeLog.apply(z).mean().real.backward()
+    assert torch.all(torch.isfinite(torch.view_as_real(z.grad)))
+    assert z.grad[2] == (0.2 / torch.tensor(1 - 1j)).to(torch.complex64)
+
+
+def test_complex_lse_agrees_with_real_lse_on_tiny_weights():
+    """tests/backend/torch/test_semiring.py:41-61: x = (-200, -200, -5), w = (1, 2, 1e-38)."""
+    from oracle.reference_eval import complex_lse_apply_reduce, lse_apply_reduce
+
+    x = torch.tensor([[-200.0, -200.0, -5.0]])
+    w = torch.tensor([[1.0], [2.0], [1e-38]])
+    y1 = lse_apply_reduce(lambda e: torch.einsum("kj,ji->ki", e, w), x)
+    y2 = complex_lse_apply_reduce(
+        lambda e: torch.einsum("kj,ji->ki", e, w.to(torch.complex64)), x.to(torch.complex64))
+    assert torch.isfinite(y1).all() and torch.isfinite(torch.view_as_real(y2)).all()
+    torch.testing.assert_close(y1, y2.real)
 
 
 @pytest.mark.parametrize("name", [n for n in FULL if Golden(n).mask()[0] is not None])

@@ -31,10 +31,10 @@ def _image(reference, shape, rg, spl, K, **kw):
         sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"), **kw)
 
 
-def _compare(tc, x):
+def _compare(tc, x, semirings=("lse-sum",)):
     from cirkit_b200.adapter import plan_from_torch
 
-    low = plan_from_torch(tc)
+    low = plan_from_torch(tc, semirings=semirings)
     oc = OracleCircuit(low.plan, dtype=torch.float64)
     with torch.no_grad():
         for p, v in zip(oc.leaves, low.leaves):
@@ -47,8 +47,8 @@ def _compare(tc, x):
     assert y.shape == y_ref.shape
     torch.testing.assert_close(y, y_ref, rtol=1e-10, atol=1e-12)
     if not low.externals:
-        (-y_ref.mean()).backward()
-        (-y.mean()).backward()
+        (-(y_ref.real if y_ref.is_complex() else y_ref).mean()).backward()
+        (-(y.real if y.is_complex() else y).mean()).backward()
         for a, b in zip(oc.leaves, low.leaves):
             ga = torch.zeros_like(a) if a.grad is None else a.grad
             gb = torch.zeros_like(b) if b.grad is None else b.grad
@@ -163,3 +163,36 @@ def test_sum_collapse_matmul_parameter_is_lowered(reference):
         assert [[o for o, _ in p.ops] for s in again.steps for p in s.params.values()] == \
                [[o for o, _ in p.ops] for s in low.plan.steps for p in s.params.values()]
     assert found, "none of the PoonDomingos circuits exercised the SumCollapse weight"
+
+
+@pytest.mark.parametrize("spl,fold,optimize", [(spl, f, o) for spl in ("cp-t", "cp", "tucker")
+                                               for f, o in [(True, True), (True, False), (False, False)]])
+def test_complex_semiring_circuits(reference, spl, fold, optimize):
+    """'complex-lse-sum' (semiring.py:410-476): complex Embedding inputs and sum weights as in
+    notebooks/sum-of-squares-circuits.ipynb cell 12, every fold/optimize combination; the circuit
+    c, its conjugate (shared leaves through `conj` nodes) and their gradients.  The runtime does not
+    execute these plans yet -- the default lowering must keep refusing them."""
+    import cirkit.symbolic.functional as SF
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+    from cirkit_b200.adapter import UnsupportedCircuitError, plan_from_torch
+
+    cplx = utils.Parameterization(dtype="complex", initialization="uniform")
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=8,
+        input_layers={"name": "embedding", "args": {
+            "num_states": 7, "weight_factory": utils.parameterization_to_factory(cplx)}},
+        num_input_units=3, sum_product_layer=spl, num_sum_units=3, sum_weight_param=cplx)
+    ctx = PipelineContext(backend="torch", semiring="complex-lse-sum", fold=fold, optimize=optimize)
+    tc = ctx.compile(sc)
+    with pytest.raises(UnsupportedCircuitError):
+        plan_from_torch(tc)
+    both = ("lse-sum", "complex-lse-sum")
+    x = torch.randint(0, 7, (6, 8))
+    with torch.enable_grad():
+        low = _compare(tc, x, both)
+        assert low.plan.semiring == "complex-lse-sum" and not low.externals
+        lowc = _compare(ctx.compile(SF.conjugate(sc)), x, both)
+    assert any(op == "conj" for s in lowc.plan.steps for p in s.params.values() for op, _ in p.ops)
+    # the conjugate circuit reads the very same leaf tensors
+    assert {id(t) for t in lowc.leaves} == {id(t) for t in low.leaves}

@@ -51,3 +51,30 @@ def test_validate_rejects_bad_gathers():
     bad.steps[2].in_fold[0, 0] = 10_000
     with pytest.raises(ValueError):
         bad.validate()
+
+
+def test_complex_plans_are_described_but_not_executed():
+    """The plan format carries 'complex-lse-sum' circuits (complex leaves, `conj` parameter nodes)
+    for the oracle and the fixtures; the CUDA runtime has no kernels for them and says so."""
+    from cirkit_b200 import B200Circuit
+
+    plan = Golden("rbt16_cpt_k4_complex_conj").plan
+    assert plan.semiring == "complex-lse-sum"
+    assert {l.dtype for l in plan.leaves} == {"complex"}
+    assert any(op == "conj" for s in plan.steps for p in s.params.values() for op, _ in p.ops)
+    again = CircuitPlan.load(plan.to_bytes())
+    assert [l.dtype for l in again.leaves] == [l.dtype for l in plan.leaves]
+    with pytest.raises(NotImplementedError, match="lse-sum"):
+        B200Circuit(plan)
+    # a complex leaf or a conjugation inside a real-valued circuit is a malformed plan
+    bad = CircuitPlan.load(plan.to_bytes())
+    bad.semiring = "lse-sum"
+    with pytest.raises(ValueError):
+        bad.validate()
+    real = CircuitPlan.load(Golden("qt8_cp_k4").plan.to_bytes())
+    real.steps[1].params["weight"].ops.append(("conj", {}))
+    with pytest.raises(ValueError, match="conj"):
+        real.validate()
+    real.semiring = "tropical"
+    with pytest.raises(ValueError, match="semiring"):
+        real.validate()
