@@ -23,6 +23,21 @@ void set_error(const char* fmt, ...);
   } while (0)
 #define CKB_LAUNCH_CHECK() CKB_CUDA_CHECK(cudaGetLastError())
 
+// Kernel attributes (the opt-in to > 48 KB of dynamic shared memory) belong to a device, not to
+// the process: one mask bit per device ordinal, set the first time a launcher runs there.  A
+// race between two host threads only repeats an idempotent cudaFuncSetAttribute call.
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 // ------------------------------------------------------------------ per-call context
 struct Ctx {
   int64_t B;

@@ -147,11 +147,10 @@ template <int NO, int SW>
 static int launch_dense_fwd_small(const DenseArgs& a, int F, Ctx& c) {
   const int KredP = (a.Kred + 3) & ~3;
   const size_t smem = ((size_t)KredP * (32 * NO + 1) + 8 * SW * KredP) * 4 + 16;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_fwd_small<NO, SW>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   dim3 grid(max(1, ceil_div(a.B, 8 * SW)), F);
   dense_fwd_small<NO, SW><<<grid, 256, smem, c.stream>>>(a);
@@ -314,11 +313,10 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
     set_error("dense_fwd: reduction length %d too large", a.Kred);
     return CKB_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_fwd_generic,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
   dense_fwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride);
@@ -540,11 +538,10 @@ static int launch_dense_bwd_small(const DenseArgs& a, int F, int splits, Ctx& c)
   const int LR = max(4, (a.Ko + AL - 1) / AL * AL);
   const int LE = (a.Kred + AL - 1) / AL * AL;
   const size_t smem = ((size_t)LR * KS + 8 * SW * (LR + LE)) * 4 + 16;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_small<NI, TT, SW>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   dim3 grid(splits, F);
   dense_bwd_small<NI, TT, SW><<<grid, 256, smem, c.stream>>>(a);
@@ -663,11 +660,10 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
     set_error("dense_bwd: reduction length %d too large", a.Kred);
     return CKB_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_generic,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   if (dW) CKB_CUDA_CHECK(cudaMemsetAsync(dW, 0, n * 4, c.stream));
   dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);

@@ -735,13 +735,12 @@ int debug_read(void* dst, size_t bytes) {
 int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
   if (tc_disabled() || !dense_tc_ok(a)) return 1;
   const size_t smem = sizeof(FwdSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_fwd_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_fwd_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   const int n_tiles = ceil_div(a.B, TM);
   // ~4 CTAs per SM over the launch (2 resident), several tiles per CTA when the batch allows
@@ -780,13 +779,12 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
     a.dWp = (float*)ws;
   }
   const size_t smem = sizeof(BwdSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   dim3 grid(splits, F);
   if ((g_tc_flags & 3) == 3)

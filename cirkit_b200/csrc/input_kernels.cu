@@ -319,12 +319,11 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
     set_error("table_bwd: %d states do not fit shared memory", V);
     return CKB_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const size_t n = (size_t)d.num_folds * V * d.k_out;
   float* out = dT;

@@ -788,12 +788,11 @@ static DenseArgs tucker_tc_args(const ckb_step_desc_t& d, Ctx& c) {
 }
 
 int tucker_tc_fwd(const ckb_step_desc_t& d, Ctx& c) {
-  static bool attr = false;
+  static PerDeviceOnce attr;
   const size_t smem = sizeof(TkFwdSmem) + 1024;
-  if (!attr) {
+  if (attr.first()) {
     if (int rc = set_smem(tucker_tc_fwd_kernel<true>, smem)) return rc;
     if (int rc = set_smem(tucker_tc_fwd_kernel<false>, smem)) return rc;
-    attr = true;
   }
   const DenseArgs a = tucker_tc_args(d, c);
   if (c.ws_bytes < tucker_tc_fwd_ws(d)) {
@@ -816,13 +815,12 @@ int tucker_tc_fwd(const ckb_step_desc_t& d, Ctx& c) {
 }
 
 int tucker_tc_bwd(const ckb_step_desc_t& d, Ctx& c) {
-  static bool attr = false;
+  static PerDeviceOnce attr;
   const size_t smem_dx = sizeof(TkDxSmem) + 1024, smem_dw = sizeof(TkDwSmem) + 1024;
-  if (!attr) {
+  if (attr.first()) {
     if (int rc = set_smem(tucker_tc_bwd_dx_kernel<true>, smem_dx)) return rc;
     if (int rc = set_smem(tucker_tc_bwd_dx_kernel<false>, smem_dx)) return rc;
     if (int rc = set_smem(tucker_tc_bwd_dw_kernel, smem_dw)) return rc;
-    attr = true;
   }
   DenseArgs a = tucker_tc_args(d, c);
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
