@@ -1,0 +1,90 @@
+"""The drop-in boundary on the reference's side: `PipelineContext(backend="b200")`
+and `accelerate(tc)`, checked against the live reference up to the point where a CUDA device is
+needed (this container has the reference but no GPU; the GPU box has no reference)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.reference
+
+
+def _symbolic(reference, **kw):
+    from cirkit.templates import data_modalities, utils
+
+    return data_modalities.image_data(
+        (1, 4, 4), region_graph="quad-graph", input_layer="categorical", num_input_units=3,
+        sum_product_layer="cp", num_sum_units=3,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"), **kw)
+
+
+def test_pipeline_context_backend_b200(reference):
+    """cirkit/pipeline.py:30-51, :348-356 and backend/compiler.py:11: the backend switch."""
+    import cirkit.backend.compiler as BC
+    import cirkit.symbolic.functional as SF
+    from cirkit.backend.torch.circuits import TorchCircuit
+    from cirkit.pipeline import PipelineContext
+
+    import cirkit_b200
+
+    cirkit_b200.register_backend()
+    cirkit_b200.register_backend()  # idempotent
+    assert BC.SUPPORTED_BACKENDS.count("b200") == 1
+    with pytest.raises(NotImplementedError):  # pipeline.py:41-42 still guards unknown names
+        PipelineContext(backend="nope")
+
+    sc = _symbolic(reference)
+    torch.manual_seed(7)
+    ctx = PipelineContext(backend="b200", semiring="lse-sum", fold=True, optimize=True)
+    cc = ctx.compile(sc)
+    torch.manual_seed(7)
+    ref = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+
+    # same object model: a TorchCircuit subclass with the reference's layers, keys and values
+    assert isinstance(cc, TorchCircuit) and type(cc).__name__ == "B200TorchCircuit"
+    assert list(cc.state_dict().keys()) == list(ref.state_dict().keys())
+    for (k, a), b in zip(cc.state_dict().items(), ref.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert cc.scope == ref.scope and cc.num_variables == ref.num_variables
+    assert [type(l).__name__ for l in cc.layers] == [type(l).__name__ for l in ref.layers]
+    # the runtime binds the circuit's OWN nn.Parameter leaves (optimisers, checkpoints and
+    # pointer-shared circuits see one storage, parameters/nodes.py:193-201)
+    own = {id(p) for p in cc.parameters()}
+    assert {id(p) for p in cc._b200_lowered.leaves} <= own
+    cc.load_state_dict(ref.state_dict())
+    # compiler bookkeeping keeps working (backend/compiler.py:20-37, pipeline.py:168-229)
+    assert ctx.get_symbolic_circuit(cc) is sc
+    zc = ctx.compile(SF.integrate(sc))
+    assert type(zc).__name__ == "B200TorchCircuit" and not zc.scope
+    # learnable leaves are shared with c through pointer nodes (rules/parameters.py:111-117);
+    # what integration adds (the constant log-partition values) is not learnable
+    assert {id(p) for p in zc._b200_lowered.leaves if p.requires_grad} <= own
+    assert any(id(p) in own for p in zc._b200_lowered.leaves)
+
+    # error behaviour of TorchCircuit.forward (circuits.py:60-65, :259-260) ...
+    with pytest.raises(ValueError, match="Expected some input"):
+        cc()
+    # ... and no CPU path behind the accelerated circuit
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.randint(0, 256, (2, 16)))
+
+
+def test_accelerate_leaves_unsupported_circuits_on_the_reference_path(reference):
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    from cirkit_b200 import UnsupportedCircuitError, accelerate
+
+    cplx = utils.Parameterization(dtype="complex", initialization="uniform")
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=4,
+        input_layers={"name": "embedding", "args": {
+            "num_states": 5, "weight_factory": utils.parameterization_to_factory(cplx)}},
+        num_input_units=2, sum_product_layer="cp-t", num_sum_units=2, sum_weight_param=cplx)
+    tc = PipelineContext(backend="torch", semiring="complex-lse-sum", fold=True, optimize=True).compile(sc)
+    cls = type(tc)
+    x = torch.randint(0, 5, (3, 4))
+    y = tc(x)
+    with pytest.raises(UnsupportedCircuitError):
+        accelerate(tc, strict=True)
+    assert accelerate(tc) is tc and type(tc) is cls  # untouched: the reference evaluates it
+    assert "ComplexLSESumSemiring" in tc._b200_reason
+    assert torch.equal(tc(x), y)
