@@ -72,3 +72,40 @@ def test_uneven_sum_layers_vs_oracle(kind, H, K, Ko, dev):
             gerr = (p.grad.double().cpu() - q.grad).abs().max().item()
             tol = grad_tolerance(q.grad, gout_l1=float(w.abs().sum()))
             assert gerr <= tol, f"B={batch} leaf {i}: {gerr:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("units", [6, 8, 11])
+def test_tucker_mid_sizes_vs_oracle(units, dev):
+    """Tucker layers between the fixture size (K = 4) and the tcgen05 size (K = 64): the Kronecker
+    buffer + generic sum kernel route with a reduction length K*K in (32, 128] and K outputs, i.e.
+    again beyond the Ko-sized tile of the batched gather (TorchTuckerLayer,
+    layers/optimized.py:89-103)."""
+    import dataclasses
+
+    from cirkit_b200 import B200Circuit
+    from cirkit_b200.plan import seeded_leaves
+    from helpers import Golden
+    from oracle import OracleCircuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden("qt8_tucker_k4")
+    plan = dataclasses.replace(g.plan, meta={"units": 4}).with_units(units)
+    cc = B200Circuit(plan, seed=9).to(dev)
+    oc = OracleCircuit(plan, dtype=torch.float64)
+    with torch.no_grad():
+        for q, v in zip(oc.leaves, seeded_leaves(plan, 9)):
+            q.copy_(v)
+    batch = 53
+    x = make_inputs(plan, batch, seed=units)
+    y, yo = cc(x.to(dev)), oc(x)
+    assert y.shape == yo.shape
+    err = (y.detach().double().cpu() - yo.detach()).abs().max().item()
+    assert err <= 5e-7 * yo.abs().max().item() + 1e-5, f"{err:.3e}"
+    w = torch.randn(batch, 1, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    (y * w.to(dev, torch.float32)).sum().backward()
+    (yo * w).sum().backward()
+    ll_max = float(yo.detach().abs().max())
+    for i, (p, q) in enumerate(zip(cc.leaves, oc.leaves)):
+        gerr = (p.grad.double().cpu() - q.grad).abs().max().item()
+        tol = grad_tolerance(q.grad, gout_l1=float(w.abs().sum()), ll_max=ll_max)
+        assert gerr <= tol, f"leaf {i}: {gerr:.3e} > {tol:.3e}"
