@@ -113,8 +113,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a 128-byte-swizzled tile whose rows (128 bytes = 32 fp32)
 // are stored densely: 8-row groups are `sbo` bytes apart, 32-element column blocks `lbo` bytes
-// apart.  The same memory image serves as the K-major view of X[row][k] and as the MN-major view
-// of its transpose (see dense_tc.cu).
+// apart.  Every operand in this library is K-major.  (Whether tf32 also accepts the same image as
+// the MN-major view of the transpose -- which would remove the register transposes of the
+// backward kernels -- is what scripts/micro/mn_major_probe.cu is there to find out.)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes) {
   uint64_t d = 0;
