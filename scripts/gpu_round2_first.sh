@@ -1,0 +1,12 @@
+#!/bin/bash
+# First GPU call of round 2 (1 GPU, ~6 min): confirm the tree is green on the box, then run the
+# experiment that decides the shape of the dense_tc_bwd rewrite.
+#   gpurun --timeout 600 -- scripts/gpu_round2_first.sh
+mkdir -p gpurun_out
+if [ ! -x scripts/micro/mn_major_probe ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I cirkit_b200/csrc -I include \
+       -o scripts/micro/mn_major_probe scripts/micro/mn_major_probe.cu
+fi
+timeout 60 scripts/micro/mn_major_probe > gpurun_out/r02_mn_major_probe.txt 2>&1; echo "probe rc=$?"; cat gpurun_out/r02_mn_major_probe.txt
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -1 gpurun_out/r02_pytest_gpu.log
+timeout 400 python bench.py > gpurun_out/r02_bench_cp.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/r02_bench_cp.log | cut -c1-200
