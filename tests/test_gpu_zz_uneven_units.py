@@ -74,10 +74,10 @@ def test_uneven_sum_layers_vs_oracle(kind, H, K, Ko, dev):
             assert gerr <= tol, f"B={batch} leaf {i}: {gerr:.3e} > {tol:.3e}"
 
 
-@pytest.mark.parametrize("units", [6, 8, 11])
+@pytest.mark.parametrize("units", [6, 8, 11, 12])
 def test_tucker_mid_sizes_vs_oracle(units, dev):
     """Tucker layers between the fixture size (K = 4) and the tcgen05 size (K = 64): the Kronecker
-    buffer + generic sum kernel route with a reduction length K*K in (32, 128] and K outputs, i.e.
+    buffer + generic sum kernel route with a reduction length K*K in (32, 128] (K = 12: 144, the any-shape kernels) and K outputs, i.e.
     again beyond the Ko-sized tile of the batched gather (TorchTuckerLayer,
     layers/optimized.py:89-103)."""
     import dataclasses
