@@ -17,6 +17,7 @@ everything else in `cirkit_b200` runs without `cirkit` installed (e.g. from a st
 
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass, field
 from typing import Any
 
@@ -271,6 +272,22 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
 
 
 # --------------------------------------------------------------------------- executor swap
+def _integrate_mask_of(module_fn):
+    """The (B or 1, D) bool mask when `module_fn` is what the reference's own `IntegrateQuery`
+    hands to `evaluate` -- `functools.partial(IntegrateQuery._layer_fn, integrate_vars_mask=m)`,
+    cirkit/backend/torch/queries.py:101-107 -- else None."""
+    from cirkit.backend.torch.queries import IntegrateQuery
+
+    if (
+        isinstance(module_fn, functools.partial)
+        and module_fn.func is IntegrateQuery._layer_fn
+        and not module_fn.args
+        and set(module_fn.keywords) == {"integrate_vars_mask"}
+    ):
+        return module_fn.keywords["integrate_vars_mask"]
+    return None
+
+
 def accelerate(tc, *, strict: bool = False):
     """Re-route `tc(x)` to the CUDA runtime, in place; returns `tc`.
 
@@ -310,10 +327,15 @@ def accelerate(tc, *, strict: bool = False):
             return y
 
         def evaluate(self, x=None, module_fn=None):  # graph/modules.py:303-335
-            if module_fn is not None:
+            # `IntegrateQuery(circuit)(x, integrate_vars=...)` of the reference package arrives
+            # here: its per-layer callback is recognised and becomes the runtime's masked
+            # evaluation (queries.py:112-143).  Any other callback is arbitrary Python per layer
+            # and runs on the reference's own executor, on the circuit's device.
+            mask = _integrate_mask_of(module_fn)
+            if module_fn is not None and mask is None:
                 return super().evaluate(x, module_fn)
             leaves, ext = _tensors(self)
-            return runtime.evaluate(x, leaves, ext).transpose(0, 1)
+            return runtime.evaluate(x, leaves, ext, integrate_mask=mask).transpose(0, 1)
 
         def integrate_query(self, x, mask):
             leaves, ext = _tensors(self)

@@ -88,3 +88,51 @@ def test_accelerate_leaves_unsupported_circuits_on_the_reference_path(reference)
     assert accelerate(tc) is tc and type(tc) is cls  # untouched: the reference evaluates it
     assert "ComplexLSESumSemiring" in tc._b200_reason
     assert torch.equal(tc(x), y)
+
+
+def test_reference_integrate_query_is_routed_to_the_masked_runtime(reference, monkeypatch):
+    """`cirkit.backend.torch.queries.IntegrateQuery(circuit)(x, integrate_vars=...)` calls
+    `circuit.evaluate(x, module_fn=partial(_layer_fn, integrate_vars_mask=m))` (queries.py:101-107).
+    The accelerated circuit recognises that callback and runs its masked kernels instead of the
+    reference's layer loop; any other callback stays on the reference's executor.  No GPU here:
+    the runtime is replaced by a recorder."""
+    from cirkit.backend.torch.queries import IntegrateQuery
+    from cirkit.pipeline import PipelineContext
+    from cirkit.utils.scope import Scope
+
+    import cirkit_b200
+
+    sc = _symbolic(reference)
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    x = torch.randint(0, 256, (5, 16))
+    mask = torch.rand(5, 16) < 0.5
+    want = IntegrateQuery(tc)(x, integrate_vars=mask)  # the reference's answer, (B, O, K)
+    plain = tc(x)
+
+    cc = cirkit_b200.accelerate(tc, strict=True)
+    calls = []
+
+    def recorder(x_, leaves, ext, integrate_mask=None):
+        calls.append(integrate_mask)
+        return want  # (B, O, K), what PlanRuntime.evaluate returns
+
+    monkeypatch.setattr(cc._b200_runtime, "evaluate", recorder)
+    got = IntegrateQuery(cc)(x, integrate_vars=mask)
+    assert len(calls) == 1 and torch.equal(calls[0], mask)
+    assert got.shape == want.shape and torch.equal(got, want)
+    # scope form: one mask row, broadcast over the batch (queries.py:88-92)
+    IntegrateQuery(cc)(x, integrate_vars=Scope([0, 3]))
+    assert calls[1].shape == (1, 16) and calls[1].sum() == 2 and calls[1][0, 3]
+    # plain evaluate(): no mask
+    cc.evaluate(x)
+    assert calls[2] is None
+    # a foreign per-layer callback is not ours to interpret: reference executor, on CPU tensors here
+    seen = []
+
+    def spy(layer, *inputs):
+        seen.append(type(layer).__name__)
+        return layer(*inputs)
+
+    y = cc.evaluate(x, module_fn=spy)
+    assert len(calls) == 3 and len(seen) == len(list(cc.layers))
+    assert torch.equal(y.transpose(0, 1), plain)
