@@ -56,6 +56,30 @@ class B200Circuit(nn.Module):
         else:
             self.reset_parameters()
 
+    @classmethod
+    def from_torch(cls, tc, *, share_parameters: bool = True, fuse_tables: bool = True) -> "B200Circuit":
+        """A stand-alone circuit from one compiled by the reference (`cirkit.pipeline.compile`):
+        the address book and every layer's parameters are lowered to a plan
+        (`adapter.plan_from_torch`), after which the reference object is no longer needed -- the
+        plan can be saved and the circuit evaluated where `cirkit` is not installed.
+
+        With `share_parameters` the module holds the reference circuit's OWN `nn.Parameter` leaves
+        (`TorchTensorParameter._ptensor`, parameters/nodes.py:193-201), so both objects train the
+        same storage; otherwise it gets copies.  Parameter graphs the plan cannot express
+        (kron / einsum nodes of product circuits) need the reference at run time: use
+        `cirkit_b200.accelerate(tc)` for those."""
+        from .adapter import plan_from_torch
+
+        low = plan_from_torch(tc, allow_external_params=False)
+        self = cls(low.plan, fuse_tables=fuse_tables)
+        if share_parameters:
+            self.leaves = nn.ParameterList(low.leaves)
+        else:
+            with torch.no_grad():
+                for p, v in zip(self.leaves, low.leaves):
+                    p.copy_(v)
+        return self
+
     # -- TorchCircuit surface -------------------------------------------------------------
     @property
     def scope(self) -> tuple[int, ...]:

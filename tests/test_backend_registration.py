@@ -7,11 +7,11 @@ import torch
 pytestmark = pytest.mark.reference
 
 
-def _symbolic(reference, **kw):
+def _symbolic(reference, region_graph="quad-graph", **kw):
     from cirkit.templates import data_modalities, utils
 
     return data_modalities.image_data(
-        (1, 4, 4), region_graph="quad-graph", input_layer="categorical", num_input_units=3,
+        (1, 4, 4), region_graph=region_graph, input_layer="categorical", num_input_units=3,
         sum_product_layer="cp", num_sum_units=3,
         sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"), **kw)
 
@@ -136,3 +136,34 @@ def test_reference_integrate_query_is_routed_to_the_masked_runtime(reference, mo
     y = cc.evaluate(x, module_fn=spy)
     assert len(calls) == 3 and len(seen) == len(list(cc.layers))
     assert torch.equal(y.transpose(0, 1), plain)
+
+
+def test_b200circuit_from_torch(reference, tmp_path):
+    """Route B of SURVEY §8(b): post-compile conversion into a stand-alone module."""
+    import cirkit.symbolic.functional as SF
+    from cirkit.pipeline import PipelineContext
+
+    from cirkit_b200 import B200Circuit, CircuitPlan, UnsupportedCircuitError
+
+    sc = _symbolic(reference)
+    ctx = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True)
+    tc = ctx.compile(sc)
+    shared = B200Circuit.from_torch(tc)
+    assert [id(p) for p in shared.parameters()] == [id(p) for p in shared.leaves]
+    assert {id(p) for p in shared.leaves} <= {id(p) for p in tc.parameters()}
+    assert shared.scope == tuple(sorted(tc.scope)) and len(shared.layers) == len(list(tc.layers))
+    copied = B200Circuit.from_torch(tc, share_parameters=False)
+    for a, b in zip(copied.leaves, shared.leaves):
+        assert a is not b and torch.equal(a, b.to(a.dtype))
+    # the plan travels without the reference
+    path = tmp_path / "plan.npz"
+    shared.plan.save(str(path))
+    again = B200Circuit(CircuitPlan.load(str(path)))
+    again.load_state_dict(copied.state_dict())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        shared(torch.randint(0, 256, (2, 16)))
+    # product circuits carry kron parameter graphs: not expressible as a stand-alone plan
+    qt = _symbolic(reference, "quad-tree-2")
+    plain = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=False)
+    with pytest.raises(UnsupportedCircuitError, match="parameter graph"):
+        B200Circuit.from_torch(plain.compile(SF.multiply(qt, qt)))
