@@ -42,3 +42,23 @@ def test_workloads_resolve():
         plan = bench.load_plan(name).plan
         assert (plan.activation_units(), plan.parameter_elements()) == sizes[name], name
         assert bench.metric_name(name).startswith("samples/sec (fwd+bwd log-lik)")
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """The driver launches the reference arm like the CUDA arm (torchrun, N ranks): rank 0 alone
+    runs and prints the line, the other ranks exit 0 without work."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "bench.py"),
+         "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-batch", "8"],
+        capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
