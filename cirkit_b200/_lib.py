@@ -32,6 +32,11 @@ EXPORTS = (
     "ckb_plan_last_launches",
     "ckb_set_option",
     "ckb_debug_read",
+    # experimental complex-semiring building blocks (not used by the plan executor)
+    "ckb_complex_cpt_fwd",
+    "ckb_complex_cpt_bwd",
+    "ckb_complex_embedding_fwd",
+    "ckb_complex_embedding_bwd",
 )
 OPT_TENSOR_CORES = 0
 
@@ -119,6 +124,13 @@ def load():
     lib.ckb_set_option.restype = C.c_int
     lib.ckb_debug_read.argtypes = [vp, C.c_size_t]
     lib.ckb_debug_read.restype = C.c_int
+    lib.ckb_complex_cpt_fwd.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, vp]
+    lib.ckb_complex_cpt_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp]
+    lib.ckb_complex_embedding_fwd.argtypes = [vp, i64, vp, vp, vp, i32, i64, i32, i32, vp]
+    lib.ckb_complex_embedding_bwd.argtypes = [vp, i64, vp, vp, vp, vp, i32, i64, i32, i32, vp]
+    for fn in (lib.ckb_complex_cpt_fwd, lib.ckb_complex_cpt_bwd, lib.ckb_complex_embedding_fwd,
+               lib.ckb_complex_embedding_bwd):
+        fn.restype = C.c_int
     _lib = lib
     return lib
 

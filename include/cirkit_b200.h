@@ -171,6 +171,27 @@ int ckb_set_option(int32_t option, int32_t value);
 /* Copies the device-side debug timeline (clock64 stamps of the tcgen05 kernels) to host memory. */
 int ckb_debug_read(void* dst, size_t bytes);
 
+/* ---- 'complex-lse-sum' building blocks (EXPERIMENTAL: compiled, not yet validated on a GPU; the
+ * plan executor does not use them and refuses complex plans).  Complex tensors are interleaved
+ * (re, im) float pairs in the (fold, batch, unit) layout.  Replaces, per layer:
+ * ComplexLSESumSemiring.apply_reduce semiring.py:440-476 under TorchCPTLayer.forward
+ * layers/optimized.py:171-178 (x1 == NULL: an arity-1 TorchSumLayer, layers/inner.py:266-273),
+ * csafelog utils.py:32-50, TorchEmbeddingLayer.forward layers/input.py:258-266.
+ *   cpt:  x0, x1 (F,B,Ki)  w (F,Ko,Ki)  y, gy (F,B,Ko)  gu (F,B,Ki) = gradient of x0 + x1
+ *         gw (F,Ko,Ki) ACCUMULATED (caller zeroes; may be NULL)
+ *   embedding:  x (B, ld) int64 evidence, var (F,) device int32 column per fold, w (F,K,V),
+ *         y, gy (F,B,K), gw (F,K,V) ACCUMULATED */
+int ckb_complex_cpt_fwd(const float* x0, const float* x1, const float* w, float* y, int32_t F,
+                        int64_t B, int32_t Ki, int32_t Ko, void* stream);
+int ckb_complex_cpt_bwd(const float* x0, const float* x1, const float* w, const float* y,
+                        const float* gy, float* gu, float* gw, int32_t F, int64_t B, int32_t Ki,
+                        int32_t Ko, void* stream);
+int ckb_complex_embedding_fwd(const int64_t* x, int64_t ld, const int32_t* var, const float* w,
+                              float* y, int32_t F, int64_t B, int32_t K, int32_t V, void* stream);
+int ckb_complex_embedding_bwd(const int64_t* x, int64_t ld, const int32_t* var, const float* w,
+                              const float* gy, float* gw, int32_t F, int64_t B, int32_t K,
+                              int32_t V, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

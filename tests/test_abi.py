@@ -54,6 +54,21 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert lib.ckb_plan_workspace_bytes(None, 128) >= 256
 
 
+def test_experimental_complex_entry_points_validate_arguments(lib):
+    """No GPU: the complex building blocks reject null pointers and bad shapes before launching."""
+    assert lib.ckb_complex_cpt_fwd(None, None, None, None, 1, 1, 4, 4, None) == -1
+    assert b"null pointer" in lib.ckb_last_error()
+    buf = (ctypes.c_float * 8)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.ckb_complex_cpt_fwd(p, None, p, p, 0, 1, 4, 4, None) == -1
+    assert b"bad shape" in lib.ckb_last_error()
+    assert lib.ckb_complex_cpt_bwd(p, None, p, p, p, None, None, 1, 1, 4, 4, None) == -1
+    assert lib.ckb_complex_embedding_fwd(None, 0, None, None, None, 1, 1, 4, 4, None) == -1
+    assert lib.ckb_complex_embedding_bwd(p, 1, p, p, p, None, 1, 1, 4, 4, None) == -1
+    # an empty batch is a no-op, not an error
+    assert lib.ckb_complex_cpt_fwd(p, None, p, p, 1, 0, 4, 4, None) == 0
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from cirkit_b200 import _lib
 

@@ -147,3 +147,47 @@ def test_error_behaviour():
         oc()
     with pytest.raises(ValueError, match="shape"):
         oc(torch.zeros(3, dtype=torch.int64))
+
+
+def test_complex_backward_formulas_of_the_kernels():
+    """The closed-form backward csrc/complex_kernels.cu implements -- r = gy / conj(S) with
+    S = exp(y - m), g_e = r conj(W), g_u = g_e conj(e), g_W = r conj(e), the shift m held constant;
+    Embedding: g_W[f,k,x] += gy / conj(W[f,k,x]) -- equals autograd through the oracle's complex
+    path (PyTorch's convention for complex gradients), layer by layer, in float64."""
+    from oracle.reference_eval import _ComplexSafeLog, complex_lse_apply_reduce
+
+    g = Golden("rbt16_cpt_k4_complex")
+    plan = g.plan
+    oc = _oracle(g)
+    x = g.x()
+    y = oc(x)
+    outs = oc.last_outputs
+    for t in outs:
+        t.retain_grad()
+    (-y.real.mean()).backward()
+    for sid, s in enumerate(plan.steps):
+        F, gy = s.num_folds, outs[sid].grad
+        w = oc.param(s.params["weight"]).detach()
+        w_ = w.clone().requires_grad_()
+        if s.kind == "embedding":
+            xs = x[:, torch.as_tensor(s.scope_idx, dtype=torch.int64)].t()  # (F, B)
+            _ComplexSafeLog.apply(w_[torch.arange(F)[:, None], :, xs]).backward(gy)
+            gw = torch.zeros_like(w)
+            for f in range(F):
+                for b in range(x.shape[0]):
+                    gw[f, :, xs[f, b]] += gy[f, b, :] / w[f, :, xs[f, b]].conj()
+            torch.testing.assert_close(gw, w_.grad, rtol=1e-12, atol=1e-14)
+            continue
+        ins = [torch.stack([outs[int(s.in_step[f, h])][int(s.in_fold[f, h])] for f in range(F)])
+               for h in range(s.arity)]
+        u = sum(ins).detach()
+        u_ = u.clone().requires_grad_()
+        y_ = complex_lse_apply_reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w_), u_)
+        y_.backward(gy)
+        m = u.real.amax(-1, keepdim=True)
+        e, S = torch.exp(u - m), torch.exp(y_.detach() - m)
+        r = gy / S.conj()
+        gu = torch.einsum("fbo,foi->fbi", r, w.conj()) * e.conj()
+        gw = torch.einsum("fbo,fbi->foi", r, e.conj())
+        torch.testing.assert_close(gu, u_.grad, rtol=1e-10, atol=1e-14)
+        torch.testing.assert_close(gw, w_.grad, rtol=1e-10, atol=1e-14)
