@@ -1,0 +1,213 @@
+// Forward of the fused sum-product block for Ki = Ko = 128 (BASELINE.json configs[3]) on tcgen05,
+// TS form: the generated operand e = exp(u - m) lives in TMEM, the fold's split weights in shared
+// memory for the whole CTA.
+//
+// EXPERIMENTAL -- written at the end of round 1 without GPU time left: compiled for sm_100a, NOT
+// yet run.  It is only dispatched when bit 9 (512) of CKB_OPT_TC_FAST_MATH is set
+// (tests/test_gpu_zzz_dense128.py, CKB_EXPERIMENTAL=1); by default K = 128 layers keep taking the
+// FP32 SIMT kernels.  The backward stays on the SIMT kernels either way.
+//
+//   y[b,o] = log( sum_i W[o,i] exp(u[b,i] - m[b]) ) + m[b],  u = x_0 (+ x_1),  m = max_i u
+//   (TorchCPTLayer.forward layers/optimized.py:171-178 / TorchSumLayer.forward
+//   layers/inner.py:266-273 through LSESumSemiring.apply_reduce semiring.py:382-408)
+//
+// CTA = (fold, a run of 128-sample tiles), 16 warps.  Thread = (sample row q*32 + lane, column
+// group cg of 32 units): it loads its 32 pre-activations, the four column groups of a row combine
+// their maxima through shared memory, e is split into (hi, lo) and written to TMEM with
+// tcgen05.st, warp 0 issues 16 k-steps of  e_hi x [W_hi | W_lo] (N = 256: main | correction)  and
+// e_lo x W_hi (N = 128: correction), and every thread reads its 32 outputs back for the log
+// epilogue.  TMEM: e_hi [0,128) e_lo [128,256) main [256,384) correction [384,512) -- all 512
+// columns, one CTA per SM.  Phases of a tile are serial (no room to double-buffer); the
+// feasibility arithmetic is in DESIGN.md section 8, item 4.
+#include "dense.cuh"
+#include "sm100.cuh"
+#include "tc_util.cuh"
+
+namespace ckb {
+using namespace sm100;
+
+namespace {
+
+constexpr int TM = 128;   // samples per tile (UMMA M)
+constexpr int K128 = 128; // Ki = Ko
+constexpr int kThreads128 = 512;
+constexpr uint32_t kWBlk = 256 * 128;  // bytes of one k-block: [hi o 0..127 | lo o 0..127] x 32 fp32
+
+struct __align__(1024) Fwd128Smem {
+  float w[4][256 * 32];  // [k-block][hi rows | lo rows][32], 128-byte swizzle        128 KB
+  float part[4][TM];     // per column group row maxima
+  uint64_t a_full, d_full;
+  uint32_t tmem_base;
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads128, 1)
+dense128_tc_fwd_kernel(DenseArgs a, int tiles_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  Fwd128Smem& s = *reinterpret_cast<Fwd128Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int n_tiles_total = (int)((a.B + TM - 1) / TM);
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
+  if (n_tiles <= 0) return;
+
+  const float* row0 = in_row(a, f, 0);
+  const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
+
+  if (tid == 0) {
+    mbar_init(&s.a_full, kThreads128 / 32);
+    mbar_init(&s.d_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
+
+  // ---- the fold's weights -> (hi | lo) swizzled K-major image; loads first, stores after
+  {
+    const float* Wf = a.W + (int64_t)f * K128 * K128;
+    const uint32_t wbase = smem_u32(s.w);
+    constexpr int PER = K128 * K128 / 4 / kThreads128;  // 8 float4 per thread
+    float4 v[PER];
+#pragma unroll
+    for (int n = 0; n < PER; ++n) v[n] = __ldg(reinterpret_cast<const float4*>(Wf) + tid + n * kThreads128);
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      const int p = tid + n * kThreads128;
+      const int o = p >> 5, c4 = p & 31;  // row o, float4 number c4 of its 32
+      const uint32_t kb = c4 >> 3, chunk = c4 & 7;
+      float4 hi, lo;
+      split4(v[n], hi, lo);
+      const uint32_t off = kb * kWBlk + (uint32_t)o * 128u + (((chunk ^ (uint32_t)o) & 7u) << 4);
+      sts128(wbase + off, hi);
+      sts128(wbase + off + 128u * 128u, lo);  // rows 128 + o: same swizzle phase
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+
+  const int q = warp & 3, cg = warp >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  constexpr uint32_t kColLo = 128, kColMain = 256, kColCorr = 384;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int64_t b = (int64_t)(t_begin + it) * TM + row;
+    const bool valid = b < a.B;
+    const int64_t off = (valid ? b : 0) * K128 + cg * 32;
+    // ---- this thread's 32 pre-activations
+    float u[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 v = ldg_stream(row0 + off + 4 * c);
+      if (row1) {
+        const float4 w = ldg_stream(row1 + off + 4 * c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+    }
+    float m = u[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) m = fmaxf(m, u[j]);
+    s.part[cg][row] = m;
+    __syncthreads();  // also: every thread is past the previous tile's epilogue
+    m = clamp_max(fmaxf(fmaxf(s.part[0][row], s.part[1][row]), fmaxf(s.part[2][row], s.part[3][row])));
+    // ---- e = exp(u - m) -> (hi, lo) -> TMEM columns cg*32 .. cg*32+31 of lane `row`
+    // (the previous tile's MMAs have completed: this thread waited for d_full in its epilogue)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = valid ? exp_nonpos<FAST>(u[16 * h + j] - m) : 0.f;
+        split_tf32(e, hi[j], lo[j]);
+      }
+      tmem_st16(lane_base + cg * 32 + 16 * h, hi);
+      tmem_st16(lane_base + kColLo + cg * 32 + 16 * h, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.a_full);
+    // ---- MMA issue: whole warp converged, instructions on the elected lane
+    if (warp == 0) {
+      mbar_wait(&s.a_full, it & 1);
+      tc_fence_after_sync();
+      constexpr uint32_t idesc_n256 = make_idesc_tf32(TM, 2 * K128, 0, 0);
+      constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, K128, 0, 0);
+      const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+#pragma unroll
+      for (int ks = 0; ks < K128 / 8; ++ks) {
+        const uint64_t b_w = desc_at(d_w, (ks >> 2) * kWBlk + (ks & 3) * 32);
+        mma_tf32_ts_warp(tmem_base + kColMain, tmem_base + ks * 8, b_w, idesc_n256, ks ? 1u : 0u);
+        mma_tf32_ts_warp(tmem_base + kColCorr, tmem_base + kColLo + ks * 8, b_w, idesc_n128, 1u);
+      }
+      mma_commit_warp(&s.d_full);
+      __syncwarp();
+    }
+    // ---- epilogue: y = log(main + correction) + m for this thread's 32 outputs
+    mbar_wait(&s.d_full, it & 1);
+    tc_fence_after_sync();
+    float* yo = a.y + ((int64_t)f * a.B + (valid ? b : 0)) * K128 + cg * 32;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[16], w[16];
+      tmem_ld16(lane_base + kColMain + cg * 32 + 16 * h, v);
+      tmem_ld16(lane_base + kColCorr + cg * 32 + 16 * h, w);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 o;
+          o.x = log_<FAST>(v[j] + w[j]) + m;
+          o.y = log_<FAST>(v[j + 1] + w[j + 1]) + m;
+          o.z = log_<FAST>(v[j + 2] + w[j + 2]) + m;
+          o.w = log_<FAST>(v[j + 3] + w[j + 3]) + m;
+          *reinterpret_cast<float4*>(yo + 16 * h + j) = o;
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool dense128_tc_ok(const DenseArgs& a) {
+  return (tc_flags() & 512) && !tc_disabled() && a.Ki == K128 && a.Ko == K128 && a.Kred == K128 &&
+         !a.concat && a.H >= 1 && a.H <= 2;
+}
+
+int dense128_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
+  const size_t smem = sizeof(Fwd128Smem) + 1024;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense128_tc_fwd_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense128_tc_fwd_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int n_tiles = ceil_div(a.B, TM);
+  // one CTA per SM (all of TMEM); two waves of CTAs over the launch when the batch allows
+  int splits = (int)max64(1, min64(n_tiles, ceil_div(2 * kNumSMs, F)));
+  const int tiles_per_cta = ceil_div(n_tiles, splits);
+  splits = ceil_div(n_tiles, tiles_per_cta);
+  dim3 grid(splits, F);
+  if ((tc_flags() & 3) == 3)
+    dense128_tc_fwd_kernel<true><<<grid, kThreads128, smem, c.stream>>>(a, tiles_per_cta);
+  else
+    dense128_tc_fwd_kernel<false><<<grid, kThreads128, smem, c.stream>>>(a, tiles_per_cta);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+}  // namespace ckb

@@ -292,6 +292,7 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
     if (rc <= 0) return rc;
   }
   if (dense32_ok(a)) return dense32_fwd(a, F, c);
+  if (dense128_tc_ok(a)) return dense128_tc_fwd(a, F, c);  // experimental, off by default
   if (dense_ko1_ok(a)) {
     dim3 grid(dense_ko1_blocks(F, a.B), F);
     dense_ko1_fwd_kernel<<<grid, 256, 0, c.stream>>>(a);

@@ -165,7 +165,8 @@ int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 
 /* Process-wide switches (testing / A-B measurements). */
 #define CKB_OPT_TENSOR_CORES 0 /* 1 (default): tcgen05 kernels for the shapes that have one; 0: FP32 SIMT only */
-#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels (default 3) */
+#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels (default 3);
+                                  bit 9 (512): EXPERIMENTAL tcgen05 forward for Ki = Ko = 128 (not yet validated, off by default) */
 int ckb_set_option(int32_t option, int32_t value);
 
 /* Copies the device-side debug timeline (clock64 stamps of the tcgen05 kernels) to host memory. */

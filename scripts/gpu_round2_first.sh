@@ -9,5 +9,6 @@ if [ ! -x scripts/micro/mn_major_probe ]; then
 fi
 timeout 60 scripts/micro/mn_major_probe > gpurun_out/r02_mn_major_probe.txt 2>&1; echo "probe rc=$?"; cat gpurun_out/r02_mn_major_probe.txt
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -1 gpurun_out/r02_pytest_gpu.log
+CKB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zzz_dense128.py -m gpu -q -x > gpurun_out/r02_dense128.log 2>&1; echo "dense128 rc=$?"; tail -15 gpurun_out/r02_dense128.log
 CKB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zzz_complex_kernels.py -m gpu -q > gpurun_out/r02_complex_kernels.log 2>&1; echo "complex kernels rc=$?"; tail -15 gpurun_out/r02_complex_kernels.log
 timeout 400 python bench.py > gpurun_out/r02_bench_cp.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/r02_bench_cp.log | cut -c1-200
