@@ -52,8 +52,11 @@ int dense_tc_bwd(const DenseArgs& a, int F, float* dW, Ctx& c, char* ws, size_t 
 size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B);
 
 // Ki = Ko = 128 forward on tcgen05 (dense128_tc.cu): EXPERIMENTAL, opt-in (CKB_OPT_TC_FAST_MATH bit 9)
+int tc_flags();  // CKB_OPT_TC_FAST_MATH bits (dense_tc.cu)
 bool dense128_tc_ok(const DenseArgs& a);
 int dense128_tc_fwd(const DenseArgs& a, int F, Ctx& c);
+size_t dense128_tc_bwd_ws(int F, int64_t B);
+int dense128_tc_bwd(const DenseArgs& a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes);
 
 // Ki = Ko = 32 (dense32_kernels.cu)
 bool dense32_ok(const DenseArgs& a);

@@ -595,7 +595,17 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
   }
 }
 
+static size_t run_dense_bwd_ws_default(int F, int H, int Ko, int Kred, int64_t B);
 static size_t run_dense_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
+  const size_t base = run_dense_bwd_ws_default(F, H, Ko, Kred, B);
+  // experimental K = 128 tcgen05 backward (off by default): room for its row shifts and partials
+  if ((tc_flags() & 512) && Ko == 128 && Kred == 128 && H <= 2) {
+    const size_t need = dense128_tc_bwd_ws(F, B);
+    return need > base ? need : base;
+  }
+  return base;
+}
+static size_t run_dense_bwd_ws_default(int F, int H, int Ko, int Kred, int64_t B) {
   if (Ko == 1 && Kred <= 32 * kKo1MaxPerLane) return (size_t)dense_ko1_blocks(F, B) * F * Kred * 4;
   const size_t tc = dense_tc_bwd_ws(F, H, Ko, Kred, B);
   if (Ko == 32 && Kred == 32 && H <= 2) return dense32_bwd_ws(F, B);
@@ -614,6 +624,10 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
   }
   const size_t n = (size_t)F * a.Ko * a.Kred;
   if (dense32_ok(a)) return dense32_bwd(a, F, dW, c, ws, ws_bytes);
+  if (dense128_tc_ok(a)) {  // experimental, off by default
+    const int rc = dense128_tc_bwd(a, F, dW, c, ws, ws_bytes);
+    if (rc <= 0) return rc;
+  }
   if (dense_ko1_ok(a)) {
     const int blocks = dense_ko1_blocks(F, a.B);
     a.dWp = dW;
