@@ -230,18 +230,23 @@ dense128_tc_bwd_du_kernel(DenseArgs a, int tiles_per_cta, float* __restrict__ m_
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 512);
 
-  // ---- W^T image: rows i (N), K = o.  Element (i, o) = W[o][i].
+  // ---- W^T image: rows i (N), K = o.  Element (i, o) = W[o][i].  The lanes of a warp take 32
+  // consecutive o's (the K axis, contiguous inside an image row), so the scalar stores of one
+  // instruction fill one 128-byte row segment: no bank conflicts.
   {
     const float* Wf = a.W + (int64_t)f * K128 * K128;
     const uint32_t wbase = smem_u32(s.w);
     constexpr int PER = K128 * K128 / 4 / kThreads128;
     float4 v[PER];
 #pragma unroll
-    for (int n = 0; n < PER; ++n) v[n] = __ldg(reinterpret_cast<const float4*>(Wf) + tid + n * kThreads128);
+    for (int n = 0; n < PER; ++n) {
+      const int p = tid + n * kThreads128;
+      v[n] = __ldg(reinterpret_cast<const float4*>(Wf + (p & 127) * K128 + (p >> 7) * 4));
+    }
 #pragma unroll
     for (int n = 0; n < PER; ++n) {
       const int p = tid + n * kThreads128;
-      const uint32_t o = p >> 5, i0 = (p & 31) * 4;
+      const uint32_t o = p & 127, i0 = (uint32_t)(p >> 7) * 4;
       float4 hi, lo;
       split4(v[n], hi, lo);
       const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
