@@ -219,6 +219,10 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.tc_flags is not None:
+        from cirkit_b200 import _lib
+
+        _lib.check(_lib.load().ckb_set_option(1, args.tc_flags), "ckb_set_option")
     g = load_plan(args.workload)
     plan = g.plan
     cc = B200Circuit(plan, seed=1234).to(dev)
@@ -387,6 +391,7 @@ def run_b200(args):
             "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
             "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
             "leaves": "seeded N(0,1), seed 1234",
+            **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8,
@@ -430,6 +435,9 @@ def main():
     ap.add_argument("--no-grad-allreduce", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
+    ap.add_argument("--tc-flags", type=int, default=None,
+                    help="developer switch: value for CKB_OPT_TC_FAST_MATH (3 = default kernels; "
+                         "3|512 also routes K=128 layers to the experimental tcgen05 kernels)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 512 if args.workload == "pd32_cp_k128" else 2048
