@@ -26,6 +26,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "samples/sec (fwd+bwd log-lik) QuadTree 28x28 K=64"  # BASELINE.json metric
+REF_VERSION = "0.2.1"  # libcirkit, pyproject.toml of the reference checkout
 UNIT = "samples/s"
 WORKLOADS = {
     "qt28_cp_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=64",
@@ -130,30 +131,88 @@ class ClockSampler(threading.Thread):
         }
 
 
+def make_config(args, world, plan):
+    """The `config` object of the JSON line -- the same for this repo's arm and the reference arm."""
+    B = args.batch
+    return {
+        "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
+        "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
+        "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
+        "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
+        "leaves": "seeded N(0,1), seed 1234",
+        **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
+    }
+
+
 # ------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference's algorithm on the host cores (oracle port: same PyTorch op sequence as
-    cirkit/backend/torch, see oracle/reference_eval.py).  Bounded sample of the same workload."""
-    from oracle import OracleCircuit
+REF_DIR = os.path.join(REPO, "baseline", "_ref")  # pip --target install of the unmodified reference
+REF_SPECS = {  # workload -> image_data(shape, region graph, sum-product layer, units)
+    "qt28_cp_k64": ((1, 28, 28), "quad-tree-2", "cp", 64),
+    "qt28_cp_k32": ((1, 28, 28), "quad-tree-2", "cp", 32),
+    "qt28_tucker_k64": ((1, 28, 28), "quad-tree-2", "tucker", 64),
+    "pd32_cp_k128": ((3, 32, 32), "poon-domingos", "cp", 128),
+}
+
+
+def build_reference(workload, plan):
+    """The UNMODIFIED reference (april-tools/cirkit, installed under baseline/_ref) compiled through
+    its own public API -- `data_modalities.image_data` -> `PipelineContext(backend="torch")` -- for
+    `workload`, holding the same seeded parameters as this repo's arm.  Returns (circuit, kind):
+    kind "reference", or (OracleCircuit, "port") when the install is missing / cannot be imported."""
     from cirkit_b200.plan import seeded_leaves
 
+    try:
+        if not os.path.isdir(os.path.join(REF_DIR, "cirkit")):
+            raise ImportError(f"{REF_DIR} not present")
+        if REF_DIR not in sys.path:
+            sys.path.insert(1, REF_DIR)
+        from cirkit.pipeline import PipelineContext
+        from cirkit.templates import data_modalities, utils
+
+        from cirkit_b200.adapter import plan_from_torch
+
+        shape, rg, spl, K = REF_SPECS[workload]
+        sc = data_modalities.image_data(
+            shape, region_graph=rg, input_layer="categorical", num_input_units=K,
+            sum_product_layer=spl, num_sum_units=K,
+            sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+        tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+        low = plan_from_torch(tc, allow_external_params=False)  # only to name the leaves in plan order
+        if [tuple(l.shape) for l in low.plan.leaves] != [tuple(l.shape) for l in plan.leaves]:
+            raise RuntimeError("reference circuit and fixture plan disagree on the leaf shapes")
+        with torch.no_grad():
+            for p, v in zip(low.leaves, seeded_leaves(plan, 1234)):
+                p.copy_(v)
+        return tc, "reference"
+    except Exception as exc:  # pragma: no cover - depends on the box
+        sys.stderr.write(f"bench: reference install unusable ({exc!r}); timing the oracle port\n")
+        from oracle import OracleCircuit
+
+        oc = OracleCircuit(plan, dtype=torch.float32)
+        with torch.no_grad():
+            for p, v in zip(oc.leaves, seeded_leaves(plan, 1234)):
+                p.copy_(v)
+        return oc, "port"
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores: the unmodified
+    reference package from baseline/_ref through its public API (fallback: the oracle port, same
+    PyTorch op sequence, when the install is absent).  Same workload and batch as this repo's arm."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = load_plan(args.workload)
-    oc = OracleCircuit(g.plan, dtype=torch.float32)
-    with torch.no_grad():
-        for p, v in zip(oc.leaves, seeded_leaves(g.plan, 1234)):
-            p.copy_(v)
+    oc, kind = build_reference(args.workload, g.plan)
     B = args.cpu_batch
     gen = torch.Generator().manual_seed(0)
     xs = [torch.randint(0, 256, (B, g.plan.num_variables), generator=gen) for _ in range(2)]
 
     def step(i):
-        for p in oc.leaves:
-            p.grad = None
+        oc.zero_grad(set_to_none=True)
         ll = oc(xs[i % len(xs)])
         (-ll.mean()).backward()
         return ll
@@ -170,38 +229,33 @@ def run_reference(args):
         "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "batch": B, "device": "cpu",
-                   "leaves": "seeded N(0,1), seed 1234"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of batch {B} (same circuit, fp32, torch CPU ops)"},
+        "config": make_config(args, world, g.plan),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps of batch {B} on rank 0's host cores "
+                                   f"({'cirkit ' + REF_VERSION + ' from baseline/_ref, backend=torch' if kind == 'reference' else 'oracle port, torch CPU ops'}, "
+                                   f"fp32, {cores} threads, device cpu)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(g, batch, steps=3, warmup=1):
-    from oracle import OracleCircuit
-    from cirkit_b200.plan import seeded_leaves
-
+def cpu_baseline(g, workload, batch, steps=3, warmup=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    oc = OracleCircuit(g.plan, dtype=torch.float32)
-    with torch.no_grad():
-        for p, v in zip(oc.leaves, seeded_leaves(g.plan, 1234)):
-            p.copy_(v)
+    oc, kind = build_reference(workload, g.plan)
     x = torch.randint(0, 256, (batch, g.plan.num_variables), generator=torch.Generator().manual_seed(0))
     ts = []
     for i in range(warmup + steps):
-        for p in oc.leaves:
-            p.grad = None
+        oc.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
         ll = oc(x)
         (-ll.mean()).backward()
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
-    return {"value": batch / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"median of {steps} steps of batch {batch} (same circuit, fp32, torch CPU ops, "
+    return {"value": batch / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"median of {steps} steps of batch {batch} (same circuit and parameters, fp32, "
+                      f"{'unmodified reference from baseline/_ref' if kind == 'reference' else 'oracle port'}, "
                       f"{cores} threads)"}
 
 
@@ -380,19 +434,12 @@ def run_b200(args):
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump(prof, fh, indent=1)
-    base = cpu_baseline(g, args.cpu_batch) if world == 1 and not args.no_cpu_baseline else None
+    base = cpu_baseline(g, args.workload, args.cpu_batch) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
-            "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
-            "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
-            "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
-            "leaves": "seeded N(0,1), seed 1234",
-            **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
-        },
+        "config": make_config(args, world, plan),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": float(ms2.item()) / args.steps,
@@ -431,7 +478,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None,
                     help="per-GPU batch (default 2048; 512 for pd32_cp_k128 = configs[3]: 4096 over 8 GPUs)")
     ap.add_argument("--cpu-batch", type=int, default=None,
-                    help="batch of the bounded CPU sample (default 256; 32 for pd32_cp_k128)")
+                    help="batch of the CPU arm (default: the per-GPU batch, i.e. the same config; "
+                         "256 for the Tucker workload and 32 for pd32_cp_k128, whose full batch takes minutes per step)")
     ap.add_argument("--no-grad-allreduce", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None)
@@ -442,7 +490,7 @@ def main():
     if args.batch is None:
         args.batch = 512 if args.workload == "pd32_cp_k128" else 2048
     if args.cpu_batch is None:
-        args.cpu_batch = 32 if args.workload == "pd32_cp_k128" else 256
+        args.cpu_batch = {"pd32_cp_k128": 32, "qt28_tucker_k64": 256}.get(args.workload, args.batch)
     if args.impl == "reference":
         run_reference(args)  # bounded sample: --cpu-batch samples per step
     else:

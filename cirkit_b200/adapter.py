@@ -248,6 +248,13 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
             arity, k_in = 1, 0
         else:
             arity, k_in = int(m.arity), int(m.num_input_units)
+            if kind in ("tucker", "kronecker") and arity != 2:
+                # the library rejects these at ckb_plan_create (plan.cu:check_step); say so here,
+                # while accelerate() can still leave the circuit on the reference path
+                raise UnsupportedCircuitError(
+                    f"step {sid}: {kind} layers have CUDA kernels for arity 2 only (got {arity})")
+            if kind == "mixing" and k_in != int(m.num_output_units):
+                raise UnsupportedCircuitError(f"step {sid}: mixing layer with {k_in} != {m.num_output_units} units")
             in_step, in_fold = resolve(e.in_module_ids[0], e.in_fold_idx[0], F, arity)
         steps.append(
             StepSpec(kind, F, arity, k_in, int(m.num_output_units), params, in_step, in_fold,

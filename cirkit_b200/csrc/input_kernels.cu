@@ -288,6 +288,34 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
   }
 }
 
+// Gradient of the value an integrated variable contributes (logsumexp of unnormalised logits,
+// layers/input.py:414-421): dI[f,k] = sum of g[f,b,k] over the samples whose variable is masked.
+// One CTA per fold, fixed summation order (threads: 32 units x 8 batch slices).
+__global__ void masked_gsum_kernel(GradSrc gs, const int32_t* __restrict__ scope_var,
+                                   const uint8_t* __restrict__ maskT, int64_t mask_ld,
+                                   float* __restrict__ dint, int64_t B, int K) {
+  __shared__ float red[8][33];
+  const int f = blockIdx.x;
+  const int var = scope_var[f];
+  const int lane = threadIdx.x, slice = threadIdx.y;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    float a = 0.f;
+    if (k < K)
+      for (int64_t b = slice; b < B; b += 8)
+        if (read_mask(maskT, mask_ld, var, b)) a += pull_grad(gs, f, b, K, k);
+    red[slice][lane] = a;
+    __syncthreads();
+    if (slice == 0 && k < K) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += red[j][lane];
+      dint[(int64_t)f * K + k] = s;
+    }
+    __syncthreads();
+  }
+}
+
 static int table_bwd_nt(int K) { return K <= 32 ? 1 : (K <= 64 ? 2 : 4); }
 
 static void table_bwd_config(const ckb_step_desc_t& d, int64_t B, int& splits, int64_t& chunk) {
@@ -309,6 +337,18 @@ size_t table_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
 
 int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   float* dT = c.grads[d.slot[0]];
+  if (d.int_slot >= 0 && c.grads[d.int_slot] != nullptr) {
+    float* dint = c.grads[d.int_slot];
+    if (c.maskT == nullptr) {
+      CKB_CUDA_CHECK(cudaMemsetAsync(dint, 0, (size_t)d.num_folds * d.k_out * 4, c.stream));
+    } else {
+      GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
+      masked_gsum_kernel<<<d.num_folds, dim3(32, 8), 0, c.stream>>>(gs, d.scope_var, c.maskT,
+                                                                   c.mask_ld, dint, c.B, d.k_out);
+      CKB_LAUNCH_CHECK();
+      c.launches++;
+    }
+  }
   if (dT == nullptr) return CKB_OK;
   int splits;
   int64_t chunk;

@@ -178,6 +178,18 @@ __global__ void lse_rows_kernel(const float* __restrict__ src, float* __restrict
     if (lane == 0) dst[r] = m + logf(z);
   }
 }
+// d/dsrc of logsumexp: softmax(src) * g, ADDED to dsrc (the same logits also feed the table op,
+// whose backward has already written dsrc when this one runs)
+__global__ void lse_rows_bwd_kernel(const float* __restrict__ src, const float* __restrict__ lse,
+                                    const float* __restrict__ g, float* __restrict__ dsrc,
+                                    int64_t rows, int cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    dsrc[i] += g[r] * expf(src[i] - lse[r]);
+  }
+}
 
 // ---- all softmax ops of a plan in one launch ------------------------------------------------
 // Every sum layer re-normalises its weights each step (TorchSoftmaxParameter, nodes.py:764-772);
@@ -389,7 +401,8 @@ int param_op_fwd(const ckb_param_op_t& op, Ctx& c) {
 int param_op_bwd(const ckb_param_op_t& op, Ctx& c) {
   float* dsrc = c.grads[op.src];
   const float* g = c.grads[op.dst];
-  if (dsrc == nullptr || op.kind == CKB_POP_LSE_ROWS) return CKB_OK;
+  if (dsrc == nullptr) return CKB_OK;
+  if (op.kind == CKB_POP_LSE_ROWS && g == nullptr) return CKB_OK;  // value used, gradient not wanted
   if (g == nullptr) {
     set_error("parameter op %d: gradient of slot %d requested but slot %d has none", op.kind,
               op.src, op.dst);
@@ -419,6 +432,9 @@ int param_op_bwd(const ckb_param_op_t& op, Ctx& c) {
       break;
     case CKB_POP_LOG:
       log_bwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, g, dsrc, n);
+      break;
+    case CKB_POP_LSE_ROWS:
+      lse_rows_bwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, dst, g, dsrc, op.rows, op.cols);
       break;
     default:
       set_error("unknown parameter op %d", op.kind);

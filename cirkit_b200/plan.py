@@ -343,7 +343,7 @@ class CircuitPlan:
                 if p.leaf >= 0:
                     resize_leaf(p.leaf, p.ops, shape)
             steps.append(dataclasses.replace(s, num_input_units=ki, num_output_units=ko, params=params))
-        leaves = [LeafSpec(tuple(leaf_shapes.get(i, l.shape)), l.init, l.requires_grad, l.name)
+        leaves = [dataclasses.replace(l, shape=tuple(leaf_shapes.get(i, l.shape)))
                   for i, l in enumerate(self.leaves)]
         meta = dict(self.meta)
         meta["units"] = k

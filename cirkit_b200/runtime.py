@@ -256,7 +256,10 @@ class _DeviceState:
     def grad_buffer(self, slot: int) -> Tensor:
         g = self.eff_grad.get(slot)
         if g is None:
-            g = self.eff_grad[slot] = torch.empty_like(self.eff[slot])
+            like = self.eff.get(slot)
+            if like is None:  # an integrate-value buffer
+                like = next(b for sid, b in self.int_buf.items() if self.rt.int_slots[sid] == slot)
+            g = self.eff_grad[slot] = torch.empty_like(like)
         return g
 
     def handle(self, which: str) -> C.c_void_p:
@@ -288,14 +291,20 @@ class _DeviceState:
             d.int_slot = rt.int_slots.get(es.sids[0], -1) if es.kind != STEP_TABLE_DENSE else -1
             cp = lay.cons_ptr[es.out_sid]
             d.max_consumers = int(np.max(np.diff(cp))) if len(cp) > 1 else 0
-        ops = (L.ParamOp * max(1, len(rt.native_ops)))()
-        for i, (b, (kind, rows, cols, aux, a, bb)) in enumerate(rt.native_ops):
-            ops[i].kind, ops[i].src, ops[i].dst = kind, b.src_slot, b.dst_slot
+        # the logsumexp ops come first: the backward pass runs the ops in reverse, and theirs ADDS
+        # to the logits gradient the table op has written by then
+        op_list = [(L.POP_LSE_ROWS, src, dst, rows, cols, 0, 0.0, 0.0)
+                   for src, dst, rows, cols in (rt.lse_ops if which == "masked" else [])]
+        op_list += [(kind, b.src_slot, b.dst_slot, rows, cols, aux, a, bb)
+                    for b, (kind, rows, cols, aux, a, bb) in rt.native_ops]
+        ops = (L.ParamOp * max(1, len(op_list)))()
+        for i, (kind, src, dst, rows, cols, aux, a, bb) in enumerate(op_list):
+            ops[i].kind, ops[i].src, ops[i].dst = kind, src, dst
             ops[i].rows, ops[i].cols, ops[i].aux, ops[i].a, ops[i].b = rows, cols, aux, a, bb
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(
-                self.lib.ckb_plan_create(descs, len(steps), ops, len(rt.native_ops), rt.n_slots, C.byref(h)),
+                self.lib.ckb_plan_create(descs, len(steps), ops, len(op_list), rt.n_slots, C.byref(h)),
                 "ckb_plan_create",
             )
         self.handles[which] = h
@@ -326,6 +335,7 @@ class PlanRuntime:
         self.step_slots: list[list[int]] = []
         self.int_slots: dict[int, int] = {}
         self.int_buf_sids: list[int] = []  # steps whose integrate values live in a runtime buffer
+        self.lse_ops: list[tuple] = []  # (src slot, dst slot, rows, cols) of CKB_POP_LSE_ROWS ops
         n = 0
         for sid, s in enumerate(plan.steps):
             slots = []
@@ -345,9 +355,14 @@ class PlanRuntime:
                 self.bindings.append(b)
                 slots.append(b.dst_slot)
             self.step_slots.append(slots)
-            if s.kind == "categorical" and "logits" in s.params:
-                self.int_slots[sid] = n  # logsumexp(logits): what integrating the variable yields
+            if s.kind == "categorical" and "logits" in s.params and b.native[0] == L.POP_COPY_T:
+                # unnormalised logits: integrating the variable yields logsumexp(logits)
+                # (layers/input.py:414-421), a parameter op of the masked plan (normalised
+                # logits integrate to log 1 = 0, the kernels' default)
+                self.int_slots[sid] = n
                 self.int_buf_sids.append(sid)
+                K, V = b.src_shape[1], b.src_shape[2]
+                self.lse_ops.append((b.src_slot, n, s.num_folds * K, V))
                 n += 1
             if s.kind == "gaussian" and "log_partition" in s.params:
                 self.int_slots[sid] = slots[2]
@@ -381,7 +396,8 @@ class PlanRuntime:
                                       scratch=(t2, (c.num_folds, V, c.num_output_units))))
             else:
                 fused.append(plain[sid])
-        self.exec_plans = {"plain": plain, "fused": fused}
+        # "masked": the plain step list plus the logsumexp ops of unnormalised categoricals
+        self.exec_plans = {"plain": plain, "fused": fused, "masked": plain}
         self.n_slots = n
         self.native_ops = [(b, b.native) for b in self.bindings if b.native is not None]
         self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
@@ -399,7 +415,9 @@ class PlanRuntime:
         return self.last_arena[off : off + n].view(s.num_folds, batch, s.num_output_units)
 
     def choose_plan(self, batch: int, masked: bool) -> str:
-        if self.table_pairs and not masked and 2 * batch >= self.table_states:
+        if masked:
+            return "masked" if self.lse_ops else "plain"
+        if self.table_pairs and 2 * batch >= self.table_states:
             return "fused"
         return "plain"
 
@@ -467,6 +485,18 @@ class PlanRuntime:
                 f"the circuit reads variable {self.plan.num_variables - 1} but the input has "
                 f"{x.shape[1]} columns"
             )
+        if integrate_mask is not None:
+            # TorchInputLayer.integrate raises for layers that cannot be integrated
+            # (layers/input.py:82-92: Embedding), and IntegrateQuery._layer_fn calls it only when
+            # one of the layer's variables is actually masked (queries.py:136-139)
+            m = integrate_mask if integrate_mask.ndim == 2 else integrate_mask.unsqueeze(0)
+            for sid, s in enumerate(self.plan.steps):
+                if s.kind == "embedding" and m.shape[1] > int(s.scope_idx.max()):
+                    cols = torch.as_tensor(s.scope_idx, dtype=torch.int64, device=m.device)
+                    if bool(m[:, cols].any()):
+                        raise TypeError(
+                            f"Integration is not supported for layers of type embedding (step {sid})"
+                        )
         P = self.parameter_tensors(leaves, externals)
         if not P:
             raise ValueError("circuit without parameters")
@@ -525,13 +555,6 @@ def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Cal
             lib.ckb_transpose_mask(m.data_ptr(), mask_rows, plan.num_variables, maskT.data_ptr(), stream),
             "ckb_transpose_mask",
         )
-        # values an integrated variable contributes for unnormalised categoricals
-        for sid, buf in st.int_buf.items():
-            i = next(j for j, bb in enumerate(rt.bindings) if bb.sid == sid and bb.name == "logits")
-            if rt.bindings[i].native[0] == L.POP_LOG_SOFTMAX_T:
-                buf.zero_()  # normalised logits integrate to log 1
-            else:
-                buf.copy_(torch.logsumexp(P[i].detach(), dim=2))
     which = rt.choose_plan(B, mask is not None)
     tensors = (C.c_void_p * rt.n_slots)()
     for b, p in zip(rt.bindings, P):
@@ -563,6 +586,12 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
         grads[b.src_slot] = g.data_ptr()
         if b.native is not None:
             grads[b.dst_slot] = st.grad_buffer(b.dst_slot).data_ptr()
+    if call.which == "masked":
+        # d(loss)/d(logsumexp(logits)) of the integrated variables: written by the table backward,
+        # consumed by the CKB_POP_LSE_ROWS backward
+        for src, dst, _, _ in rt.lse_ops:
+            if grads[src]:
+                grads[dst] = st.grad_buffer(dst).data_ptr()
     for es in rt.exec_plans[call.which]:
         if es.scratch is not None:
             grads[es.scratch[0]] = st.grad_buffer(es.scratch[0]).data_ptr()

@@ -98,7 +98,9 @@ typedef enum {
   CKB_POP_COPY_T = 3,        /* transpose only                                                 */
   CKB_POP_SCALED_SIGMOID = 4,/* nodes.py:682-699: sigmoid(x)*(b-a)+a, elementwise              */
   CKB_POP_LOG = 5,           /* elementwise log                                                */
-  CKB_POP_LSE_ROWS = 6       /* logsumexp over the last axis: (rows, cols) -> (rows); no backward */
+  CKB_POP_LSE_ROWS = 6       /* logsumexp over the last axis: (rows, cols) -> (rows): the value an
+                                integrated variable of an unnormalised Categorical yields
+                                (layers/input.py:414-421); backward ADDS softmax * g to d(src) */
 } ckb_param_op_kind;
 
 typedef struct {

@@ -48,6 +48,7 @@ from cirkit_b200.adapter import plan_from_torch  # noqa: E402
 from cirkit_b200.plan import seeded_leaves  # noqa: E402
 
 PROBE = 64  # gradient entries kept per leaf in seeded fixtures
+FULL_GRAD_MAX = 1 << 17  # leaves up to this many elements keep their whole float64 gradient
 
 
 def compile_ref(sc, fold=True, optimize=True, semiring="lse-sum"):
@@ -72,7 +73,12 @@ def ref_forward_backward(tc, leaves, x):
     ]
 
 
+NAMES: set | None = None  # --names filter: fixtures to (re)write
+
+
 def write_full(name, tc, x, *, masks=None, extra=None, kind="full"):
+    if NAMES is not None and name not in NAMES:
+        return
     low = plan_from_torch(tc, allow_external_params=False, semirings=("lse-sum", "complex-lse-sum"))
     y, grads = ref_forward_backward(tc, low.leaves, x)
     out = {"plan": plan_array(low.plan), "x": x.numpy(), "y": y.numpy()}
@@ -81,9 +87,17 @@ def write_full(name, tc, x, *, masks=None, extra=None, kind="full"):
         out[f"grad_{i}"] = g.numpy()
     if masks is not None:
         q = IntegrateQuery(tc)
-        with torch.no_grad():
-            out["mask"] = masks.numpy()
-            out["y_mask"] = q(x, integrate_vars=masks).numpy()
+        out["mask"] = masks.numpy()
+        for p in low.leaves:
+            p.grad = None
+        with torch.enable_grad():
+            ym = q(x, integrate_vars=masks)
+            (-ym.mean()).backward()
+        out["y_mask"] = ym.detach().numpy()
+        # gradient of the marginal log-likelihood (reference: autograd through
+        # torch.where(mask, layer.integrate(), output), queries.py:132-143)
+        for i, p in enumerate(low.leaves):
+            out[f"grad_mask_{i}"] = (torch.zeros_like(p) if p.grad is None else p.grad.detach().clone()).numpy()
     meta = {"kind": kind, "steps": [s.kind for s in low.plan.steps]}
     meta.update(extra or {})
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
@@ -92,6 +106,8 @@ def write_full(name, tc, x, *, masks=None, extra=None, kind="full"):
 
 
 def write_seeded(name, tc, x, seed, extra=None):
+    if NAMES is not None and name not in NAMES:
+        return
     low = plan_from_torch(tc, allow_external_params=False)
     vals = seeded_leaves(low.plan, seed)
     with torch.no_grad():
@@ -106,6 +122,9 @@ def write_seeded(name, tc, x, seed, extra=None):
         out[f"gsum_{i}"] = np.array([flat.sum().item(), flat.abs().sum().item(), flat.abs().max().item()])
         out[f"gidx_{i}"] = idx.numpy()
         out[f"gval_{i}"] = flat[idx].numpy()
+        if flat.numel() <= FULL_GRAD_MAX:
+            # the small (top-of-the-tree) weight tensors are compared densely on the GPU
+            out[f"gfull_{i}"] = g.numpy()
     meta = {"kind": "seeded", "seed": seed, "steps": [s.kind for s in low.plan.steps]}
     meta.update(extra or {})
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
@@ -228,7 +247,15 @@ def case_random_small():
                  in_layers={h1: ins[:2], h2: ins[2:], s1: [h1], s2: [h2], h3: [s1, s2], s3: [h3]},
                  outputs=[s3])
     _, tc = compile_ref(sc)
-    write_full("cat_logits_k3", tc, torch.randint(0, 5, (B, 4)))
+    xl = torch.randint(0, 5, (B, 4))
+    write_full("cat_logits_k3", tc, xl)
+    # Marginals of unnormalised categoricals: integrating a variable yields logsumexp(logits)
+    # (layers/input.py:414-421).  The reference returns that as (F, K) instead of (F, 1, K), so
+    # its IntegrateQuery (queries.py:143, torch.where) only broadcasts correctly when every
+    # Categorical layer has ONE fold -- i.e. for the un-folded circuit, which is what this fixture
+    # is generated from (a folded circuit raises "size of tensor a must match ..." there).
+    _, tcu = compile_ref(sc, fold=False)
+    write_full("cat_logits_k3_unfolded", tcu, xl, masks=torch.rand(B, 4) < 0.4)
 
 
 def case_bench():
@@ -299,7 +326,10 @@ CASES = {
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--names", nargs="*", default=None, help="write only these fixtures")
     args = ap.parse_args()
+    if args.names:
+        NAMES = set(args.names)
     torch.set_default_dtype(torch.float64)
     torch.manual_seed(42)
     np.random.seed(42)

@@ -41,6 +41,16 @@ class Golden:
     def grads(self) -> list[torch.Tensor]:
         return [torch.from_numpy(self.z[f"grad_{i}"]) for i in range(len(self.plan.leaves))]
 
+    def grads_mask(self) -> list[torch.Tensor] | None:
+        """Gradients of -mean(IntegrateQuery output) the reference's autograd produced."""
+        if "grad_mask_0" not in self.z:
+            return None
+        return [torch.from_numpy(self.z[f"grad_mask_{i}"]) for i in range(len(self.plan.leaves))]
+
+    def grad_full(self, i: int) -> torch.Tensor | None:
+        """Whole float64 gradient of leaf i (seeded fixtures keep it for the small leaves)."""
+        return torch.from_numpy(self.z[f"gfull_{i}"]) if f"gfull_{i}" in self.z else None
+
     def mask(self):
         if "mask" not in self.z:
             return None, None

@@ -1,0 +1,187 @@
+"""The drop-in routes ON THE GPU, against the unmodified reference.
+
+The reference is a pure-Python package: `baseline/_ref/` holds an install of it
+(`pip install --no-index --no-deps --target baseline/_ref`, git-ignored, shipped to the GPU box by
+gpurun), so these tests compile the same symbolic circuit twice -- `PipelineContext(backend="b200")`
+and `PipelineContext(backend="torch")` in float64 on the CPU -- and compare values, gradients and the
+reference's own `IntegrateQuery`.  Nothing here reads /root/reference."""
+import os
+import sys
+
+import pytest
+import torch
+
+from helpers import grad_tolerance
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def cirkit():
+    if not os.path.isdir(os.path.join(REF, "cirkit")):
+        pytest.skip("baseline/_ref (reference install) not present")
+    if REF not in sys.path:
+        sys.path.insert(1, REF)
+    import cirkit
+
+    import cirkit_b200
+
+    cirkit_b200.register_backend()
+    return cirkit
+
+
+def _image(K=8, rg="quad-graph", spl="cp", shape=(1, 6, 6), **kw):
+    from cirkit.templates import data_modalities, utils
+
+    return data_modalities.image_data(
+        shape, region_graph=rg, input_layer="categorical", num_input_units=K,
+        sum_product_layer=spl, num_sum_units=K,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"), **kw)
+
+
+def _compile_pair(sc, dev, **flags):
+    """(b200 circuit on the GPU in fp32, reference circuit on the CPU in fp64), same parameters."""
+    from cirkit.pipeline import PipelineContext
+
+    torch.manual_seed(3)
+    ctx = PipelineContext(backend="b200", semiring="lse-sum", **flags)
+    cc = ctx.compile(sc)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        rctx = PipelineContext(backend="torch", semiring="lse-sum", **flags)
+        ref = rctx.compile(sc)
+    finally:
+        torch.set_default_dtype(prev)
+    ref.load_state_dict({k: v.double() for k, v in cc.state_dict().items()})
+    return ctx, cc.to(dev), rctx, ref
+
+
+def _close(y, yr):
+    y = y.detach().double().cpu()
+    assert y.shape == yr.shape
+    err = (y - yr.detach()).abs()
+    assert bool((err <= 5e-7 * yr.detach().abs() + 1e-5).all()), f"max err {err.max().item():.3e}"
+
+
+@pytest.mark.parametrize("rg,spl,K,flags", [
+    ("quad-graph", "cp", 8, dict(fold=True, optimize=True)),
+    ("quad-tree-2", "cp", 64, dict(fold=True, optimize=True)),
+    ("quad-tree-2", "tucker", 4, dict(fold=True, optimize=True)),
+    ("quad-tree-2", "cp-t", 5, dict(fold=True, optimize=False)),
+    ("poon-domingos", "cp", 3, dict(fold=False, optimize=False)),
+])
+def test_backend_b200_matches_backend_torch(cirkit, dev, rg, spl, K, flags):
+    """Route A: PipelineContext(backend="b200") -> .to("cuda") -> cc(x) vs backend="torch" fp64:
+    forward, gradients of every parameter, and the reference's IntegrateQuery class."""
+    from cirkit.backend.torch.queries import IntegrateQuery
+
+    sc = _image(K, rg, spl)
+    ctx, cc, rctx, ref = _compile_pair(sc, dev, **flags)
+    assert type(cc).__name__ == "B200TorchCircuit", getattr(cc, "_b200_reason", "")
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 256, (150, 36), generator=gen)
+    y = cc(x.to(dev))
+    yr = ref(x)
+    _close(y, yr)
+    (-y.mean()).backward()
+    (-yr.mean()).backward()
+    ref_grads = dict(ref.named_parameters())
+    n = 0
+    for name, p in cc.named_parameters():
+        gr = ref_grads[name].grad
+        if gr is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        err = (p.grad.double().cpu() - gr).abs().max().item()
+        tol = grad_tolerance(gr, ll_max=float(yr.detach().abs().max()))
+        assert err <= tol, f"{name}: {err:.3e} > {tol:.3e}"
+        n += 1
+    assert n > 0
+    # the reference's own query class drives the accelerated circuit (queries.py:48-109)
+    mask = torch.rand(150, 36, generator=gen) < 0.3
+    with torch.no_grad():
+        ym = IntegrateQuery(cc)(x.to(dev), integrate_vars=mask.to(dev))
+        ymr = IntegrateQuery(ref)(x, integrate_vars=mask)
+    _close(ym, ymr)
+    # an optimiser step on the shared leaves moves both executors the same way
+    opt = torch.optim.SGD(cc.parameters(), lr=0.1)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    opt.step()
+    ropt.step()
+    with torch.no_grad():
+        _close(cc(x.to(dev)), ref(x))
+
+
+def test_integrate_circuit_shares_parameters(cirkit, dev):
+    """ctx.integrate(cc) (pipeline.py:168-229): the partition-function circuit is compiled by the
+    same backend, evaluates on the GPU without input, and sees c's parameters through pointer
+    nodes (rules/parameters.py:111-117): after a parameter update both change consistently."""
+    import cirkit.symbolic.functional as SF
+    from cirkit.pipeline import PipelineContext
+
+    from cirkit.templates import data_modalities, utils
+
+    sc = data_modalities.image_data(
+        (1, 4, 4), region_graph="quad-tree-2", input_layer="categorical", num_input_units=4,
+        sum_product_layer="cp", num_sum_units=4, input_params={
+            "logits": utils.Parameterization(initialization="normal")},
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+    ctx, cc, rctx, ref = _compile_pair(sc, dev, fold=True, optimize=True)
+    zc = ctx.compile(SF.integrate(sc)).to(dev)
+    zr = rctx.compile(SF.integrate(sc))
+    assert type(zc).__name__ == "B200TorchCircuit", getattr(zc, "_b200_reason", "")
+    with torch.no_grad():
+        z = zc()
+        _close(z, zr())
+        # normalisation: sum over a tiny domain is intractable here, but log Z must move with the
+        # shared logits
+        for p in cc.parameters():
+            p.add_(0.25)
+        for p in ref.parameters():
+            p.add_(0.25)
+        z2 = zc()
+        _close(z2, zr())
+        assert not torch.equal(z, z2)
+
+
+def test_from_torch_standalone(cirkit, dev):
+    """Route B: B200Circuit.from_torch(tc) holds the reference circuit's own parameters."""
+    from cirkit.pipeline import PipelineContext
+
+    from cirkit_b200 import B200Circuit
+
+    sc = _image(8, "quad-tree-2")
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    cc = B200Circuit.from_torch(tc, share_parameters=False).to(dev)
+    x = torch.randint(0, 256, (64, 36), generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        y = cc(x.to(dev))
+        yr = tc(x)  # the reference in fp32 on the CPU
+    assert (y.cpu() - yr).abs().max().item() <= 5e-6 * yr.abs().max().item() + 1e-4  # fp32 vs fp32
+
+
+def test_unsupported_layers_stay_on_the_reference_backend(cirkit, dev):
+    """A circuit with a layer kind the runtime has no kernel for is left untouched by
+    backend="b200" (accelerate(strict=False)): it evaluates through the reference's PyTorch ops on
+    the GPU, never through a silent CPU path of this package."""
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    sc = data_modalities.image_data(
+        (1, 4, 4), region_graph="quad-tree-2", input_layer="binomial", num_input_units=3,
+        sum_product_layer="cp", num_sum_units=3,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+    ctx = PipelineContext(backend="b200", semiring="lse-sum", fold=True, optimize=True)
+    cc = ctx.compile(sc).to(dev)
+    x = torch.randint(0, 256, (8, 16)).to(dev)
+    y = cc(x)
+    assert y.shape == (8, 1, 1) and y.is_cuda and torch.isfinite(y).all()

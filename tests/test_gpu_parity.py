@@ -112,6 +112,7 @@ def test_benchmark_circuits_vs_reference(name, dev):
     _check_forward(y, g.y())
     (-y.mean()).backward()
     ll_max = float(g.y().abs().max())
+    dense = 0
     for i, p in enumerate(cc.leaves):
         flat = p.grad.double().cpu().reshape(-1)
         gsum, gabs, gmax = g.z[f"gsum_{i}"]
@@ -131,6 +132,14 @@ def test_benchmark_circuits_vs_reference(name, dev):
         got_abs = flat.abs().sum().item()
         floor = min(max(5e-7, tol), 5e-6)
         assert abs(got_abs - gabs) <= 2e-3 * gabs + flat.numel() * floor, f"leaf {i} abs-sum {got_abs} vs {gabs}"
+        # the small weight tensors (top levels of the tree, up to 2^17 elements) are compared
+        # DENSELY with the reference's float64 gradient, element by element
+        full = g.grad_full(i)
+        if full is not None:
+            dense += 1
+            err = (p.grad.double().cpu() - full).abs().max().item()
+            assert err <= tol, f"leaf {i} dense: {err:.3e} > {tol:.3e}"
+    assert dense >= 1, "seeded fixtures carry the full gradients of their small leaves"
 
 
 @pytest.mark.parametrize("name", ["qt8_cp_k4", "qg8_cp_k4", "qt8_tucker_k4", "rbt12_gaussian_k5"])
