@@ -18,6 +18,7 @@ struct DenseArgs {
   float* dWp;   // [splits][F][Ko][Kred] or nullptr
   int64_t chunk;
   int max_cons;  // largest number of consumer rows any fold sums (1 in a tree)
+  int rows64;    // every gathered / consumer row offset is a multiple of 64 floats (CKB_STEP_ROWS64)
 };
 
 __device__ __forceinline__ const float* in_row(const DenseArgs& a, int f, int h) {
@@ -50,6 +51,11 @@ __device__ __forceinline__ float load_u(const DenseArgs& a, const float* const* 
 int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c);
 int dense_tc_bwd(const DenseArgs& a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes);
 size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B);
+
+// TMA-fed backward for Ki = Ko = 64 (dense_tc_bwd3.cu)
+bool dense_tc_bwd3_ok(const DenseArgs& a, int rows64);
+size_t dense_tc_bwd3_ws(int F, int64_t B);
+int dense_tc_bwd3(const DenseArgs& a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes);
 
 // Ki = Ko = 128 forward on tcgen05 (dense128_tc.cu): EXPERIMENTAL, opt-in (CKB_OPT_TC_FAST_MATH bit 9)
 int tc_flags();  // CKB_OPT_TC_FAST_MATH bits (dense_tc.cu)

@@ -720,6 +720,7 @@ int dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
   a.gin = c.garena + c.B * d.gin_off;
   a.max_cons = d.max_consumers;
+  a.rows64 = (d.flags & CKB_STEP_ROWS64) ? 1 : 0;
   return run_dense_bwd(a, d.num_folds, c.grads[d.slot[0]], c, c.ws, c.ws_bytes);
 }
 
@@ -858,6 +859,7 @@ int table_dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
   a.gs = GradSrc{dT2, nullptr, nullptr, (int64_t)d.num_states};
   a.gin = dT;
   a.max_cons = 1;
+  a.rows64 = 1;  // tables are dense (F, V, K) blocks
   const size_t off = (table_bwd_ws(as_table(d), c.B) + 255) & ~(size_t)255;
   return run_dense_bwd(a, d.num_folds, c.grads[d.slot[1]], c, c.ws + off,
                        c.ws_bytes > off ? c.ws_bytes - off : 0);

@@ -696,6 +696,419 @@ dense_tc_bwd_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
 #undef DBG
 }
 
+
+// ==========================================================================================
+// Backward, second version (round 2).  What the B200 probes of round 2 established
+// (scripts/micro/mn_major_probe.cu, umma_probe2.cu, tmem_shape_probe.cu):
+//   * kind::tf32 accepts MN-major A and B operands with the SWIZZLE_128B_BASE32B layout (rows of
+//     128 bytes per k, 32-byte chunks xor (k & 3)), so GEMM 2 (dW = r^T e, contraction over the
+//     samples) reads r and e as plain [sample][unit] rows: no register transposes;
+//   * K-major operands do NOT accept that layout, so GEMM 1 (T = r W, contraction over the units)
+//     cannot share the image: its A operand r goes to TENSOR MEMORY instead (tcgen05.st, TS-form
+//     MMA), which also takes 128 KB of operand traffic per tile off the shared-memory port;
+//   * the 16x256b shape of tcgen05.ld/st is the mma C-fragment mapping: thread t of a warp owns
+//     rows t/4 and t/4+8 of a 16-row slab and, in every group of 8 columns, columns 2(t%4), +1.
+// One thread <-> element ownership therefore serves everything: 8-byte global loads (a warp
+// instruction covers 8 rows x 32 bytes = whole sectors), r -> TMEM, r and e -> the MN-major images
+// (conflict-free 8-byte stores), the read-back of T, and the du stores (whole sectors again) --
+// e never leaves the registers between the transform and the epilogue, and du is not staged.
+//   warp w: TMEM quadrant q = w & 3 (rows 32q..), rows +16 * ((w >> 2) & 1), columns 32 * (w >> 3);
+//   the two warps that share rows (w, w ^ 8) exchange their half-row maxima through shared memory.
+// ==========================================================================================
+struct __align__(1024) Bwd2Smem {
+  float r_mn[4][TM * 32];  // [r_hi units 0..31 | r_hi 32..63 | r_lo 0..31 | r_lo 32..63][sample][32]  64 KB
+  float e_mn[4][TM * 32];  // same for e                                                            64 KB
+  float w[2][128 * 32];    // W^T: [o-block][hi i 0..63 | lo i 0..63][32 o's]   GEMM 1 B             32 KB
+  float mbuf[2][2][TM];    // [tile parity][column half][row]: half-row maxima
+  uint64_t ab_full, ab_empty, d1_full, d2_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream2_if(const float* p, bool ok) {
+  float2 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];\n\t}"
+      : "=&f"(v.x), "=&f"(v.y)
+      : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+// 16 TMEM lanes x 32 columns <-> 16 registers per thread: reg 4n + 2a + c = (row t/4 + 8a,
+// column 8n + 2(t%4) + c)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+      "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+
+// a thread's share of a tile: [row a][column group n] pairs of consecutive columns
+struct Bwd2Loads {
+  float2 x0[2][4], x1[2][4], y[2][4], g[2][4];
+};
+struct Bwd2Stream {
+  const float *x0, *x1, *y, *g;  // first element of the thread's share of the NEXT tile to load
+  int64_t rows_left;             // B - (row a = 0 of that tile)
+};
+// MODE 2: the tile is complete, 1: rows must be checked
+template <int MODE>
+__device__ __forceinline__ void bwd2_load(Bwd2Loads& L, const Bwd2Stream& st) {
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const bool ok = MODE == 2 || st.rows_left > 8 * a;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int o = a * 8 * KK + 8 * n;
+      if (MODE == 2) {
+        L.x0[a][n] = ldg_stream2(st.x0 + o);
+        if (st.x1) L.x1[a][n] = ldg_stream2(st.x1 + o);
+        L.y[a][n] = ldg_stream2(st.y + o);
+        if (st.g) L.g[a][n] = ldg_stream2(st.g + o);
+      } else {
+        L.x0[a][n] = ldg_stream2_if(st.x0 + o, ok);
+        L.x1[a][n] = ldg_stream2_if(st.x1 + o, ok && st.x1 != nullptr);
+        L.y[a][n] = ldg_stream2_if(st.y + o, ok);
+        L.g[a][n] = ldg_stream2_if(st.g + o, ok && st.g != nullptr);
+      }
+    }
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+dense_tc_bwd2_kernel(DenseArgs a, int tiles_per_cta, int want_dw, int flags) {
+  extern __shared__ uint8_t smem_raw[];
+  Bwd2Smem& s = *reinterpret_cast<Bwd2Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int n_tiles_total = (int)((a.B + TM - 1) / TM);
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
+  if (n_tiles <= 0) return;
+#ifdef CKB_TIMELINE
+  // timeline of warps 0 and 9 of CTA (0, gridDim.y / 2): clock64() at the phase boundaries
+  const bool dbg = (flags & 128) && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && (tid & 31) == 0 &&
+                   ((tid >> 5) == 0 || (tid >> 5) == 9);
+  const int dbg_base = (tid >> 5) == 0 ? 16 : 272;
+#define DBG2(it, slot) do { if (dbg && (it) < 15) g_dbg[dbg_base + (it) * 16 + (slot)] = clock64(); } while (0)
+  if (dbg && (tid >> 5) == 0) g_dbg[0] = clock64();
+#else
+#define DBG2(it, slot) do { } while (0)
+#endif
+
+  const float* row0 = in_row(a, f, 0);
+  const float* row1 = a.H == 2 ? in_row(a, f, 1) : nullptr;
+  const float* yrow = a.y + (int64_t)f * a.B * KK;
+  const float* grow0 = nullptr;
+  int n_cons = 1, cons0 = 0;
+  if (a.gs.cons_ptr == nullptr) {
+    grow0 = a.gs.garena + (int64_t)f * a.gs.B * KK;
+  } else {
+    cons0 = a.gs.cons_ptr[f];
+    n_cons = a.gs.cons_ptr[f + 1] - cons0;
+    if (n_cons > 0) grow0 = a.gs.garena + a.gs.B * a.gs.cons_rows[cons0];
+  }
+
+  if (tid == 0) {
+    mbar_init(&s.ab_full, kWorkers);
+    mbar_init(&s.ab_empty, 1);  // GEMM 2 has finished reading the shared-memory images
+    mbar_init(&s.d1_full, 1);
+    mbar_init(&s.d2_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
+  stage_weights<true, kBwdThreads>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+  // TMEM columns: D1 [0,128) (main | correction), D2 [128,256), r_hi [256,320), r_lo [320,384)
+  constexpr uint32_t kD2Col = 128, kRhiCol = 256, kRloCol = 320;
+
+  const int q = warp & 3, half = (warp >> 2) & 1, chalf = warp >> 3;
+  const int r8 = lane >> 2, c2 = lane & 3;
+  const int trow = q * 32 + half * 16 + r8;  // row a = 0 inside the tile; a = 1 adds 8
+  const uint32_t lane_addr = (uint32_t)(q * 32 + half * 16) << 16;
+  const uint32_t mn_base = smem_u32(s.r_mn);
+  constexpr uint32_t kEmn = offsetof(Bwd2Smem, e_mn) - offsetof(Bwd2Smem, r_mn);
+  constexpr uint32_t kLo = 2 * TM * 128;  // hi -> lo inside an image
+  // byte offset of (row a, column group n) of this thread inside an MN-major image:
+  //   atom chalf, row * 128, 32-byte chunk n ^ (row & 3), 8 bytes per thread
+  uint32_t mn_off[2];
+#pragma unroll
+  for (int aa = 0; aa < 2; ++aa) mn_off[aa] = (uint32_t)chalf * (TM * 128) + (uint32_t)(trow + 8 * aa) * 128u + c2 * 8u;
+  const uint32_t rsw = (uint32_t)(trow & 3);  // (row & 3) is the same for a = 0 and a = 1
+
+  Bwd2Stream st;
+  {
+    const int64_t row = (int64_t)t_begin * TM + trow;
+    const int64_t e0 = row * KK + 32 * chalf + 2 * c2;
+    st.x0 = row0 + e0;
+    st.x1 = row1 ? row1 + e0 : nullptr;
+    st.y = yrow + e0;
+    st.g = n_cons > 0 ? grow0 + e0 : nullptr;
+    st.rows_left = a.B - row;
+  }
+  auto advance = [&]() {
+    st.x0 += TM * KK;
+    if (st.x1) st.x1 += TM * KK;
+    st.y += TM * KK;
+    if (st.g) st.g += TM * KK;
+    st.rows_left -= TM;
+  };
+  float* pdu = a.gin + ((int64_t)f * a.B + (int64_t)t_begin * TM + trow) * KK + 32 * chalf + 2 * c2;
+  int64_t du_left = a.B - ((int64_t)t_begin * TM + trow);
+
+  Bwd2Loads L;
+#pragma unroll
+  for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) L.x0[aa][n] = L.x1[aa][n] = L.y[aa][n] = L.g[aa][n] = make_float2(0.f, 0.f);
+  bwd2_load<1>(L, st);
+  advance();
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int64_t b0 = (int64_t)(t_begin + it) * TM;
+    DBG2(it, 0);
+    if (n_cons > 1) {  // rare (DAG-shaped circuits): add the other consumers' rows to g
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa) {
+        const int64_t b = b0 + trow + 8 * aa;
+        for (int c = 1; c < n_cons; ++c) {
+          const float* gr = a.gs.garena + a.gs.B * a.gs.cons_rows[cons0 + c] + b * KK + 32 * chalf + 2 * c2;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float2 z = ldg_stream2_if(gr + 8 * n, b < a.B);
+            L.g[aa][n].x += z.x; L.g[aa][n].y += z.y;
+          }
+        }
+      }
+    }
+    // ---- transform: u, row max (exchanged with the warp that holds the other 32 columns), e, r
+    float e[2][4][2];  // stays in registers until the du epilogue
+    float rr[2][4][2];
+    {
+      float mloc[2];
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          e[aa][n][0] = L.x0[aa][n].x + L.x1[aa][n].x;
+          e[aa][n][1] = L.x0[aa][n].y + L.x1[aa][n].y;
+          m = fmaxf(m, fmaxf(e[aa][n][0], e[aa][n][1]));
+        }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        mloc[aa] = m;
+        if (c2 == 0) s.mbuf[it & 1][chalf][trow + 8 * aa] = m;
+      }
+      DBG2(it, 1);
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 7)) : "memory");
+      DBG2(it, 2);
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa) {
+        const float m = clamp_max(fmaxf(mloc[aa], s.mbuf[it & 1][chalf ^ 1][trow + 8 * aa]));
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const float ux = e[aa][n][0], uy = e[aa][n][1];
+          e[aa][n][0] = exp_nonpos<FAST>(ux - m);
+          e[aa][n][1] = exp_nonpos<FAST>(uy - m);
+          rr[aa][n][0] = L.g[aa][n].x * exp_capped<FAST>(m - L.y[aa][n].x);
+          rr[aa][n][1] = L.g[aa][n].y * exp_capped<FAST>(m - L.y[aa][n].y);
+        }
+      }
+    }
+    DBG2(it, 3);
+    // GEMM 2 of the previous tile has finished reading the images (GEMM 1 and the epilogue of the
+    // previous tile are behind this thread in program order)
+    mbar_wait(&s.ab_empty, (it & 1) ^ 1);
+    DBG2(it, 4);
+    {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) split_tf32(rr[aa][n][c], hi[4 * n + 2 * aa + c], lo[4 * n + 2 * aa + c]);
+      tmem_st_16x256b_x4(tmem_base + lane_addr + kRhiCol + 32 * chalf, hi);
+      tmem_st_16x256b_x4(tmem_base + lane_addr + kRloCol + 32 * chalf, lo);
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const uint32_t o = mn_base + mn_off[aa] + (((uint32_t)n ^ rsw) << 5);
+          sts64(o, hi[4 * n + 2 * aa], hi[4 * n + 2 * aa + 1]);
+          sts64(o + kLo, lo[4 * n + 2 * aa], lo[4 * n + 2 * aa + 1]);
+        }
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          float h0, l0, h1, l1;
+          split_tf32(e[aa][n][0], h0, l0);
+          split_tf32(e[aa][n][1], h1, l1);
+          const uint32_t o = mn_base + kEmn + mn_off[aa] + (((uint32_t)n ^ rsw) << 5);
+          sts64(o, h0, h1);
+          sts64(o + kLo, l0, l1);
+        }
+    }
+    tmem_st_wait();
+#ifdef CKB_TIMELINE
+    if (!(flags & 2048))
+#endif
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.ab_full);
+    DBG2(it, 5);
+    // next tile's rows: requested after the proxy fence (which waits for loads in flight)
+    if (it + 1 < n_tiles && !(flags & 64)) {
+      if (st.rows_left >= TM - trow) bwd2_load<2>(L, st);
+      else bwd2_load<1>(L, st);
+    }
+    advance();
+    DBG2(it, 6);
+    // ---- MMA issue: lane-elected instructions from converged warps 0 (GEMM 1) and 1 (GEMM 2)
+    if (warp == kGemm1Warp) {
+      mbar_wait(&s.ab_full, it & 1);
+      tc_fence_after_sync();
+      DBG2(it, 7);
+      // GEMM 1: T[b,i] = sum_o r[b,o] W[o,i], A = r from tensor memory
+      //   r_hi x [W_hi | W_lo]  (N = 128): main | correction;  r_lo x W_hi (N = 64): correction
+      constexpr uint32_t idesc_n128 = make_idesc_tf32(TM, 2 * KK, 0, 0);
+      constexpr uint32_t idesc_n64 = make_idesc_tf32(TM, KK, 0, 0);
+      const uint64_t d_w = make_desc(smem_u32(s.w), 16, 1024);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        mma_tf32_ts_warp(tmem_base, tmem_base + kRhiCol + 8 * ks,
+                         desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n128, ks ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        mma_tf32_ts_warp(tmem_base + KK, tmem_base + kRloCol + 8 * ks,
+                         desc_at(d_w, (ks >> 2) * kWBlock + (ks & 3) * 32), idesc_n64, 1u);
+      mma_commit_warp(&s.d1_full);
+      DBG2(it, 8);
+      if (!want_dw) mma_commit_warp(&s.ab_empty);
+      __syncwarp();
+    } else if (warp == kGemm2Warp && want_dw) {
+      mbar_wait(&s.ab_full, it & 1);
+      tc_fence_after_sync();
+      // GEMM 2: dW[o,i] += sum_b r[b,o] e[b,i]: both operands MN-major (rows = samples),
+      // M = [r_hi | r_lo] units, N = [e_hi | e_lo] units, 8 samples per instruction
+      constexpr uint32_t idesc2 = make_idesc_tf32(128, 128, 1, 1);
+      const uint64_t d_r = make_desc_mn(mn_base, TM * 128, 512);
+      const uint64_t d_e = make_desc_mn(mn_base + kEmn, TM * 128, 512);
+#pragma unroll
+      for (int ks = 0; ks < TM / 8; ++ks)
+        mma_tf32_warp(tmem_base + kD2Col, desc_at(d_r, ks * 1024), desc_at(d_e, ks * 1024), idesc2,
+                      (it || ks) ? 1u : 0u);
+      mma_commit_warp(&s.ab_empty);
+      if (it + 1 == n_tiles) mma_commit_warp(&s.d2_full);
+      __syncwarp();
+    }
+    // ---- du epilogue: du = e * (main + correction), same element ownership
+    mbar_wait(&s.d1_full, it & 1);
+    tc_fence_after_sync();
+    DBG2(it, 9);
+    {
+      float v[16], w[16];
+      tmem_ld_16x256b_x4(tmem_base + lane_addr + 32 * chalf, v);
+      tmem_ld_16x256b_x4(tmem_base + lane_addr + KK + 32 * chalf, w);
+      tmem_ld_wait();
+      DBG2(it, 10);
+#pragma unroll
+      for (int aa = 0; aa < 2; ++aa)
+        if (du_left > 8 * aa && !(flags & 32)) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            float2 o;
+            o.x = e[aa][n][0] * (v[4 * n + 2 * aa] + w[4 * n + 2 * aa]);
+            o.y = e[aa][n][1] * (v[4 * n + 2 * aa + 1] + w[4 * n + 2 * aa + 1]);
+            *reinterpret_cast<float2*>(pdu + aa * 8 * KK + 8 * n) = o;
+          }
+        }
+      pdu += TM * KK;
+      du_left -= TM;
+    }
+    tc_fence_before_sync();
+    DBG2(it, 11);
+  }
+#ifdef CKB_TIMELINE
+  if (dbg && (tid >> 5) == 0) g_dbg[1] = clock64();
+#endif
+  if (want_dw) {
+    // D2 quadrants: rows 0..63 = r_hi^T [e_hi | e_lo], rows 64..127 = r_lo^T [e_hi | (dropped)].
+    // dW[o][i] = D2[o][i] + D2[o][64+i] + D2[64+o][i]: the lower half goes through shared memory
+    // (the operand images are dead once every MMA has completed).
+    mbar_wait(&s.d2_full, 0);
+    tc_fence_after_sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
+    const int cg = warp >> 2;
+    const int row = q * 32 + lane;  // 0..127
+    const int o = row & 63;
+    const uint32_t xch = smem_u32(s.r_mn);  // [64 columns][64 + 1] exchange buffer
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + cg * 16;
+    float v[16];
+    tmem_ld16(taddr, v);
+    if (row < 64) {
+      float w[16];
+      tmem_ld16(taddr + KK, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += w[j];
+    } else {
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sts32(xch + (uint32_t)((cg * 16 + j) * (KK + 1) + o) * 4u, v[j]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
+    if (row < 64) {
+      float* out = a.dWp + (((int64_t)blockIdx.x * gridDim.y + f) * KK + o) * KK + cg * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += lds32(xch + (uint32_t)((cg * 16 + j) * (KK + 1) + o) * 4u);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+#ifdef CKB_TIMELINE
+  if (dbg && (tid >> 5) == 0) g_dbg[2] = clock64();
+#endif
+#undef DBG2
+}
+
 void dense_tc_bwd_config(int F, int64_t B, int& splits, int& tiles_per_cta) {
   const int n_tiles = ceil_div(B, TM);
   splits = (int)max64(1, min64(n_tiles, ceil_div(2 * kNumSMs, F)));
@@ -710,7 +1123,7 @@ bool dense_tc_ok(const DenseArgs& a) {
 }  // namespace
 
 static int g_tc_enabled = -1;
-static int g_tc_flags = 3;  // bit 0: MUFU exp, bit 1: MUFU log (both set: the fast-math kernels)
+static int g_tc_flags = 3 | 512;  // bit 0: MUFU exp, bit 1: MUFU log (both set: the fast-math kernels), bit 9: tcgen05 kernels for Ki = Ko = 128
 void set_tensor_cores(int on) { g_tc_enabled = on ? 1 : 0; }
 void set_tc_fast_math(int bits) { g_tc_flags = bits; }
 bool tc_disabled() {
@@ -725,7 +1138,10 @@ int tc_flags() { return g_tc_flags; }
 
 int tucker_debug_read(void* dst, size_t bytes);
 
+int bwd3_debug_read(void* dst, size_t bytes);
+
 int debug_read(void* dst, size_t bytes) {
+  if (g_tc_flags & 4096) return bwd3_debug_read(dst, bytes);
   if (g_tc_flags & 256) return tucker_debug_read(dst, bytes);
   if (bytes > sizeof(long long) * 512) bytes = sizeof(long long) * 512;
   CKB_CUDA_CHECK(cudaMemcpyFromSymbol(dst, g_dbg, bytes));
@@ -761,11 +1177,14 @@ size_t dense_tc_bwd_ws(int F, int H, int Ko, int Kred, int64_t B) {
   if (Ko != KK || Kred != KK || H > 2) return 0;
   int splits, tpc;
   dense_tc_bwd_config(F, B, splits, tpc);
-  return splits > 1 ? (size_t)splits * F * KK * KK * 4 : 0;
+  const size_t a = splits > 1 ? (size_t)splits * F * KK * KK * 4 : 0;
+  const size_t b = dense_tc_bwd3_ws(F, B);
+  return a > b ? a : b;
 }
 
 int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes) {
   if (tc_disabled() || !dense_tc_ok(a_in) || a_in.max_cons > kMaxCons) return 1;
+  if (dense_tc_bwd3_ok(a_in, a_in.rows64)) return dense_tc_bwd3(a_in, F, dW, c, ws, ws_bytes);
   DenseArgs a = a_in;
   int splits, tpc;
   dense_tc_bwd_config(F, a.B, splits, tpc);
@@ -779,15 +1198,25 @@ int dense_tc_bwd(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, size
     a.dWp = (float*)ws;
   }
   const size_t smem = sizeof(BwdSmem) + 1024;
+  const size_t smem2 = sizeof(Bwd2Smem) + 1024;
   static PerDeviceOnce attr;
   if (attr.first()) {
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd_kernel<false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd2_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd2_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   }
   dim3 grid(splits, F);
-  if ((g_tc_flags & 3) == 3)
+  if (!(g_tc_flags & 1024)) {  // bit 10: the round-1 kernel (A/B runs)
+    if ((g_tc_flags & 3) == 3)
+      dense_tc_bwd2_kernel<true><<<grid, kBwdThreads, smem2, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);
+    else
+      dense_tc_bwd2_kernel<false><<<grid, kBwdThreads, smem2, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);
+  } else if ((g_tc_flags & 3) == 3)
     dense_tc_bwd_kernel<true><<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);
   else
     dense_tc_bwd_kernel<false><<<grid, kBwdThreads, smem, c.stream>>>(a, tpc, dW ? 1 : 0, g_tc_flags);

@@ -127,6 +127,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// MN-major kind::tf32 operand (M or N index contiguous, one 128-byte row of 32 elements per k):
+// layout type SWIZZLE_128B_BASE32B -- 32-byte chunks xor (k & 3); `atom_bytes` = distance between
+// consecutive groups of 32 M/N elements (LBO), `kgroup_bytes` = distance between groups of 4 k-rows
+// (SBO, 512 for dense rows).  A k-step of 8 rows advances the start address by 1024 bytes.
+// Established on the B200 by scripts/micro/mn_major_probe.cu and umma_probe2.cu; K-major operands
+// do not accept this layout type ("misaligned address").
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t atom_bytes,
+                                                 uint32_t kgroup_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((atom_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((kgroup_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
 // The descriptor of the tile `off_bytes` further on in shared memory (same LBO / SBO / swizzle):
 // a 32-bit add on the low word.  Shared addresses are below 2^18, so the 14-bit start-address
 // field cannot carry into its neighbours.
@@ -270,10 +287,13 @@ __device__ __forceinline__ float fast_exp_finite(float x) {
 __device__ __forceinline__ float fast_exp(float x) {
   return fast_exp_finite(fminf(fmaxf(x, -104.f), 88.f));
 }
-// log(x) on the MUFU: lg2.approx * ln2 (absolute error ~2^-22 * |log2 x| + 2^-24).
+// log(x) on the MUFU: lg2.approx * ln2 (absolute error ~2^-22 * |log2 x| + 2^-24).  NOT the .ftz
+// form: a sum of products may legitimately be subnormal (the reference's edge case
+// tests/backend/torch/test_semiring.py:41-61: weight 1e-38 -> log(1e-38) = -87.5, finite), and the
+// tensor core keeps subnormal operands and products (scripts/micro/umma_probe2.cu, test 4).
 __device__ __forceinline__ float fast_log(float x) {
   float l;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("lg2.approx.f32 %0, %1;" : "=f"(l) : "f"(x));
   return l * 0.6931471805599453f;
 }
 

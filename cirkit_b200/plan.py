@@ -386,7 +386,10 @@ class PlanLayout:
 SHARED_GRAD_KINDS = ("cpt", "hadamard")  # every input of a fold receives the same gradient
 
 
-def _align(n: int, a: int = 4) -> int:
+def _align(n: int, a: int = 64) -> int:
+    """Blocks start at multiples of 64 floats per sample (256 bytes times the batch size): the
+    TMA-fed kernels address the arenas as matrices of 64-float rows, and every vector access of
+    the others stays 16-byte aligned."""
     return (n + a - 1) // a * a
 
 

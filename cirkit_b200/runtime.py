@@ -183,6 +183,15 @@ class ExecStep:
     scratch: tuple | None = None  # (slot, shape) of a runtime-owned buffer (TABLE_DENSE: T2)
 
 
+def _rows64(lay, sid: int) -> bool:
+    """All arena / gradient-arena row offsets of step `sid` are multiples of 64 floats
+    (CKB_STEP_ROWS64: the TMA-fed kernels address the arenas as matrices of 64-float rows)."""
+    for arr in (lay.in_rows[sid], lay.cons_rows[sid]):
+        if arr is not None and arr.size and np.any(arr % 64):
+            return False
+    return lay.out_off[sid] % 64 == 0 and (lay.gin_off[sid] < 0 or lay.gin_off[sid] % 64 == 0)
+
+
 def find_table_dense_pairs(plan: CircuitPlan) -> dict[int, int]:
     """input step -> sum step, for every table layer whose only consumer is an arity-1 sum layer
     reading it fold by fold (e.g. the Categorical -> Sum pair every region-graph circuit starts
@@ -278,6 +287,8 @@ class _DeviceState:
             d.num_folds, d.arity = s.num_folds, s.arity
             d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
             d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
+            if _rows64(lay, es.out_sid):
+                d.flags |= L.STEP_ROWS64
             d.num_states = int(first.config.get("num_categories", first.config.get("num_states", 0)))
             d.gin_h = int(lay.gin_h[es.out_sid])
             d.out_off = int(lay.out_off[es.out_sid])

@@ -65,6 +65,9 @@ typedef enum {
 } ckb_step_kind;
 
 #define CKB_DENSE_CONCAT 1 /* reduce over the concatenation of the H inputs instead of their sum */
+#define CKB_STEP_ROWS64 2  /* promise: out_off, gin_off and every entry of in_rows / cons_rows are
+                              multiples of 64 floats (lets the TMA-fed kernels address the arenas
+                              as matrices of 64-float rows; cirkit_b200.plan.build_layout aligns so) */
 
 typedef struct {
   int32_t kind;       /* ckb_step_kind                                                        */
@@ -167,8 +170,8 @@ int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 
 /* Process-wide switches (testing / A-B measurements). */
 #define CKB_OPT_TENSOR_CORES 0 /* 1 (default): tcgen05 kernels for the shapes that have one; 0: FP32 SIMT only */
-#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels (default 3);
-                                  bit 9 (512): EXPERIMENTAL tcgen05 forward for Ki = Ko = 128 (not yet validated, off by default) */
+#define CKB_OPT_TC_FAST_MATH 1 /* bit 0: MUFU ex2-based exp (error-compensated), bit 1: MUFU lg2-based log in the tcgen05 kernels;
+                                  bit 9 (512): tcgen05 kernels for Ki = Ko = 128 (dense128_tc.cu); default 3 | 512 */
 int ckb_set_option(int32_t option, int32_t value);
 
 /* Copies the device-side debug timeline (clock64 stamps of the tcgen05 kernels) to host memory. */

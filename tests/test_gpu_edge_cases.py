@@ -80,6 +80,17 @@ def test_semiring_subnormal_weight(K, dev):
     assert yo.shape == (200, 1, K)
     assert torch.isfinite(yo[0, 0, 0]) and abs(yo[0, 0, 0].item() + 92.5) < 0.1
     assert torch.isfinite(y[0, 0, 0]), "the subnormal sum was flushed to zero"
+    # The FP32 SIMT kernels keep the subnormal product exactly.  The tcgen05 kernels (K = 64, 128)
+    # multiply in 3xTF32: w = hi + lo with hi = tf32(w); for w = 1e-38 the correction lo = 1.4e-42
+    # lies below tf32's smallest subnormal (2^-136) and is dropped by the tensor core, so that ONE
+    # entry carries tf32's precision, 2^-11 relative in linear space -> 1.4e-4 in the log (measured,
+    # scripts/micro/umma_probe2.cu test 4: 1 x 1e-38 -> 9.99859e-39).  Every other entry must meet
+    # the usual tolerance.
+    if K in (64, 128):
+        assert abs(y[0, 0, 0].item() - yo[0, 0, 0].item()) <= 2.0 ** -11
+        y = y.clone()
+        sub = (x[:, 0] == 0).to(dev)  # the samples whose unit-0 sum is the subnormal
+        y[sub, 0, 0] = yo[0, 0, 0].float().item()
     _same(y, yo, "subnormal weight")
 
 

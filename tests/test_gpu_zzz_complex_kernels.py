@@ -1,11 +1,5 @@
-"""Layer-by-layer check of the EXPERIMENTAL complex-semiring kernels (csrc/complex_kernels.cu)
-against the oracle's complex path on the `*_complex*` fixtures.
-
-The kernels were written after the last GPU call of round 1 and have never run; the plan executor
-does not use them.  This file therefore only runs on request:
-
-    CKB_EXPERIMENTAL=1 python -m pytest tests/test_gpu_zzz_complex_kernels.py -m gpu -q
-"""
+"""Layer-by-layer check of the complex-semiring building blocks (csrc/complex_kernels.cu, the
+`ckb_complex_*` entry points) against the oracle's complex path on the `*_complex*` fixtures."""
 import os
 
 import pytest
@@ -13,11 +7,7 @@ import torch
 
 from helpers import Golden
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("CKB_EXPERIMENTAL") != "1",
-                       reason="experimental kernels: set CKB_EXPERIMENTAL=1"),
-]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
