@@ -16,7 +16,9 @@ LIB_PATH = os.path.join(HERE, "lib", "libcirkit_b200.so")
 STEP_TABLE, STEP_GAUSSIAN, STEP_CONSTANT, STEP_DENSE, STEP_MIXING, STEP_HADAMARD, STEP_KRONECKER, STEP_TUCKER = range(8)
 DENSE_CONCAT = 1
 STEP_ROWS64 = 2
-POP_SOFTMAX, POP_LOG_SOFTMAX_T, POP_LOG_T, POP_COPY_T, POP_SCALED_SIGMOID, POP_LOG, POP_LSE_ROWS = range(7)
+STEP_COMPLEX = 4
+STEP_REAL_TABLE = 8
+POP_SOFTMAX, POP_LOG_SOFTMAX_T, POP_LOG_T, POP_COPY_T, POP_SCALED_SIGMOID, POP_LOG, POP_LSE_ROWS, POP_CONJ = range(8)
 U8, I32, I64, F32, F64, I16 = range(6)
 RUN_PARAM_OPS = 1
 

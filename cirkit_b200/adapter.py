@@ -190,9 +190,7 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
     for sid, e in enumerate(entries[:-1]):
         m = e.module
         if semiring_names.get(m.semiring) not in semirings:
-            raise UnsupportedCircuitError(
-                f"semiring {m.semiring.__name__} has no CUDA path yet (lse-sum only)"
-            )
+            raise UnsupportedCircuitError(f"semiring {m.semiring.__name__} has no CUDA path")
         if semiring not in (None, m.semiring):
             raise UnsupportedCircuitError("layers of one circuit disagree on the semiring")
         semiring = m.semiring
@@ -305,15 +303,15 @@ def accelerate(tc, *, strict: bool = False):
     from .runtime import PlanRuntime
 
     try:
-        lowered = plan_from_torch(tc)
-    except UnsupportedCircuitError as exc:
+        lowered = plan_from_torch(tc, semirings=("lse-sum", "complex-lse-sum"))
+        runtime = PlanRuntime(lowered.plan)
+    except NotImplementedError as exc:  # UnsupportedCircuitError, or a plan the runtime has no kernels for
         if strict:
-            raise
+            raise exc if isinstance(exc, UnsupportedCircuitError) else UnsupportedCircuitError(str(exc)) from exc
         tc._b200_reason = str(exc)
         return tc
 
     base = type(tc)
-    runtime = PlanRuntime(lowered.plan)
 
     def _tensors(self):
         ext = {k: p() for k, p in lowered.externals.items()}

@@ -44,7 +44,8 @@ class B200Circuit(nn.Module):
         self.plan = plan
         self.runtime = PlanRuntime(plan, fuse_tables=fuse_tables)
         self.leaves = nn.ParameterList(
-            [nn.Parameter(torch.empty(l.shape, dtype=torch.float32), requires_grad=l.requires_grad)
+            [nn.Parameter(torch.empty(l.shape, dtype=torch.complex64 if l.dtype == "complex" else torch.float32),
+                          requires_grad=l.requires_grad)
              for l in plan.leaves]
         )
         if seed is not None:
@@ -99,7 +100,8 @@ class B200Circuit(nn.Module):
 
     def reset_parameters(self) -> None:
         for t, spec in zip(self.leaves, self.plan.leaves):
-            init_leaf_(t.data, spec)
+            # complex leaves: real and imaginary parts drawn independently
+            init_leaf_(torch.view_as_real(t.data) if t.is_complex() else t.data, spec)
 
     def forward(self, x: Tensor | None = None) -> Tensor:
         if self.plan.scope and x is None:

@@ -526,8 +526,9 @@ int bwd3_debug_read(void* dst, size_t bytes) {
 
 void dense_tc_bwd3_config(int F, int64_t B, int& splits, int& tiles_per_cta) {
   const int n_tiles = (int)(B / TM3);
-  // CTAs in multiples of the SM count where the batch allows, at least 8 tiles per CTA
-  splits = (int)max64(1, min64(n_tiles / 8, ceil_div(2 * kNumSMs, F)));
+  // about two CTAs per SM over the launch; a CTA's fixed cost (weight image, TMEM, pipeline fill)
+  // is worth about two tiles, so the small top levels are cut down to 2 tiles per CTA
+  splits = (int)max64(1, min64(n_tiles / 2, ceil_div(2 * kNumSMs, F)));
   tiles_per_cta = ceil_div(n_tiles, splits);
   splits = ceil_div(n_tiles, tiles_per_cta);
 }

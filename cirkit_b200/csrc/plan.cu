@@ -23,6 +23,10 @@ int transpose_mask(const uint8_t* m, int64_t rows, int D, uint8_t* mT, cudaStrea
 void set_tensor_cores(int on);
 void set_tc_fast_math(int bits);
 int debug_read(void* dst, size_t bytes);
+int complex_step_fwd(const ckb_step_desc_t& d, Ctx& c);
+int complex_step_bwd(const ckb_step_desc_t& d, Ctx& c);
+size_t complex_step_ws(const ckb_step_desc_t& d, int64_t B);
+int complex_conj(const float* src, float* dst, int64_t n, Ctx& c);
 
 }  // namespace ckb
 
@@ -126,7 +130,7 @@ int ckb_plan_create(const ckb_step_desc_t* steps, int32_t n_steps, const ckb_par
   for (int i = 0; i < n_ops; ++i) {
     const ckb_param_op_t& op = ops[i];
     if (op.src < 0 || op.src >= n_slots || op.dst < 0 || op.dst >= n_slots || op.rows <= 0 ||
-        op.cols <= 0 || op.kind < 0 || op.kind > CKB_POP_LSE_ROWS) {
+        op.cols <= 0 || op.kind < 0 || op.kind > CKB_POP_CONJ) {
       set_error("parameter op %d: bad descriptor", i);
       return CKB_ERR_INVALID;
     }
@@ -146,6 +150,10 @@ size_t ckb_plan_workspace_bytes(const ckb_plan_t* plan, int64_t batch) {
   if (plan == nullptr || batch <= 0) return need;
   for (const ckb_step_desc_t& d : plan->steps) {
     size_t w = 0;
+    if (d.flags & CKB_STEP_COMPLEX) {
+      need = std::max(need, complex_step_ws(d, batch) + 256);
+      continue;
+    }
     switch (d.kind) {
       case CKB_STEP_TABLE: w = table_bwd_ws(d, batch); break;
       case CKB_STEP_MIXING: w = mixing_bwd_ws(d, batch); break;
@@ -224,13 +232,21 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
   if (flags & CKB_RUN_PARAM_OPS) {
     // ops are independent of each other (one per parameter): softmaxes go out as one batch
     if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), false, c)) return rc;
-    for (const ckb_param_op_t& op : plan->ops)
-      if (op.kind != CKB_POP_SOFTMAX)
+    for (const ckb_param_op_t& op : plan->ops) {
+      if (op.kind == CKB_POP_CONJ) {
+        if (int rc = complex_conj(c.tensors[op.src], c.tensors[op.dst], op.rows * op.cols, c)) return rc;
+      } else if (op.kind != CKB_POP_SOFTMAX) {
         if (int rc = param_op_fwd(op, c)) return rc;
+      }
+    }
   }
   for (int i = step_begin; i < step_end; ++i) {
     const ckb_step_desc_t& d = plan->steps[i];
     int rc = CKB_OK;
+    if (d.flags & CKB_STEP_COMPLEX) {
+      if ((rc = complex_step_fwd(d, c)) != CKB_OK) return rc;
+      continue;
+    }
     switch (d.kind) {
       case CKB_STEP_TABLE: rc = table_fwd(d, c); break;
       case CKB_STEP_GAUSSIAN: rc = gaussian_fwd(d, c); break;
@@ -265,6 +281,10 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
   for (int i = step_end - 1; i >= step_begin; --i) {
     const ckb_step_desc_t& d = plan->steps[i];
     int rc = CKB_OK;
+    if (d.flags & CKB_STEP_COMPLEX) {
+      if ((rc = complex_step_bwd(d, c)) != CKB_OK) return rc;
+      continue;
+    }
     switch (d.kind) {
       case CKB_STEP_TABLE: rc = table_bwd(d, c); break;
       case CKB_STEP_GAUSSIAN: rc = gaussian_bwd(d, c); break;
@@ -280,9 +300,18 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
   }
   if (flags & CKB_RUN_PARAM_OPS) {
     if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), true, c)) return rc;
-    for (auto it = plan->ops.rbegin(); it != plan->ops.rend(); ++it)
-      if (it->kind != CKB_POP_SOFTMAX)
+    for (auto it = plan->ops.rbegin(); it != plan->ops.rend(); ++it) {
+      if (it->kind == CKB_POP_CONJ) {
+        if (c.grads[it->src] == nullptr) continue;
+        if (c.grads[it->dst] == nullptr) {
+          set_error("conj op: gradient of slot %d requested but slot %d has none", it->src, it->dst);
+          return CKB_ERR_INVALID;
+        }
+        if (int rc = complex_conj(c.grads[it->dst], c.grads[it->src], it->rows * it->cols, c)) return rc;
+      } else if (it->kind != CKB_POP_SOFTMAX) {
         if (int rc = param_op_bwd(*it, c)) return rc;
+      }
+    }
   }
   plan->last_launches = c.launches;
   return CKB_OK;

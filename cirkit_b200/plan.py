@@ -481,4 +481,12 @@ def seeded_leaves(plan: CircuitPlan, seed: int) -> list:
     import torch
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    return [torch.randn(l.shape, generator=g, dtype=torch.float32) for l in plan.leaves]
+    out = []
+    for l in plan.leaves:
+        if l.dtype == "complex":
+            # real and imaginary parts uniform in [0, 1), as notebooks/sum-of-squares-circuits.ipynb
+            # initialises complex weights (cell 12)
+            out.append(torch.view_as_complex(torch.rand((*l.shape, 2), generator=g, dtype=torch.float32)))
+        else:
+            out.append(torch.randn(l.shape, generator=g, dtype=torch.float32))
+    return out

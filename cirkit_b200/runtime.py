@@ -68,6 +68,10 @@ def apply_param_op(t: Tensor, op: str, attrs: dict) -> Tensor:
     if op == "mixing":
         d = torch.vmap(torch.vmap(torch.diag, in_dims=1))(t)
         return d.permute(0, 2, 1, 3).flatten(start_dim=2)
+    if op == "conj":
+        return torch.conj(t).resolve_conj()
+    if op == "clog":  # semiring.map_from(value, SumProduct) of a complex constant (semiring.py:506-508)
+        return torch.log(t.to(torch.complex64) if not t.is_complex() else t)
     raise ValueError(f"unknown parameter op {op!r}")
 
 
@@ -98,11 +102,31 @@ class _Binding:
     eff_shape: tuple
     src_slot: int = -1
     dst_slot: int = -1
+    is_complex: bool = False  # the tensor holds complex numbers ((re, im) float pairs on the device)
 
 
 def _is_last_dim(op: tuple, name: str, shape: tuple) -> bool:
     nd = len(shape) - 1
     return op[0] == name and op[1].get("dim", nd - 1) in (nd - 1, -1)
+
+
+def _bind_complex(sid: int, step: StepSpec, name: str, spec: ParamSpec, leaf_is_complex: bool) -> _Binding:
+    """Parameters of a 'complex-lse-sum' plan.  Complex tensors stay in the reference's layout
+    (Embedding weights (F, K, V), sum weights (F, Ko, Kred)); the only fused op is the conjugate
+    (TorchConjugateParameter, nodes.py:742-746).  A Categorical layer keeps its REAL parameters and
+    the real log-softmax-transpose op: its log-probabilities are cast to complex by the kernel."""
+    ops = list(spec.ops)
+    shape = tuple(spec.shape)
+    if step.kind == "categorical" and not leaf_is_complex:
+        return _bind(sid, step, name, spec)
+    if step.kind not in ("embedding", "sum", "cpt", "tucker", "constant"):
+        raise NotImplementedError(f"step {sid}: no complex kernel for {step.kind!r} parameters")
+    native, prefix = None, ops
+    if ops and ops[-1][0] == "conj":
+        prefix, native = ops[:-1], (L.POP_CONJ, int(np.prod(shape)), 1, 0, 0.0, 0.0)
+    if step.kind == "constant" and not step.config.get("log_space", False):
+        prefix = prefix + [("clog", {})]  # batch-free (F, K): the host maps it to log space
+    return _Binding(sid, name, spec, prefix, native, shape, shape, is_complex=True)
 
 
 def _bind(sid: int, step: StepSpec, name: str, spec: ParamSpec) -> _Binding:
@@ -250,7 +274,8 @@ class _DeviceState:
         self.eff_grad: dict[int, Tensor] = {}
         for b in rt.bindings:
             if b.native is not None:
-                self.eff[b.dst_slot] = torch.empty(b.eff_shape, dtype=torch.float32, device=device)
+                shape = (*b.eff_shape, 2) if b.is_complex else b.eff_shape
+                self.eff[b.dst_slot] = torch.empty(shape, dtype=torch.float32, device=device)
         for es in rt.exec_plans["fused"]:
             if es.scratch is not None:
                 slot, shape = es.scratch
@@ -289,6 +314,10 @@ class _DeviceState:
             d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
             if _rows64(lay, es.out_sid):
                 d.flags |= L.STEP_ROWS64
+            if rt.is_complex:
+                d.flags |= L.STEP_COMPLEX
+                if s.kind == "categorical":
+                    d.flags |= L.STEP_REAL_TABLE
             d.num_states = int(first.config.get("num_categories", first.config.get("num_states", 0)))
             d.gin_h = int(lay.gin_h[es.out_sid])
             d.out_off = int(lay.out_off[es.out_sid])
@@ -338,8 +367,16 @@ class _DeviceState:
 class PlanRuntime:
     def __init__(self, plan: CircuitPlan, *, fuse_tables: bool = True):
         plan.validate()
-        if plan.semiring != "lse-sum":
-            raise NotImplementedError("only the 'lse-sum' semiring has a CUDA path")
+        self.is_complex = plan.semiring == "complex-lse-sum"
+        if self.is_complex:
+            fuse_tables = False
+            for sid, s in enumerate(plan.steps):
+                if s.kind in ("mixing", "kronecker", "gaussian") or (s.kind == "sum" and s.arity > 1):
+                    raise NotImplementedError(
+                        f"step {sid}: no 'complex-lse-sum' kernel for {s.kind!r} layers"
+                        + (" over concatenated inputs" if s.kind == "sum" else ""))
+                if s.kind == "tucker" and s.arity != 2:
+                    raise NotImplementedError(f"step {sid}: complex tucker layers of arity {s.arity}")
         self.plan = plan
         self.layout = build_layout(plan)
         self.bindings: list[_Binding] = []
@@ -355,7 +392,12 @@ class PlanRuntime:
                 if name is None:
                     slots.append(-1)
                     continue
-                b = _bind(sid, s, name, s.params[name])
+                if self.is_complex:
+                    spec = s.params[name]
+                    leaf_c = spec.leaf >= 0 and plan.leaves[spec.leaf].dtype == "complex"
+                    b = _bind_complex(sid, s, name, spec, leaf_c or spec.leaf < 0)
+                else:
+                    b = _bind(sid, s, name, s.params[name])
                 b.src_slot = n
                 n += 1
                 if b.native is not None:
@@ -463,13 +505,14 @@ class PlanRuntime:
                     t = torch.matmul(t, eval_param_chain(leaves, attrs["rhs"]))
                 else:
                     t = apply_param_op(t, op, attrs)
-            if t.dtype != torch.float32:
-                t = t.to(torch.float32)
+            want = torch.complex64 if b.is_complex else torch.float32
+            if t.dtype != want:
+                t = t.to(want)
             if tuple(t.shape) != b.src_shape:
                 raise ValueError(
                     f"step {b.sid} parameter {b.name!r}: expected shape {b.src_shape}, got {tuple(t.shape)}"
                 )
-            out.append(t.contiguous())
+            out.append(t.resolve_conj().contiguous() if t.is_complex() else t.contiguous())
         return out
 
     # ------------------------------------------------------------------ evaluation
@@ -496,6 +539,8 @@ class PlanRuntime:
                 f"the circuit reads variable {self.plan.num_variables - 1} but the input has "
                 f"{x.shape[1]} columns"
             )
+        if integrate_mask is not None and self.is_complex:
+            raise NotImplementedError("integration masks are not implemented for 'complex-lse-sum' plans")
         if integrate_mask is not None:
             # TorchInputLayer.integrate raises for layers that cannot be integrated
             # (layers/input.py:82-92: Embedding), and IntegrateQuery._layer_fn calls it only when
@@ -569,7 +614,7 @@ def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Cal
     which = rt.choose_plan(B, mask is not None)
     tensors = (C.c_void_p * rt.n_slots)()
     for b, p in zip(rt.bindings, P):
-        tensors[b.src_slot] = p.data_ptr()
+        tensors[b.src_slot] = p.data_ptr()  # complex64 storage = interleaved (re, im) floats
     for slot, buf in st.eff.items():
         tensors[slot] = buf.data_ptr()
     for sid, slot in rt.int_slots.items():
@@ -583,15 +628,17 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
     outs: list[Tensor | None] = []
     # all requested parameter gradients are views of ONE flat buffer (16-byte aligned pieces), so
     # that a data-parallel wrapper can sum them over the ranks with a single all-reduce
-    sizes = [(-(-p.numel() // 4) * 4) if nd else 0 for p, nd in zip(P, need)]
+    nfl = [p.numel() * (2 if p.is_complex() else 1) for p in P]  # floats per tensor
+    sizes = [(-(-n // 4) * 4) if nd else 0 for n, nd in zip(nfl, need)]
     flat = torch.empty(sum(sizes), dtype=torch.float32, device=st.device) if sum(sizes) else None
     rt.last_flat_grad = flat
     off = 0
-    for b, p, nd, sz in zip(rt.bindings, P, need, sizes):
+    for b, p, nd, sz, n in zip(rt.bindings, P, need, sizes, nfl):
         if not nd:
             outs.append(None)
             continue
-        g = flat[off : off + p.numel()].view(p.shape)
+        g = flat[off : off + n]
+        g = torch.view_as_complex(g.view(*p.shape, 2)) if p.is_complex() else g.view(p.shape)
         off += sz
         outs.append(g)
         grads[b.src_slot] = g.data_ptr()
@@ -622,7 +669,8 @@ class _PlanFn(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             call = _prepare_call(rt, st, x, mask, P, stream)
             B = call.B
-            arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
+            cpx = 2 if rt.is_complex else 1  # complex activations: (re, im) float pairs
+            arena = torch.empty(cpx * B * lay.arena_units, dtype=torch.float32, device=dev)
             ws = st.workspace(call.which, B)
             L.check(
                 lib.ckb_plan_forward(
@@ -636,7 +684,10 @@ class _PlanFn(torch.autograd.Function):
                 1 if call.xT is not None else 0)
             K = plan.num_output_units
             rows = lay.out_rows
-            if len(rows) == 1:
+            if rt.is_complex:
+                ac = torch.view_as_complex(arena.view(-1, 2))
+                out = torch.stack([ac[B * int(r) : B * int(r) + B * K].view(B, K) for r in rows], dim=1)
+            elif len(rows) == 1:
                 r = int(rows[0])
                 out = arena[B * r : B * r + B * K].view(B, 1, K).clone()
             else:
@@ -658,10 +709,16 @@ class _PlanFn(torch.autograd.Function):
         need = ctx.needs_input_grad[4:]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            garena = torch.empty(B * lay.garena_units, dtype=torch.float32, device=dev)
+            cpx = 2 if rt.is_complex else 1
+            garena = torch.empty(cpx * B * lay.garena_units, dtype=torch.float32, device=dev)
             O, K = plan.num_outputs, plan.num_output_units
-            go = garena[B * lay.out_goff : B * lay.out_goff + O * B * K].view(O, B, K)
-            go.copy_(gout.to(torch.float32).transpose(0, 1))
+            if rt.is_complex:
+                gc = torch.view_as_complex(garena.view(-1, 2))
+                gc[B * lay.out_goff : B * lay.out_goff + O * B * K].view(O, B, K).copy_(
+                    gout.to(torch.complex64).transpose(0, 1))
+            else:
+                go = garena[B * lay.out_goff : B * lay.out_goff + O * B * K].view(O, B, K)
+                go.copy_(gout.to(torch.float32).transpose(0, 1))
             grads, outs = _grad_table(rt, st, call, ctx.P, need)
             ws = st.workspace(call.which, B)
             L.check(

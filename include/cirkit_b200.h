@@ -69,6 +69,14 @@ typedef enum {
                               multiples of 64 floats (lets the TMA-fed kernels address the arenas
                               as matrices of 64-float rows; cirkit_b200.plan.build_layout aligns so) */
 
+#define CKB_STEP_COMPLEX 4 /* 'complex-lse-sum' semiring (semiring.py:410-476): the step's arena blocks,
+                              gradient blocks and weights hold interleaved (re, im) float pairs;
+                              offsets stay in units per sample.  Kinds: TABLE (Embedding
+                              layers/input.py:258-266, weights (F,K,V) complex), DENSE without
+                              CONCAT, TUCKER (arity 2), HADAMARD, CONSTANT (log-space value)       */
+#define CKB_STEP_REAL_TABLE 8 /* with CKB_STEP_COMPLEX on a TABLE step: the table is the REAL (F,V,K)
+                              log-table of a Categorical layer, cast to complex (semiring.py:511-514) */
+
 typedef struct {
   int32_t kind;       /* ckb_step_kind                                                        */
   int32_t num_folds;  /* F                                                                    */
@@ -104,6 +112,8 @@ typedef enum {
   CKB_POP_LSE_ROWS = 6       /* logsumexp over the last axis: (rows, cols) -> (rows): the value an
                                 integrated variable of an unnormalised Categorical yields
                                 (layers/input.py:414-421); backward ADDS softmax * g to d(src) */
+  ,CKB_POP_CONJ = 7          /* complex conjugate of (rows * cols) complex numbers, nodes.py:742-746;
+                                backward: conj of the gradient                                  */
 } ckb_param_op_kind;
 
 typedef struct {

@@ -73,6 +73,29 @@ def test_accelerate_leaves_unsupported_circuits_on_the_reference_path(reference)
 
     from cirkit_b200 import UnsupportedCircuitError, accelerate
 
+    sc = data_modalities.image_data(
+        (1, 4, 4), region_graph="quad-tree-2", input_layer="binomial", num_input_units=3,
+        sum_product_layer="cp", num_sum_units=3,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    cls = type(tc)
+    x = torch.randint(0, 256, (3, 16))
+    y = tc(x)
+    with pytest.raises(UnsupportedCircuitError):
+        accelerate(tc, strict=True)
+    assert accelerate(tc) is tc and type(tc) is cls  # untouched: the reference evaluates it
+    assert "TorchBinomialLayer" in tc._b200_reason
+    assert torch.equal(tc(x), y)
+
+
+def test_complex_semiring_circuits_are_accelerated(reference):
+    """'complex-lse-sum' circuits (squared circuits, semiring.py:410-476) lower to a complex plan;
+    layer kinds without a complex kernel (mixing, concatenating sums) stay on the reference path."""
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    from cirkit_b200 import accelerate
+
     cplx = utils.Parameterization(dtype="complex", initialization="uniform")
     sc = data_modalities.tabular_data(
         "random-binary-tree", num_features=4,
@@ -80,14 +103,11 @@ def test_accelerate_leaves_unsupported_circuits_on_the_reference_path(reference)
             "num_states": 5, "weight_factory": utils.parameterization_to_factory(cplx)}},
         num_input_units=2, sum_product_layer="cp-t", num_sum_units=2, sum_weight_param=cplx)
     tc = PipelineContext(backend="torch", semiring="complex-lse-sum", fold=True, optimize=True).compile(sc)
-    cls = type(tc)
-    x = torch.randint(0, 5, (3, 4))
-    y = tc(x)
-    with pytest.raises(UnsupportedCircuitError):
-        accelerate(tc, strict=True)
-    assert accelerate(tc) is tc and type(tc) is cls  # untouched: the reference evaluates it
-    assert "ComplexLSESumSemiring" in tc._b200_reason
-    assert torch.equal(tc(x), y)
+    cc = accelerate(tc, strict=True)
+    assert type(cc).__name__ == "B200TorchCircuit" and cc._b200_runtime.is_complex
+    assert all(p.is_complex() for p in cc._b200_lowered.leaves)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.randint(0, 5, (3, 4)))
 
 
 def test_reference_integrate_query_is_routed_to_the_masked_runtime(reference, monkeypatch):

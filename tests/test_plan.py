@@ -1,6 +1,7 @@
 """Plan / layout host logic (no GPU)."""
 import numpy as np
 import pytest
+import torch
 
 from cirkit_b200.plan import CircuitPlan, build_layout
 from helpers import Golden, golden_names
@@ -53,9 +54,10 @@ def test_validate_rejects_bad_gathers():
         bad.validate()
 
 
-def test_complex_plans_are_described_but_not_executed():
-    """The plan format carries 'complex-lse-sum' circuits (complex leaves, `conj` parameter nodes)
-    for the oracle and the fixtures; the CUDA runtime has no kernels for them and says so."""
+def test_complex_plans():
+    """The plan format carries 'complex-lse-sum' circuits (complex leaves, `conj` parameter nodes);
+    the runtime binds them with complex64 leaves and the fused conjugate op, and refuses the layer
+    kinds it has no complex kernel for."""
     from cirkit_b200 import B200Circuit
 
     plan = Golden("rbt16_cpt_k4_complex_conj").plan
@@ -64,8 +66,13 @@ def test_complex_plans_are_described_but_not_executed():
     assert any(op == "conj" for s in plan.steps for p in s.params.values() for op, _ in p.ops)
     again = CircuitPlan.load(plan.to_bytes())
     assert [l.dtype for l in again.leaves] == [l.dtype for l in plan.leaves]
-    with pytest.raises(NotImplementedError, match="lse-sum"):
-        B200Circuit(plan)
+    cc = B200Circuit(plan)
+    assert cc.runtime.is_complex and all(p.dtype == torch.complex64 for p in cc.leaves)
+    assert all(b.native is not None and b.is_complex for b in cc.runtime.bindings)  # conj is fused
+    mixing = CircuitPlan.load(Golden("qg8_cp_k4").plan.to_bytes())
+    mixing.semiring = "complex-lse-sum"
+    with pytest.raises(NotImplementedError, match="mixing"):
+        B200Circuit(mixing)
     # a complex leaf or a conjugation inside a real-valued circuit is a malformed plan
     bad = CircuitPlan.load(plan.to_bytes())
     bad.semiring = "lse-sum"
