@@ -33,6 +33,8 @@ WORKLOADS = {
     "qt28_cp_k32": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, CP (Dense+Hadamard), K=32",
     "qt28_tucker_k64": "QuadTree(quad-tree-2) 28x28, Categorical-256 inputs, Tucker, K=64",
     "pd32_cp_k128": "PoonDomingos 32x32x3, Categorical-256 inputs, CP (fold+optimize), K=128",
+    "rbt64_sos_k64": "Sum-of-squares circuit: RandomBinaryTree 64 vars, complex Embedding-256 inputs, CP-T, K=64, "
+                     "complex-lse-sum; log p(x) = 2 Re c(x) - Re Z, Z = integrate(c conj(c))",
 }
 # workloads built by resizing a structure fixture: name -> (fixture, its units, units to run at)
 RESIZED = {"pd32_cp_k128": ("pd32_cp_k4", 4, 128)}
@@ -45,13 +47,24 @@ def metric_name(workload):
         return METRIC
     return "samples/sec (fwd+bwd log-lik) " + {"qt28_cp_k32": "QuadTree 28x28 K=32 (configs[1])",
                                                "qt28_tucker_k64": "QuadTree 28x28 Tucker K=64 (configs[2])",
-                                               "pd32_cp_k128": "PoonDomingos 32x32x3 K=128 (configs[3])"}[workload]
+                                               "pd32_cp_k128": "PoonDomingos 32x32x3 K=128 (configs[3])",
+                                               "rbt64_sos_k64": "squared circuit RBT-64 K=64 complex (configs[4])"}[workload]
+
+
+class _PlanOnly:
+    def __init__(self, plan):
+        self.plan = plan
 
 
 def load_plan(name):
     import dataclasses
 
     from helpers import Golden
+
+    if name == "rbt64_sos_k64":  # the plan of c(x), lowered from the reference's compiled circuit
+        from cirkit_b200.adapter import plan_from_torch
+
+        return _PlanOnly(plan_from_torch(build_squared("torch").c, semirings=("complex-lse-sum",)).plan)
 
     if name in RESIZED:
         fixture, k0, k = RESIZED[name]
@@ -154,6 +167,47 @@ REF_SPECS = {  # workload -> image_data(shape, region graph, sum-product layer, 
 }
 
 
+class SquaredCircuit(torch.nn.Module):
+    """log p(x) = 2 Re c(x) - Re Z of a squared circuit (notebooks/sum-of-squares-circuits.ipynb
+    cell 32): `c` evaluates the complex log-scores, `z` the batch-free log-partition function of
+    c conj(c); both are compiled by ONE PipelineContext and share their parameters."""
+
+    def __init__(self, c, z):
+        super().__init__()
+        self.c, self.z = c, z
+
+    def forward(self, x):
+        return 2.0 * self.c(x).real - self.z().real
+
+
+def build_squared(backend, units=64):
+    """BASELINE.json configs[4] through the reference's own front-end (needs baseline/_ref):
+    tabular_data('random-binary-tree', 64 features, complex Embedding(256) inputs, 'cp-t', K units),
+    semiring 'complex-lse-sum', Z = integrate(multiply(c, conjugate(c)))."""
+    if not os.path.isdir(os.path.join(REF_DIR, "cirkit")):
+        raise RuntimeError(f"workload rbt64_sos_k64 is built by the reference's front-end: {REF_DIR} is missing")
+    if REF_DIR not in sys.path:
+        sys.path.insert(1, REF_DIR)
+    import cirkit.symbolic.functional as SF
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    if backend == "b200":
+        import cirkit_b200
+
+        cirkit_b200.register_backend()
+    cplx = utils.Parameterization(dtype="complex", initialization="uniform")
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=64,
+        input_layers={"name": "embedding", "args": {
+            "num_states": 256, "weight_factory": utils.parameterization_to_factory(cplx)}},
+        num_input_units=units, sum_product_layer="cp-t", num_sum_units=units, sum_weight_param=cplx)
+    zsc = SF.integrate(SF.multiply(sc, SF.conjugate(sc)))
+    torch.manual_seed(1234)
+    ctx = PipelineContext(backend=backend, semiring="complex-lse-sum", fold=True, optimize=True)
+    return SquaredCircuit(ctx.compile(sc), ctx.compile(zsc))
+
+
 def build_reference(workload, plan):
     """The UNMODIFIED reference (april-tools/cirkit, installed under baseline/_ref) compiled through
     its own public API -- `data_modalities.image_data` -> `PipelineContext(backend="torch")` -- for
@@ -161,6 +215,8 @@ def build_reference(workload, plan):
     kind "reference", or (OracleCircuit, "port") when the install is missing / cannot be imported."""
     from cirkit_b200.plan import seeded_leaves
 
+    if workload == "rbt64_sos_k64":
+        return build_squared("torch"), "reference"
     try:
         if not os.path.isdir(os.path.join(REF_DIR, "cirkit")):
             raise ImportError(f"{REF_DIR} not present")
@@ -228,7 +284,8 @@ def run_reference(args):
         "impl": "reference",
         "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "c64" if args.workload == "rbt64_sos_k64" else "f32",
+        "data": "synthetic",
         "config": make_config(args, world, g.plan),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{args.steps} steps of batch {B} on rank 0's host cores "
@@ -277,10 +334,19 @@ def run_b200(args):
         from cirkit_b200 import _lib
 
         _lib.check(_lib.load().ckb_set_option(1, args.tc_flags), "ckb_set_option")
-    g = load_plan(args.workload)
-    plan = g.plan
-    cc = B200Circuit(plan, seed=1234).to(dev)
-    leaves = list(cc.leaves)
+    if args.workload == "rbt64_sos_k64":
+        cc = build_squared("b200").to(dev)
+        assert type(cc.c).__name__ == "B200TorchCircuit", getattr(cc.c, "_b200_reason", "")
+        runtime, plan = cc.c._b200_runtime, cc.c._b200_lowered.plan
+        z_runtime = getattr(cc.z, "_b200_runtime", None)  # the partition-function circuit (batch-free)
+        leaves, prof_leaves = list(cc.parameters()), cc.c._b200_lowered.leaves
+        g = _PlanOnly(plan)
+    else:
+        g = load_plan(args.workload)
+        plan = g.plan
+        cc = B200Circuit(plan, seed=1234).to(dev)
+        runtime, z_runtime = cc.runtime, None
+        leaves = prof_leaves = list(cc.leaves)
     B, D = args.batch, plan.num_variables
     gen = torch.Generator().manual_seed(1000 + rank)
     n_batches = 4
@@ -299,10 +365,10 @@ def run_b200(args):
         for p in leaves:
             p.grad = None
         ll = cc(x)
-        n = cc.runtime.last_launches
+        n = runtime.last_launches + (z_runtime.last_launches if z_runtime else 0)
         loss = -ll.sum() / (world * B)  # this rank's share of the global-batch mean NLL
         loss.backward()
-        launches = n + cc.runtime.last_launches
+        launches = n + runtime.last_launches + (z_runtime.last_launches if z_runtime else 0)
         if world > 1:
             # the one collective of the data path: all-gather of the root log-densities ...
             all_gather_rows(ll, world * B)
@@ -383,7 +449,7 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel (rank 0, live, CUDA events around each step's launches)
-    prof = profile_steps(cc.runtime, dev_x[0], leaves, iters=5)
+    prof = profile_steps(runtime, dev_x[0], prof_leaves, iters=5)
     peak, peak_src = peaks()
     # the dominant KERNEL: the step/direction with the largest time per launch (a step that is
     # two kernels, like the fused table+dense one, is not a single roofline point)
@@ -438,7 +504,8 @@ def run_b200(args):
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "c64" if args.workload == "rbt64_sos_k64" else "f32",
+        "data": "synthetic",
         "config": make_config(args, world, plan),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 8,
@@ -488,7 +555,7 @@ def main():
                          "3|512 also routes K=128 layers to the experimental tcgen05 kernels)")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 512 if args.workload == "pd32_cp_k128" else 2048
+        args.batch = {"pd32_cp_k128": 512, "rbt64_sos_k64": 1024}.get(args.workload, 2048)
     if args.cpu_batch is None:
         args.cpu_batch = {"pd32_cp_k128": 32, "qt28_tucker_k64": 256}.get(args.workload, args.batch)
     if args.impl == "reference":

@@ -159,7 +159,7 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
         TorchEmbeddingLayer,
         TorchGaussianLayer,
     )
-    from cirkit.backend.torch.layers.optimized import TorchCPTLayer, TorchTuckerLayer
+    from cirkit.backend.torch.layers.optimized import TorchCPTLayer, TorchTensorDotLayer, TorchTuckerLayer
     from cirkit.backend.torch.semiring import ComplexLSESumSemiring, LSESumSemiring
 
     semiring_names = {LSESumSemiring: "lse-sum", ComplexLSESumSemiring: "complex-lse-sum"}
@@ -223,6 +223,9 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
             kind = "cpt"
         elif isinstance(m, TorchTuckerLayer):
             kind = "tucker"
+        elif isinstance(m, TorchTensorDotLayer):  # layers/optimized.py:205-300
+            kind = "tensordot"
+            config["kq"] = int(m._num_batch_units)
         elif isinstance(m, TorchSumLayer):
             kind = "sum"
             w = params["weight"]

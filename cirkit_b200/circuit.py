@@ -102,6 +102,7 @@ class B200Circuit(nn.Module):
         for t, spec in zip(self.leaves, self.plan.leaves):
             # complex leaves: real and imaginary parts drawn independently
             init_leaf_(torch.view_as_real(t.data) if t.is_complex() else t.data, spec)
+        self.runtime.invalidate_parameter_cache()
 
     def forward(self, x: Tensor | None = None) -> Tensor:
         if self.plan.scope and x is None:

@@ -150,20 +150,24 @@ struct CDenseArgs {
   float2* y;                // (F, B, Ko)
   int64_t B, chunk;
   int H, Ki, Ko, Kred, tucker;
+  int Kq;  // TENSORDOT (layers/optimized.py:205-300): every sample row holds Kq interleaved vectors --
+           // input element i of vector q sits at i*Kq + q, output o at q*Ko + o; 1 for the sum layers
   CGradSrc gs;
   float2* gin;              // (F, gin_h, B, Ki)
   float* dWp;               // [chunks][F][Ko][Kred] complex, or nullptr
 };
 
 // e[0..Kred) of one sample into shared memory; returns the shift (sum of the per-input shifts)
-__device__ __forceinline__ float cload_e(const CDenseArgs& a, int f, int64_t b, int lane, float2* e,
+__device__ __forceinline__ float cload_e(const CDenseArgs& a, int f, int64_t s, int lane, float2* e,
                                          float2* e12) {
+  const int64_t b = s / a.Kq;
+  const int q = (int)(s - b * a.Kq);
   if (!a.tucker) {
     float m = -INFINITY;
     for (int i = lane; i < a.Ki; i += 32) {
       float2 u = make_float2(0.f, 0.f);
       for (int h = 0; h < a.H; ++h) {
-        const float2 v = a.arena[a.B * a.in_rows[f * a.H + h] + b * a.Ki + i];
+        const float2 v = a.arena[a.B * a.in_rows[f * a.H + h] + b * a.Ki * a.Kq + i * a.Kq + q];
         u.x += v.x;
         u.y += v.y;
       }
@@ -195,17 +199,18 @@ __global__ void __launch_bounds__(kCWarps * 32) cdense_fwd_kernel(CDenseArgs a) 
   extern __shared__ float2 smem_d[];
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* Ws = smem_d;                                   // [Ko][Kred]
-  float2* e = Ws + a.Ko * a.Kred + warp * (a.Kred + 2 * a.Ki);
+  float2* Ws = smem_d;                                   // [Ko][Kred + 1]
+  float2* e = Ws + a.Ko * (a.Kred + 1) + warp * (a.Kred + 2 * a.Ki);
   float2* e12 = e + a.Kred;
   const float2* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
-  for (int i = threadIdx.x; i < a.Ko * a.Kred; i += blockDim.x) Ws[i] = Wf[i];
+  for (int i = threadIdx.x; i < a.Ko * a.Kred; i += blockDim.x) Ws[(i / a.Kred) * (a.Kred + 1) + i % a.Kred] = Wf[i];
   __syncthreads();
-  const int64_t b0 = (int64_t)blockIdx.x * a.chunk, b1 = min64(a.B, b0 + a.chunk);
+  const int KP = a.Kred + 1;  // padded row: lanes (= rows o) hit different banks
+  const int64_t b0 = (int64_t)blockIdx.x * a.chunk, b1 = min64(a.B * a.Kq, b0 + a.chunk);
   for (int64_t b = b0 + warp; b < b1; b += kCWarps) {
     const float m = cload_e(a, f, b, lane, e, e12);
     for (int o = lane; o < a.Ko; o += 32) {
-      const float2* wr = Ws + o * a.Kred;
+      const float2* wr = Ws + o * KP;
       float2 s = make_float2(0.f, 0.f);
       for (int i = 0; i < a.Kred; ++i) {
         const float2 p = cmul(wr[i], e[i]);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kCWarps * 32) cdense_fwd_kernel(CDenseArgs a) 
       }
       float2 l = clog(s);
       l.x += m;
-      a.y[((int64_t)f * a.B + b) * a.Ko + o] = l;
+      a.y[(int64_t)f * a.B * a.Ko * a.Kq + b * a.Ko + o] = l;  // row b = (sample, q): q*Ko + o
     }
     __syncwarp();
   }
@@ -227,47 +232,50 @@ __global__ void __launch_bounds__(kCWarps * 32) cdense_bwd_kernel(CDenseArgs a) 
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nW = a.Ko * a.Kred;
-  float2* Ws = smem_d;                                  // [Ko][Kred]
-  float2* es = Ws + nW;                                 // [warps][Kred]
+  const int KP = a.Kred + 1;
+  float2* Ws = smem_d;                                  // [Ko][Kred + 1]
+  float2* es = Ws + a.Ko * KP;                          // [warps][Kred]
   float2* rs = es + kCWarps * a.Kred;                   // [warps][Ko]
   float2* e12 = rs + kCWarps * a.Ko + warp * 2 * a.Ki;  // [warps][2 Ki]  (tucker)
   float2* ge = e12 + (kCWarps - warp) * 2 * a.Ki + warp * a.Kred;  // [warps][Kred] (tucker)
   float2* e = es + warp * a.Kred;
   float2* r = rs + warp * a.Ko;
   const float2* Wf = a.W + (int64_t)f * nW;
-  for (int i = threadIdx.x; i < nW; i += blockDim.x) Ws[i] = Wf[i];
+  for (int i = threadIdx.x; i < nW; i += blockDim.x) Ws[(i / a.Kred) * KP + i % a.Kred] = Wf[i];
   float2 acc[NE];
 #pragma unroll
   for (int j = 0; j < NE; ++j) acc[j] = make_float2(0.f, 0.f);
   __syncthreads();
-  const int64_t b0 = (int64_t)blockIdx.x * a.chunk, b1 = min64(a.B, b0 + a.chunk);
+  const int64_t b0 = (int64_t)blockIdx.x * a.chunk, b1 = min64(a.B * a.Kq, b0 + a.chunk);
   for (int64_t bb = b0; bb < b1; bb += kCWarps) {
-    const int64_t b = bb + warp;
+    const int64_t b = bb + warp;  // row (sample, q)
     const bool live = b < b1;
+    const int64_t smp = b / a.Kq;
+    const int q = (int)(b - smp * a.Kq);
     if (live) {
       const float m = cload_e(a, f, b, lane, e, e12);
       for (int o = lane; o < a.Ko; o += 32) {
         // S_o = exp(y_o - m): the sum the forward took the logarithm of
-        const float2 s = cexp_shifted(a.y[((int64_t)f * a.B + b) * a.Ko + o], m);
-        r[o] = safe_div_conj(cpull(a.gs, f, b, a.Ko, o), s);
+        const float2 s = cexp_shifted(a.y[(int64_t)f * a.B * a.Ko * a.Kq + b * a.Ko + o], m);
+        r[o] = safe_div_conj(cpull(a.gs, f, smp, a.Ko * a.Kq, q * a.Ko + o), s);
       }
       __syncwarp();
       if (!a.tucker) {
         for (int i = lane; i < a.Ki; i += 32) {
           float2 g = make_float2(0.f, 0.f);
           for (int o = 0; o < a.Ko; ++o) {
-            const float2 p = cmul_conj(r[o], Ws[o * a.Kred + i]);
+            const float2 p = cmul_conj(r[o], Ws[o * KP + i]);
             g.x += p.x;
             g.y += p.y;
           }
           // every input of the fold receives the same gradient (u is their sum)
-          a.gin[((int64_t)f * a.B + b) * a.Ki + i] = cmul_conj(g, e[i]);
+          a.gin[((int64_t)f * a.B + smp) * a.Ki * a.Kq + i * a.Kq + q] = cmul_conj(g, e[i]);
         }
       } else {
         for (int ij = lane; ij < a.Kred; ij += 32) {
           float2 g = make_float2(0.f, 0.f);
           for (int o = 0; o < a.Ko; ++o) {
-            const float2 p = cmul_conj(r[o], Ws[o * a.Kred + ij]);
+            const float2 p = cmul_conj(r[o], Ws[o * KP + ij]);
             g.x += p.x;
             g.y += p.y;
           }
@@ -377,7 +385,7 @@ __global__ void conj_kernel(const float2* __restrict__ src, float2* __restrict__
 }
 
 size_t cdense_smem(int Ki, int Ko, int Kred, bool bwd) {
-  size_t n = (size_t)Ko * Kred;
+  size_t n = (size_t)Ko * (Kred + 1);
   if (!bwd) n += (size_t)kCWarps * (Kred + 2 * Ki);
   else n += (size_t)kCWarps * (Kred + Ko + 2 * Ki + Kred);
   return n * sizeof(float2);
@@ -398,6 +406,9 @@ static void ctable_config(int F, int64_t B, int& chunks, int64_t& chunk) {
   chunks = ceil_div(B, chunk);
 }
 
+// TENSORDOT steps: k_in = Kj * Kq and k_out = Kq * Kk; num_states carries Kq
+static int tdot_kq(const ckb_step_desc_t& d) { return d.kind == CKB_STEP_TENSORDOT ? d.num_states : 1; }
+
 static CDenseArgs cdense_args(const ckb_step_desc_t& d, Ctx& c) {
   CDenseArgs a{};
   a.W = reinterpret_cast<const float2*>(c.tensors[d.slot[0]]);
@@ -406,10 +417,11 @@ static CDenseArgs cdense_args(const ckb_step_desc_t& d, Ctx& c) {
   a.y = reinterpret_cast<float2*>(c.arena) + c.B * d.out_off;
   a.B = c.B;
   a.H = d.arity;
-  a.Ki = d.k_in;
-  a.Ko = d.k_out;
+  a.Kq = tdot_kq(d);
+  a.Ki = d.k_in / a.Kq;
+  a.Ko = d.k_out / a.Kq;
   a.tucker = d.kind == CKB_STEP_TUCKER;
-  a.Kred = a.tucker ? d.k_in * d.k_in : d.k_in;
+  a.Kred = a.tucker ? a.Ki * a.Ki : a.Ki;
   return a;
 }
 
@@ -418,9 +430,15 @@ static int cdense_check(const ckb_step_desc_t& d) {
     set_error("complex semiring: sum layers over concatenated inputs have no kernel");
     return CKB_ERR_UNSUPPORTED;
   }
-  const int Kred = d.kind == CKB_STEP_TUCKER ? d.k_in * d.k_in : d.k_in;
-  if ((int64_t)d.k_out * Kred > 256 * 16 || cdense_smem(d.k_in, d.k_out, Kred, true) > 200 * 1024) {
-    set_error("complex semiring: %d x %d weights exceed the kernels' shared-memory tiles", d.k_out, Kred);
+  const int kq = tdot_kq(d);
+  if (kq <= 0 || d.k_in % kq || d.k_out % kq) {
+    set_error("complex tensordot: %d / %d units are not multiples of Kq = %d", d.k_in, d.k_out, kq);
+    return CKB_ERR_INVALID;
+  }
+  const int Ki = d.k_in / kq, Ko = d.k_out / kq;
+  const int Kred = d.kind == CKB_STEP_TUCKER ? Ki * Ki : Ki;
+  if ((int64_t)Ko * Kred > 256 * 16 || cdense_smem(Ki, Ko, Kred, true) > 200 * 1024) {
+    set_error("complex semiring: %d x %d weights exceed the kernels' shared-memory tiles", Ko, Kred);
     return CKB_ERR_UNSUPPORTED;
   }
   if (d.kind == CKB_STEP_TUCKER && d.arity != 2) {
@@ -438,10 +456,13 @@ size_t complex_step_ws(const ckb_step_desc_t& d, int64_t B) {
       ctable_config(d.num_folds, B, chunks, chunk);
       return (size_t)chunks * d.num_folds * d.k_out * d.num_states * 8;
     case CKB_STEP_DENSE:
+    case CKB_STEP_TENSORDOT:
     case CKB_STEP_TUCKER: {
-      cdense_config(d.num_folds, B, chunks, chunk);
-      const int Kred = d.kind == CKB_STEP_TUCKER ? d.k_in * d.k_in : d.k_in;
-      return (size_t)chunks * d.num_folds * d.k_out * Kred * 8;
+      const int kq = tdot_kq(d) > 0 ? tdot_kq(d) : 1;
+      cdense_config(d.num_folds, B * kq, chunks, chunk);
+      const int Ki = d.k_in / kq, Ko = d.k_out / kq;
+      const int Kred = d.kind == CKB_STEP_TUCKER ? Ki * Ki : Ki;
+      return (size_t)chunks * d.num_folds * Ko * Kred * 8;
     }
     default: return 0;
   }
@@ -474,11 +495,12 @@ int complex_step_fwd(const ckb_step_desc_t& d, Ctx& c) {
       break;
     }
     case CKB_STEP_DENSE:
+    case CKB_STEP_TENSORDOT:
     case CKB_STEP_TUCKER: {
       if (int rc = cdense_check(d)) return rc;
       CDenseArgs a = cdense_args(d, c);
       int chunks;
-      cdense_config(F, c.B, chunks, a.chunk);
+      cdense_config(F, c.B * a.Kq, chunks, a.chunk);
       const size_t smem = cdense_smem(a.Ki, a.Ko, a.Kred, false);
       static PerDeviceOnce attr;
       if (attr.first())
@@ -567,13 +589,14 @@ int complex_step_bwd(const ckb_step_desc_t& d, Ctx& c) {
       return CKB_OK;
     }
     case CKB_STEP_DENSE:
+    case CKB_STEP_TENSORDOT:
     case CKB_STEP_TUCKER: {
       if (int rc = cdense_check(d)) return rc;
       CDenseArgs a = cdense_args(d, c);
       a.gs = gs;
       a.gin = gin;
       int chunks;
-      cdense_config(F, c.B, chunks, a.chunk);
+      cdense_config(F, c.B * a.Kq, chunks, a.chunk);
       float* dW = c.grads[d.slot[0]];
       const size_t n = (size_t)2 * F * a.Ko * a.Kred;
       a.dWp = dW;

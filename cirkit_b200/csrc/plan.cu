@@ -84,6 +84,12 @@ static int check_step(const ckb_step_desc_t& d, int idx, int n_slots) {
         return CKB_ERR_INVALID;
       }
       break;
+    case CKB_STEP_TENSORDOT:
+      if (!(d.flags & CKB_STEP_COMPLEX)) {
+        set_error("step %d: tensordot layers have kernels for the complex semiring only", idx);
+        return CKB_ERR_UNSUPPORTED;
+      }
+      // fallthrough
     case CKB_STEP_DENSE:
     case CKB_STEP_MIXING:
     case CKB_STEP_TUCKER:

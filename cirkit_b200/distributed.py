@@ -112,7 +112,9 @@ def all_reduce_gradients(params: Iterable[Tensor], *, average: bool = False, gro
             p.grad = torch.zeros_like(p)
         total += p.grad.numel() * p.grad.element_size()
         if world > 1:
-            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+            # complex gradients travel as (re, im) float pairs (NCCL has no complex types)
+            g = torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
             if average:
                 p.grad.div_(world)
     return total
@@ -168,3 +170,6 @@ class BatchShardedCircuit(nn.Module):
         if self.world_size > 1:
             for p in self.circuit.parameters():
                 dist.broadcast(p.data, src=src, group=self.group)
+            rt = getattr(self.circuit, "runtime", None)
+            if rt is not None and hasattr(rt, "invalidate_parameter_cache"):
+                rt.invalidate_parameter_cache()  # `.data` writes do not bump the version counter

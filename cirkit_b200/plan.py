@@ -31,7 +31,7 @@ import numpy as np
 
 # Step kinds (names follow the reference layer classes they restate).
 INPUT_KINDS = ("categorical", "gaussian", "embedding", "constant")
-INNER_KINDS = ("sum", "cpt", "mixing", "hadamard", "kronecker", "tucker")
+INNER_KINDS = ("sum", "cpt", "mixing", "hadamard", "kronecker", "tucker", "tensordot")
 ALL_KINDS = INPUT_KINDS + INNER_KINDS
 
 # Re-parameterisation ops a ParamSpec chain may hold (reference:
@@ -128,11 +128,14 @@ class CircuitPlan:
         return sum(int(np.prod(l.shape)) for l in self.leaves)
 
     def algorithmic_bytes(self, batch: int, x_itemsize: int = 8) -> int:
-        """Bytes one forward+backward pass must move (SURVEY §8(d) formula)."""
+        """Bytes one forward+backward pass must move (SURVEY §8(d) formula; complex circuits move
+        8 bytes per unit and per complex parameter)."""
+        unit = 8 if self.semiring == "complex-lse-sum" else 4
+        pbytes = sum(int(np.prod(l.shape)) * (8 if l.dtype == "complex" else 4) for l in self.leaves)
         return (
             x_itemsize * batch * self.num_variables
-            + 5 * 4 * self.activation_units() * batch
-            + 7 * 4 * self.parameter_elements()
+            + 5 * unit * self.activation_units() * batch
+            + 7 * pbytes
         )
 
     # ---------------------------------------------------------------- validation

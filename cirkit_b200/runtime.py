@@ -119,7 +119,7 @@ def _bind_complex(sid: int, step: StepSpec, name: str, spec: ParamSpec, leaf_is_
     shape = tuple(spec.shape)
     if step.kind == "categorical" and not leaf_is_complex:
         return _bind(sid, step, name, spec)
-    if step.kind not in ("embedding", "sum", "cpt", "tucker", "constant"):
+    if step.kind not in ("embedding", "sum", "cpt", "tucker", "tensordot", "constant"):
         raise NotImplementedError(f"step {sid}: no complex kernel for {step.kind!r} parameters")
     native, prefix = None, ops
     if ops and ops[-1][0] == "conj":
@@ -180,6 +180,7 @@ _KIND = {
     "hadamard": L.STEP_HADAMARD,
     "kronecker": L.STEP_KRONECKER,
     "tucker": L.STEP_TUCKER,
+    "tensordot": L.STEP_TENSORDOT,
 }
 _PARAM_ORDER = {
     "categorical": ("probs|logits",),
@@ -190,6 +191,7 @@ _PARAM_ORDER = {
     "cpt": ("weight",),
     "mixing": ("weight",),
     "tucker": ("weight",),
+    "tensordot": ("weight",),
     "hadamard": (),
     "kronecker": (),
 }
@@ -286,6 +288,10 @@ class _DeviceState:
             for sid in rt.int_buf_sids
         }
         self.ws: Tensor | None = None
+        # effective-parameter cache: identity + version of every parameter tensor the
+        # buffers in `eff` (and the logsumexp buffers of the masked plan) were last computed from
+        self.param_key: tuple | None = None
+        self.lse_key: tuple | None = None
 
     def grad_buffer(self, slot: int) -> Tensor:
         g = self.eff_grad.get(slot)
@@ -319,6 +325,8 @@ class _DeviceState:
                 if s.kind == "categorical":
                     d.flags |= L.STEP_REAL_TABLE
             d.num_states = int(first.config.get("num_categories", first.config.get("num_states", 0)))
+            if s.kind == "tensordot":
+                d.num_states = int(s.config["kq"])  # vectors interleaved in a sample row
             d.gin_h = int(lay.gin_h[es.out_sid])
             d.out_off = int(lay.out_off[es.out_sid])
             d.gin_off = int(lay.gin_off[es.out_sid])
@@ -368,6 +376,8 @@ class PlanRuntime:
     def __init__(self, plan: CircuitPlan, *, fuse_tables: bool = True):
         plan.validate()
         self.is_complex = plan.semiring == "complex-lse-sum"
+        if not self.is_complex and any(s.kind == "tensordot" for s in plan.steps):
+            raise NotImplementedError("tensordot layers have kernels for the 'complex-lse-sum' semiring only")
         if self.is_complex:
             fuse_tables = False
             for sid, s in enumerate(plan.steps):
@@ -456,9 +466,16 @@ class PlanRuntime:
         self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
         self._states: dict[torch.device, _DeviceState] = {}
         self.last_launches = 0
+        self.cache_parameters = True  # skip the parameter ops of no_grad calls on unchanged parameters
         self.keep_arena = False
         self.last_arena: Tensor | None = None
         self.last_flat_grad: Tensor | None = None  # flat buffer behind the last backward's gradients
+
+    def invalidate_parameter_cache(self) -> None:
+        """Forget the cached effective parameters (call after changing parameter storage behind
+        autograd's back, e.g. through `.data`, which does not bump the version counter)."""
+        for st in self._states.values():
+            st.param_key = st.lse_key = None
 
     def step_output(self, sid: int, batch: int) -> Tensor:
         """(F, B, K) activations of plan step `sid` from the last forward pass (keep_arena=True)."""
@@ -557,7 +574,9 @@ class PlanRuntime:
         if not P:
             raise ValueError("circuit without parameters")
         st = self.state(P[0].device)
-        return _PlanFn.apply(self, st, x, integrate_mask, *P)
+        # (inside autograd.Function.forward grad mode is always off: sample it here)
+        cache_ok = self.cache_parameters and not torch.is_grad_enabled()
+        return _PlanFn.apply(self, st, x, integrate_mask, cache_ok, *P)
 
 
 @dataclass
@@ -662,7 +681,7 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
 
 class _PlanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rt: PlanRuntime, st: _DeviceState, x, mask, *P):
+    def forward(ctx, rt: PlanRuntime, st: _DeviceState, x, mask, cache_ok, *P):
         lib, dev = st.lib, st.device
         lay, plan = rt.layout, rt.plan
         with torch.cuda.device(dev):
@@ -672,14 +691,25 @@ class _PlanFn(torch.autograd.Function):
             cpx = 2 if rt.is_complex else 1  # complex activations: (re, im) float pairs
             arena = torch.empty(cpx * B * lay.arena_units, dtype=torch.float32, device=dev)
             ws = st.workspace(call.which, B)
+            # The reference re-materialises every effective weight on every call
+            # (TorchParameter.forward, parameters/parameter.py:180-188).  In inference loops (no
+            # gradient wanted: eval, IntegrateQuery sweeps) the parameter ops are skipped while the
+            # parameter tensors are the same objects at the same version.
+            key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in P)
+            masked = call.which == "masked"
+            fresh = cache_ok and st.param_key == key and (not masked or st.lse_key == key)
             L.check(
                 lib.ckb_plan_forward(
                     st.handle(call.which), 0, call.n_steps, B,
                     call.xT.data_ptr() if call.xT is not None else None, call.x_is_float,
                     call.maskT.data_ptr() if call.maskT is not None else None, call.mask_rows,
-                    call.tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
+                    call.tensors, arena.data_ptr(), ws.data_ptr(), ws.numel(),
+                    0 if fresh else L.RUN_PARAM_OPS, stream),
                 "ckb_plan_forward",
             )
+            st.param_key = key
+            if masked:
+                st.lse_key = key
             rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which))) + (
                 1 if call.xT is not None else 0)
             K = plan.num_output_units
@@ -706,7 +736,7 @@ class _PlanFn(torch.autograd.Function):
         lib, dev = st.lib, st.device
         lay, plan = rt.layout, rt.plan
         B = call.B
-        need = ctx.needs_input_grad[4:]
+        need = ctx.needs_input_grad[5:]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             cpx = 2 if rt.is_complex else 1
@@ -732,7 +762,7 @@ class _PlanFn(torch.autograd.Function):
             )
             rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which)))
         ctx.arena = None
-        return (None, None, None, None, *outs)
+        return (None, None, None, None, None, *outs)
 
 
 # ----------------------------------------------------------------------------- per-step timing
@@ -799,10 +829,11 @@ def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: i
         steps = rt.exec_plans[call.which]
         handle = st.handle(call.which)
         grads, keep = _grad_table(rt, st, call, P, [True] * len(P))
-        arena = torch.empty(B * lay.arena_units, dtype=torch.float32, device=dev)
-        garena = torch.zeros(B * lay.garena_units, dtype=torch.float32, device=dev)
+        cpx = 2 if rt.is_complex else 1
+        arena = torch.empty(cpx * B * lay.arena_units, dtype=torch.float32, device=dev)
+        garena = torch.zeros(cpx * B * lay.garena_units, dtype=torch.float32, device=dev)
         O, K = plan.num_outputs, plan.num_output_units
-        garena[B * lay.out_goff : B * lay.out_goff + O * B * K] = -1.0 / B
+        garena[cpx * B * lay.out_goff : cpx * (B * lay.out_goff + O * B * K) : cpx] = -1.0 / B
         ws = st.workspace(call.which, B)
         xp = call.xT.data_ptr() if call.xT is not None else None
 
@@ -833,12 +864,12 @@ def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: i
         bwd(0, S, L.RUN_PARAM_OPS)
         res = []
         t, n = timed(fwd, 0, 0, L.RUN_PARAM_OPS)
-        pbytes = sum(int(np.prod(l.shape)) for l in plan.leaves) * 4
+        pbytes = sum(int(np.prod(l.shape)) * (8 if l.dtype == "complex" else 4) for l in plan.leaves)
         res.append({"step": "param_ops", "kind": "param_ops", "fwd_ms": t, "fwd_launches": n,
                     "fwd_bytes": 2 * pbytes, "bwd_bytes": 3 * pbytes})
         for i, es in enumerate(steps):
             t, n = timed(fwd, i, i + 1, 0)
-            fb, bb = _exec_step_bytes(rt, es, B)
+            fb, bb = (cpx * v for v in _exec_step_bytes(rt, es, B))
             ff, bf = _exec_step_flops(rt, es, B)
             res.append({"step": es.label, "kind": es.label.split(":")[1], "F": plan.steps[es.out_sid].num_folds,
                         "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb,

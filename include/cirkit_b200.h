@@ -56,6 +56,11 @@ typedef enum {
   CKB_STEP_HADAMARD = 5,  /* layers/inner.py:126-127                                            */
   CKB_STEP_KRONECKER = 6, /* layers/inner.py:178-187 (arity 2)                                  */
   CKB_STEP_TUCKER = 7,    /* layers/optimized.py:89-103 (arity 2)                               */
+  CKB_STEP_TENSORDOT = 9, /* TorchTensorDotLayer layers/optimized.py:205-300 (product circuits, e.g. the
+                             partition function of a squared circuit): the Ki = Kj*Kq inputs of a
+                             sample are Kq interleaved vectors, each contracted with W (F,Kk,Kj):
+                             y[q*Kk + k] = lse_j W[k,j] x[j*Kq + q].  num_states carries Kq.
+                             'complex-lse-sum' only (CKB_STEP_COMPLEX).                          */
   CKB_STEP_TABLE_DENSE = 8 /* a TABLE layer consumed fold-by-fold by an arity-1 DENSE layer, fused:
                              the dense block is applied to the V rows of the (F,V,Ki) table once
                              per step (batch-independent), giving a (F,V,Ko) table T2, and the

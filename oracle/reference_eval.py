@@ -297,6 +297,15 @@ class OracleCircuit(nn.Module):
             w = self._operand(self.param(s.params["weight"]))
             u = x.sum(dim=1)
             return self._reduce(lambda e: torch.einsum("fbi,foi->fbo", e, w), u)
+        if s.kind == "tensordot":
+            # TorchTensorDotLayer.forward, layers/optimized.py:287-300: (F, B, Kj*Kq) -> (F, B, Kq, Kj),
+            # contraction over j with weight (F, Kk, Kj), flattened back to (F, B, Kq*Kk)
+            w = self._operand(self.param(s.params["weight"]))
+            kq = int(s.config["kq"])
+            xs = x.squeeze(dim=1)
+            xs = xs.view(xs.shape[0], xs.shape[1], w.shape[2], kq).permute(0, 1, 3, 2)
+            y = self._reduce(lambda e: torch.einsum("fbqj,fkj->fbqk", e, w), xs)
+            return y.reshape(y.shape[0], y.shape[1], s.num_output_units)
         if s.kind == "tucker":
             # TorchTuckerLayer.forward, layers/optimized.py:89-103 (einsum spec :62-66)
             H, Ki, Ko = s.arity, s.num_input_units, s.num_output_units

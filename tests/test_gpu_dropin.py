@@ -185,3 +185,53 @@ def test_unsupported_layers_stay_on_the_reference_backend(cirkit, dev):
     x = torch.randint(0, 256, (8, 16)).to(dev)
     y = cc(x)
     assert y.shape == (8, 1, 1) and y.is_cuda and torch.isfinite(y).all()
+
+
+def test_squared_circuit_matches_reference(cirkit, dev):
+    """BASELINE.json configs[4] at small size through the drop-in route: c(x) under
+    'complex-lse-sum' and Z = integrate(c conj(c)) -- a batch-free circuit of constant, Hadamard and
+    TorchTensorDotLayers (layers/optimized.py:205-300) over K^2 units whose constants come out of
+    kron/einsum parameter graphs the reference evaluates -- both run on the complex CUDA kernels
+    and share their parameters.  log p(x) = 2 Re c(x) - Re Z and its gradients against the
+    reference in complex128 on the CPU (notebooks/sum-of-squares-circuits.ipynb cells 20-32)."""
+    import cirkit.symbolic.functional as SF
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    cplx = utils.Parameterization(dtype="complex", initialization="uniform")
+    sc = data_modalities.tabular_data(
+        "random-binary-tree", num_features=16,
+        input_layers={"name": "embedding", "args": {
+            "num_states": 12, "weight_factory": utils.parameterization_to_factory(cplx)}},
+        num_input_units=8, sum_product_layer="cp-t", num_sum_units=8, sum_weight_param=cplx)
+    zsc = SF.integrate(SF.multiply(sc, SF.conjugate(sc)))
+    torch.manual_seed(5)
+    ctx = PipelineContext(backend="b200", semiring="complex-lse-sum", fold=True, optimize=True)
+    c, z = ctx.compile(sc), ctx.compile(zsc)
+    assert type(c).__name__ == "B200TorchCircuit" and c._b200_runtime.is_complex
+    assert type(z).__name__ == "B200TorchCircuit", getattr(z, "_b200_reason", "")
+    assert any(s.kind == "tensordot" for s in z._b200_lowered.plan.steps)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        rctx = PipelineContext(backend="torch", semiring="complex-lse-sum", fold=True, optimize=True)
+        rc, rz = rctx.compile(sc), rctx.compile(zsc)
+    finally:
+        torch.set_default_dtype(prev)
+    rc.load_state_dict({k: v.to(torch.complex128 if v.is_complex() else torch.float64)
+                        for k, v in c.state_dict().items()})
+    c, z = c.to(dev), z.to(dev)
+    x = torch.randint(0, 12, (200, 16), generator=torch.Generator().manual_seed(2))
+    ll = 2.0 * c(x.to(dev)).real - z().real
+    llr = 2.0 * rc(x).real - rz().real
+    assert ll.shape == llr.shape
+    err = (ll.detach().double().cpu() - llr.detach()).abs().max().item()
+    assert err <= 5e-5, f"log-likelihood error {err:.3e}"
+    (-ll.mean()).backward()
+    (-llr.mean()).backward()
+    ref_params = dict(rc.named_parameters())
+    for name, p in c.named_parameters():
+        gr = ref_params[name].grad
+        err = (p.grad.cpu().to(gr.dtype) - gr).abs().max().item()
+        tol = max(2e-6, 1e-4 * gr.abs().max().item())
+        assert err <= tol, f"{name}: {err:.3e} > {tol:.3e}"

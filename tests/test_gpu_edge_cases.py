@@ -255,3 +255,41 @@ def test_integrating_an_embedding_raises(dev):
         some[0, 5] = True
         with pytest.raises(TypeError, match="Integration is not supported"):
             IntegrateQuery(cc)(x, integrate_vars=some)
+
+
+def test_effective_parameters_are_cached_between_no_grad_calls(dev):
+    """the reference re-runs every parameter node on every call
+    (parameters/parameter.py:180-188); here the second no_grad call on unchanged parameters
+    launches no parameter kernels and returns bit-identical values, an in-place update
+    invalidates the cache, and calls that record a graph always re-run the ops."""
+    from cirkit_b200 import B200Circuit, IntegrateQuery
+
+    g = Golden("qg8_cp_k4")
+    cc = B200Circuit(g.plan)
+    with torch.no_grad():
+        for p, v in zip(cc.leaves, g.leaves(torch.float32)):
+            p.copy_(v)
+    cc = cc.to(dev)
+    x = g.x().to(dev)
+    rt = cc.runtime
+    with torch.no_grad():
+        y0 = cc(x)
+        n0 = rt.last_launches
+        y1 = cc(x)
+        n1 = rt.last_launches
+        assert torch.equal(y0, y1) and n1 < n0, (n0, n1)
+        mask = torch.zeros(1, 64, dtype=torch.bool)
+        mask[0, :7] = True
+        m0 = IntegrateQuery(cc)(x, integrate_vars=mask)
+        assert torch.equal(IntegrateQuery(cc)(x, integrate_vars=mask), m0)
+        cc.leaves[1].add_(0.5)  # version bump -> ops re-run
+        y2 = cc(x)
+        assert rt.last_launches == n0 and not torch.equal(y2, y0)
+        rt.cache_parameters = False
+        cc(x)
+        assert rt.last_launches == n0
+        rt.cache_parameters = True
+    y3 = cc(x)  # grad mode: never cached
+    assert rt.last_launches == n0 and torch.equal(y3.detach(), y2)
+    (-y3.mean()).backward()
+    assert all(p.grad is not None for p in cc.leaves)
