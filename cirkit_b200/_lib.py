@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcirkit_b200.so")
 # ckb_step_kind / ckb_param_op_kind / ckb_dtype (keep in sync with include/cirkit_b200.h)
 STEP_TABLE, STEP_GAUSSIAN, STEP_CONSTANT, STEP_DENSE, STEP_MIXING, STEP_HADAMARD, STEP_KRONECKER, STEP_TUCKER = range(8)
 STEP_TENSORDOT = 9
+STEP_EXTERNAL = 10
 DENSE_CONCAT = 1
 STEP_ROWS64 = 2
 STEP_COMPLEX = 4

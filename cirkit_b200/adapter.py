@@ -154,6 +154,7 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
         TorchSumLayer,
     )
     from cirkit.backend.torch.layers.input import (
+        TorchInputLayer,
         TorchCategoricalLayer,
         TorchConstantValueLayer,
         TorchEmbeddingLayer,
@@ -238,9 +239,19 @@ def plan_from_torch(tc, *, allow_external_params: bool = True,
             kind = "hadamard"
         elif isinstance(m, TorchKroneckerLayer):
             kind = "kronecker"
+        elif isinstance(m, TorchInputLayer) and allow_external_params and semiring_names.get(m.semiring) == "lse-sum":
+            # per-step fallback: an input layer kind without a kernel (Binomial,
+            # Polynomial, Evidence, multivariate layers ...) is evaluated by the reference's own
+            # module with PyTorch on every call; its (F, B, K) output enters the arena as a
+            # differentiable external tensor, everything above it runs on the CUDA kernels
+            kind = "external"
+            params = {"output": ParamSpec(-1, [], (F, 0, int(m.num_output_units)), None)}
+            externals[(sid, "output")] = m
         else:
             raise UnsupportedCircuitError(f"step {sid}: no CUDA kernel for {type(m).__name__}")
-        if kind in ("categorical", "embedding", "gaussian"):
+        if kind == "external":
+            arity, k_in = 1, 0
+        elif kind in ("categorical", "embedding", "gaussian"):
             if m.num_variables != 1:
                 raise UnsupportedCircuitError(f"step {sid}: multivariate input layer")
             scope_idx = m.scope_idx.cpu().numpy().astype(np.int32).reshape(F)
@@ -316,8 +327,36 @@ def accelerate(tc, *, strict: bool = False):
 
     base = type(tc)
 
-    def _tensors(self):
-        ext = {k: p() for k, p in lowered.externals.items()}
+    def _tensors(self, x=None, mask=None):
+        """Leaf tensors + what the host evaluates per call: parameter graphs the plan does not
+        model (the reference's own TorchParameter) and the outputs of input layers without a
+        kernel (the reference's own layer module, gathered as LayerAddressBook.lookup does,
+        circuits.py:57-71; under an integration mask through IntegrateQuery._layer_fn)."""
+        from cirkit.backend.torch.layers.input import TorchInputLayer
+        from cirkit.backend.torch.queries import IntegrateQuery
+
+        ext = {}
+        for k, p in lowered.externals.items():
+            if not isinstance(p, TorchInputLayer):
+                ext[k] = p()
+                continue
+            if p.num_variables:
+                if x is None:
+                    raise ValueError(f"Expected some input 'x', as the circuit has scope '{self._scope}'")
+                if x.ndim != 2:
+                    raise ValueError(
+                        "The input to the circuit should have shape (B, D), "
+                        "where B is the batch size and D is the number of variables "
+                        "the circuit is defined on")
+                args = (x.to(p.scope_idx.device)[..., p.scope_idx].permute(1, 0, 2),)
+            else:
+                args = (1 if x is None else x.shape[0],)
+            if mask is not None:
+                m = mask if mask.ndim == 2 else mask.unsqueeze(0)
+                y = IntegrateQuery._layer_fn(p, *args, integrate_vars_mask=m.to(args[0].device) if p.num_variables else m)
+            else:
+                y = p(*args)
+            ext[k] = y
         return lowered.leaves, ext
 
     class B200Circuit(base):  # type: ignore[misc, valid-type]
@@ -328,7 +367,7 @@ def accelerate(tc, *, strict: bool = False):
                 raise ValueError(
                     f"Expected some input 'x', as the circuit has scope '{self._scope}'"
                 )
-            leaves, ext = _tensors(self)
+            leaves, ext = _tensors(self, x)
             y = runtime.evaluate(x, leaves, ext)  # (B, O, K)
             if not self._scope:
                 y = y.squeeze(dim=0)
@@ -342,11 +381,11 @@ def accelerate(tc, *, strict: bool = False):
             mask = _integrate_mask_of(module_fn)
             if module_fn is not None and mask is None:
                 return super().evaluate(x, module_fn)
-            leaves, ext = _tensors(self)
+            leaves, ext = _tensors(self, x, mask)
             return runtime.evaluate(x, leaves, ext, integrate_mask=mask).transpose(0, 1)
 
         def integrate_query(self, x, mask):
-            leaves, ext = _tensors(self)
+            leaves, ext = _tensors(self, x, mask)
             return runtime.evaluate(x, leaves, ext, integrate_mask=mask)
 
     B200Circuit.__name__ = f"B200{base.__name__}"

@@ -62,6 +62,8 @@ int gaussian_fwd(const ckb_step_desc_t& d, Ctx& c);
 int gaussian_bwd(const ckb_step_desc_t& d, Ctx& c);
 int constant_fwd(const ckb_step_desc_t& d, Ctx& c);
 int constant_bwd(const ckb_step_desc_t& d, Ctx& c);
+int external_fwd(const ckb_step_desc_t& d, Ctx& c);
+int external_bwd(const ckb_step_desc_t& d, Ctx& c);
 int hadamard_fwd(const ckb_step_desc_t& d, Ctx& c);
 int hadamard_bwd(const ckb_step_desc_t& d, Ctx& c);
 int kronecker_fwd(const ckb_step_desc_t& d, Ctx& c);

@@ -546,6 +546,40 @@ int constant_bwd(const ckb_step_desc_t& d, Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// EXTERNAL: an input layer the caller evaluated (per-step PyTorch fallback for layer kinds
+// without a kernel).  Forward: (F, B, K) activations -> arena block; backward: the gradient of
+// every output element, gathered from its consumers, back to the caller.
+// ------------------------------------------------------------------------------------------
+__global__ void external_bwd_kernel(GradSrc gs, float* __restrict__ gout, int64_t B, int K) {
+  const int f = blockIdx.y;
+  const int64_t total = B * K;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / K;
+    gout[(int64_t)f * total + idx] = pull_grad(gs, f, b, K, (int)(idx - b * K));
+  }
+}
+
+int external_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  const size_t bytes = (size_t)d.num_folds * c.B * d.k_out * 4;
+  CKB_CUDA_CHECK(cudaMemcpyAsync(c.arena + c.B * d.out_off, c.tensors[d.slot[0]], bytes,
+                                 cudaMemcpyDeviceToDevice, c.stream));
+  c.launches++;
+  return CKB_OK;
+}
+
+int external_bwd(const ckb_step_desc_t& d, Ctx& c) {
+  float* g = c.grads[d.slot[0]];
+  if (!g) return CKB_OK;
+  GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
+  const int bx = (int)min64(ceil_div(c.B * d.k_out, 256), 4 * kNumSMs);
+  external_bwd_kernel<<<dim3(max(bx, 1), d.num_folds), 256, 0, c.stream>>>(gs, g, c.B, d.k_out);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                        int64_t n, int splits) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;

@@ -78,9 +78,10 @@ static int check_step(const ckb_step_desc_t& d, int idx, int n_slots) {
         return CKB_ERR_INVALID;
       }
       break;
+    case CKB_STEP_EXTERNAL:
     case CKB_STEP_CONSTANT:
       if (d.slot[0] < 0) {
-        set_error("step %d: constant layer needs a value", idx);
+        set_error("step %d: constant / external layer needs a tensor", idx);
         return CKB_ERR_INVALID;
       }
       break;
@@ -257,6 +258,7 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
       case CKB_STEP_TABLE: rc = table_fwd(d, c); break;
       case CKB_STEP_GAUSSIAN: rc = gaussian_fwd(d, c); break;
       case CKB_STEP_CONSTANT: rc = constant_fwd(d, c); break;
+      case CKB_STEP_EXTERNAL: rc = external_fwd(d, c); break;
       case CKB_STEP_DENSE: rc = dense_fwd(d, c); break;
       case CKB_STEP_MIXING: rc = mixing_fwd(d, c); break;
       case CKB_STEP_HADAMARD: rc = hadamard_fwd(d, c); break;
@@ -295,6 +297,7 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
       case CKB_STEP_TABLE: rc = table_bwd(d, c); break;
       case CKB_STEP_GAUSSIAN: rc = gaussian_bwd(d, c); break;
       case CKB_STEP_CONSTANT: rc = constant_bwd(d, c); break;
+      case CKB_STEP_EXTERNAL: rc = external_bwd(d, c); break;
       case CKB_STEP_DENSE: rc = dense_bwd(d, c); break;
       case CKB_STEP_MIXING: rc = mixing_bwd(d, c); break;
       case CKB_STEP_HADAMARD: rc = hadamard_bwd(d, c); break;

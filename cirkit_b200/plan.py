@@ -30,7 +30,8 @@ from typing import Any, Callable, Sequence
 import numpy as np
 
 # Step kinds (names follow the reference layer classes they restate).
-INPUT_KINDS = ("categorical", "gaussian", "embedding", "constant")
+# "external": an input layer of a kind without a kernel, evaluated by the host per call (adapter only)
+INPUT_KINDS = ("categorical", "gaussian", "embedding", "constant", "external")
 INNER_KINDS = ("sum", "cpt", "mixing", "hadamard", "kronecker", "tucker", "tensordot")
 ALL_KINDS = INPUT_KINDS + INNER_KINDS
 
@@ -151,7 +152,7 @@ class CircuitPlan:
             if s.kind not in ALL_KINDS:
                 raise ValueError(f"step {sid}: unknown kind {s.kind!r}")
             if s.is_input:
-                if s.kind != "constant":
+                if s.kind not in ("constant", "external"):
                     if s.scope_idx is None or s.scope_idx.shape != (s.num_folds,):
                         raise ValueError(f"step {sid}: scope_idx must have shape (F,)")
             else:

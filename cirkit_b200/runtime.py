@@ -174,6 +174,7 @@ _KIND = {
     "embedding": L.STEP_TABLE,
     "gaussian": L.STEP_GAUSSIAN,
     "constant": L.STEP_CONSTANT,
+    "external": L.STEP_EXTERNAL,
     "sum": L.STEP_DENSE,
     "cpt": L.STEP_DENSE,
     "mixing": L.STEP_MIXING,
@@ -187,6 +188,7 @@ _PARAM_ORDER = {
     "embedding": ("weight",),
     "gaussian": ("mean", "stddev", "log_partition"),
     "constant": ("value",),
+    "external": ("output",),
     "sum": ("weight",),
     "cpt": ("weight",),
     "mixing": ("weight",),
@@ -464,6 +466,7 @@ class PlanRuntime:
         self.n_slots = n
         self.native_ops = [(b, b.native) for b in self.bindings if b.native is not None]
         self.reads_evidence = any(s.kind in ("categorical", "embedding", "gaussian") for s in plan.steps)
+        self.needs_batch = any(s.kind == "external" for s in plan.steps)
         self._states: dict[torch.device, _DeviceState] = {}
         self.last_launches = 0
         self.cache_parameters = True  # skip the parameter ops of no_grad calls on unchanged parameters
@@ -525,7 +528,9 @@ class PlanRuntime:
             want = torch.complex64 if b.is_complex else torch.float32
             if t.dtype != want:
                 t = t.to(want)
-            if tuple(t.shape) != b.src_shape:
+            if b.name == "output" and self.plan.steps[b.sid].kind == "external":
+                pass  # (F, B, K): the batch axis is only known per call
+            elif tuple(t.shape) != b.src_shape:
                 raise ValueError(
                     f"step {b.sid} parameter {b.name!r}: expected shape {b.src_shape}, got {tuple(t.shape)}"
                 )

@@ -61,6 +61,10 @@ typedef enum {
                              sample are Kq interleaved vectors, each contracted with W (F,Kk,Kj):
                              y[q*Kk + k] = lse_j W[k,j] x[j*Kq + q].  num_states carries Kq.
                              'complex-lse-sum' only (CKB_STEP_COMPLEX).                          */
+  CKB_STEP_EXTERNAL = 10, /* an input layer evaluated by the CALLER (a layer kind without a kernel here,
+                             e.g. Binomial / Polynomial / Evidence: layers/input.py:437, :815, :746):
+                             slot[0] holds its (F, B, Ko) output; forward copies it into the arena,
+                             backward gathers d(loss)/d(output) into grads[slot[0]] (same shape)   */
   CKB_STEP_TABLE_DENSE = 8 /* a TABLE layer consumed fold-by-fold by an arity-1 DENSE layer, fused:
                              the dense block is applied to the V rows of the (F,V,Ki) table once
                              per step (batch-independent), giving a (F,V,Ko) table T2, and the

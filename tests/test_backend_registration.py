@@ -73,19 +73,39 @@ def test_accelerate_leaves_unsupported_circuits_on_the_reference_path(reference)
 
     from cirkit_b200 import UnsupportedCircuitError, accelerate
 
-    sc = data_modalities.image_data(
-        (1, 4, 4), region_graph="quad-tree-2", input_layer="binomial", num_input_units=3,
-        sum_product_layer="cp", num_sum_units=3,
-        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
-    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    sc = _symbolic(reference)
+    tc = PipelineContext(backend="torch", semiring="sum-product", fold=True, optimize=True).compile(sc)
     cls = type(tc)
     x = torch.randint(0, 256, (3, 16))
     y = tc(x)
     with pytest.raises(UnsupportedCircuitError):
         accelerate(tc, strict=True)
     assert accelerate(tc) is tc and type(tc) is cls  # untouched: the reference evaluates it
-    assert "TorchBinomialLayer" in tc._b200_reason
+    assert "SumProductSemiring" in tc._b200_reason
     assert torch.equal(tc(x), y)
+
+
+def test_input_layers_without_a_kernel_become_external_steps(reference):
+    """layer kinds without a kernel (here Binomial, layers/input.py:437) keep the circuit
+    on the CUDA executor: the reference's own module evaluates that ONE layer with PyTorch per call
+    and its output enters the plan as a differentiable external tensor."""
+    from cirkit.pipeline import PipelineContext
+    from cirkit.templates import data_modalities, utils
+
+    from cirkit_b200 import accelerate
+
+    sc = data_modalities.image_data(
+        (1, 4, 4), region_graph="quad-tree-2", input_layer="binomial", num_input_units=3,
+        sum_product_layer="cp", num_sum_units=3,
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    cc = accelerate(tc, strict=True)
+    plan = cc._b200_lowered.plan
+    assert plan.steps[0].kind == "external" and (0, "output") in cc._b200_lowered.externals
+    assert type(cc._b200_lowered.externals[(0, "output")]).__name__ == "TorchBinomialLayer"
+    assert not cc._b200_runtime.reads_evidence and cc._b200_runtime.needs_batch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.randint(0, 256, (3, 16)))
 
 
 def test_complex_semiring_circuits_are_accelerated(reference):

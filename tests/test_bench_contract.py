@@ -39,8 +39,11 @@ def test_workloads_resolve():
     import bench
 
     sizes = {"qt28_cp_k64": (150401, 19259456), "qt28_cp_k32": (75201, 8026144),
-             "qt28_tucker_k64": (100225, 217845760), "pd32_cp_k128": (2864783, 299603982)}
+             "qt28_tucker_k64": (100225, 217845760), "pd32_cp_k128": (2864783, 299603982),
+             "rbt64_sos_k64": (8065, 1302592)}  # c(x) of the squared circuit (built by the reference's front-end)
     for name in bench.WORKLOADS:
+        if name == "rbt64_sos_k64" and not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "cirkit")):
+            continue
         plan = bench.load_plan(name).plan
         assert (plan.activation_units(), plan.parameter_elements()) == sizes[name], name
         assert bench.metric_name(name).startswith("samples/sec (fwd+bwd log-lik)")
