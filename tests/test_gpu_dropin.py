@@ -187,10 +187,19 @@ def test_layers_without_a_kernel_run_as_external_steps(cirkit, dev):
     gen = torch.Generator().manual_seed(3)
     x = torch.randint(0, 256, (70, 16), generator=gen)
     y, yr = cc(x.to(dev)), ref(x)
-    # the Binomial log-likelihoods themselves are the REFERENCE's fp32 PyTorch ops here (lgamma of
-    # counts up to 256: each of the 16 variables contributes ~|170| * 2^-23 of rounding), so the
-    # forward tolerance is the reference's own fp32-vs-fp64 gap for this layer, 5e-6 relative
-    _close(y, yr, rtol=5e-6, atol=1e-4)
+    # The Binomial log-likelihoods themselves are the REFERENCE's fp32 PyTorch ops here:
+    # lgamma(n + 1) = lgamma(256) ~ 1161 rounds to fp32 with the SAME error (up to 6e-5) in each of
+    # the 16 variables, so the circuit output carries a systematic ~1e-3 offset against fp64 that
+    # does not shrink under marginalisation.  Two checks: against fp64 with that absolute term, and
+    # against the reference's own fp32 evaluation on the same device at the fp32-vs-fp32 level.
+    _close(y, yr, rtol=5e-7, atol=2e-3)
+    from cirkit.pipeline import PipelineContext
+    torch.manual_seed(3)
+    ref32 = PipelineContext(backend="torch", semiring="lse-sum", fold=True, optimize=True).compile(sc)
+    ref32.load_state_dict(cc.state_dict())
+    ref32 = ref32.to(dev)
+    with torch.no_grad():
+        _close(y, ref32(x.to(dev)).double().cpu(), rtol=2e-6, atol=2e-4)
     (-y.mean()).backward()
     (-yr.mean()).backward()
     ref_grads = dict(ref.named_parameters())
@@ -201,8 +210,9 @@ def test_layers_without_a_kernel_run_as_external_steps(cirkit, dev):
         assert err <= tol, f"{name}: {err:.3e} > {tol:.3e}"
     mask = torch.rand(70, 16, generator=gen) < 0.3
     with torch.no_grad():
-        _close(IntegrateQuery(cc)(x.to(dev), integrate_vars=mask.to(dev)), IntegrateQuery(ref)(x, integrate_vars=mask),
-               rtol=5e-6, atol=1e-4)
+        ym = IntegrateQuery(cc)(x.to(dev), integrate_vars=mask.to(dev))
+        _close(ym, IntegrateQuery(ref)(x, integrate_vars=mask), rtol=5e-7, atol=2e-3)
+        _close(ym, IntegrateQuery(ref32)(x.to(dev), integrate_vars=mask.to(dev)).double().cpu(), rtol=2e-6, atol=2e-4)
 
 
 def test_unsupported_semirings_stay_on_the_reference_backend(cirkit, dev):
