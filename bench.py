@@ -150,7 +150,12 @@ def make_config(args, world, plan):
     return {
         "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
         "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
-        "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
+        "collectives": "all_gather(root ll)" + (
+            "" if args.no_grad_allreduce or world == 1 else
+            " + all_reduce(param grads, sum)" + (
+                " after the backward pass" if args.grad_chunks <= 0 else
+                f", overlapped: issued per stage of the backward pass (inner layers, then {args.grad_chunks} "
+                "fold chunks of the input table)")),
         "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
         "leaves": "seeded N(0,1), seed 1234",
         **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
@@ -356,9 +361,20 @@ def run_b200(args):
     flat_grads = None
     launches = 0
 
-    from cirkit_b200.distributed import BatchShardedCircuit, all_gather_rows
+    from cirkit_b200.distributed import BatchShardedCircuit, all_gather_rows_async
 
     sharded = BatchShardedCircuit(cc)  # this rank's replica: rows [rank*B, (rank+1)*B) of the job
+    if world > 1 and not args.no_grad_allreduce and args.grad_chunks > 0 and z_runtime is None:
+        sharded.overlap_gradient_sync(args.grad_chunks)
+    if args.stage_only:  # developer A/B: the staged backward pass without any collective
+        from cirkit_b200.distributed import OverlappedGradientReducer
+
+        class _NoReduce(OverlappedGradientReducer):
+            def __call__(self, pieces):
+                self.bytes += sum(t.numel() * 4 for t in pieces)
+
+        runtime.enable_gradient_stages(args.grad_chunks)
+        runtime.grad_sync = _NoReduce()
 
     def step(x):
         nonlocal launches
@@ -366,13 +382,16 @@ def run_b200(args):
             p.grad = None
         ll = cc(x)
         n = runtime.last_launches + (z_runtime.last_launches if z_runtime else 0)
+        # the one collective of the data path: all-gather of the root log-densities (runs on the
+        # communication stream next to the backward pass) ...
+        gathered = all_gather_rows_async(ll, world * B) if world > 1 else None
         loss = -ll.sum() / (world * B)  # this rank's share of the global-batch mean NLL
         loss.backward()
         launches = n + runtime.last_launches + (z_runtime.last_launches if z_runtime else 0)
         if world > 1:
-            # the one collective of the data path: all-gather of the root log-densities ...
-            all_gather_rows(ll, world * B)
+            gathered.wait()
             # ... and, for single-GPU gradient parity, the sum of the replicas' leaf gradients
+            # (already reduced stage by stage inside backward() when the overlap is on)
             if not args.no_grad_allreduce:
                 sharded.sync_gradients()
         return loss
@@ -390,8 +409,10 @@ def run_b200(args):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         step(dev_x[i % n_batches])
+    host_issue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps  # CPU time to enqueue a step
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -512,6 +533,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": float(ms2.item()) / args.steps,
                 "pipeline": "H2D of step i+1 on a copy stream overlaps step i (2 staging buffers)"},
         "gpu_launches": launches * args.steps,
+        "host_issue_ms_per_step": host_issue_ms,  # CPU time to enqueue one step (must stay below ms_per_step)
         "roofline": roofline,
     }
     if base is not None:
@@ -548,7 +570,11 @@ def main():
                     help="batch of the CPU arm (default: the per-GPU batch, i.e. the same config; "
                          "256 for the Tucker workload and 32 for pd32_cp_k128, whose full batch takes minutes per step)")
     ap.add_argument("--no-grad-allreduce", action="store_true")
+    ap.add_argument("--grad-chunks", type=int, default=4,
+                    help="N > 1: fold chunks of the input table in the staged backward pass whose "
+                         "gradient all-reduces overlap the remaining backward work (0: one all-reduce after backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--profile-out", default=None)
     ap.add_argument("--tc-flags", type=int, default=None,
                     help="developer switch: value for CKB_OPT_TC_FAST_MATH (3 = default kernels; "

@@ -15,6 +15,7 @@ __all__ = [
     "build_layout",
     "B200Circuit",
     "IntegrateQuery",
+    "SamplingQuery",
     "PlanRuntime",
     "accelerate",
     "plan_from_torch",
@@ -33,7 +34,7 @@ def __getattr__(name):
         from . import circuit
 
         return getattr(circuit, name)
-    if name in ("IntegrateQuery",):
+    if name in ("IntegrateQuery", "SamplingQuery"):
         from . import queries
 
         return getattr(queries, name)

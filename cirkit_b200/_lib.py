@@ -34,7 +34,10 @@ EXPORTS = (
     "ckb_transpose_mask",
     "ckb_plan_forward",
     "ckb_plan_backward",
+    "ckb_plan_param_ops",
     "ckb_plan_last_launches",
+    "ckb_sample_cdf_rows",
+    "ckb_plan_sample",
     "ckb_set_option",
     "ckb_debug_read",
     # experimental complex-semiring building blocks (not used by the plan executor)
@@ -73,6 +76,24 @@ class StepDesc(C.Structure):
         ("slot", C.c_int32 * 4),
         ("int_slot", C.c_int32),
         ("max_consumers", C.c_int32),
+    ]
+
+
+class SampleStep(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("num_folds", C.c_int32),
+        ("arity", C.c_int32),
+        ("k_in", C.c_int32),
+        ("k_out", C.c_int32),
+        ("num_states", C.c_int32),
+        ("flags", C.c_int32),
+        ("sel_row", C.c_int32),
+        ("in_sel_rows", C.c_void_p),
+        ("scope_var", C.c_void_p),
+        ("cdf", C.c_void_p),
+        ("p0", C.c_void_p),
+        ("p1", C.c_void_p),
     ]
 
 
@@ -123,8 +144,14 @@ def load():
     lib.ckb_plan_forward.restype = C.c_int
     lib.ckb_plan_backward.argtypes = [vp, i32, i32, i64, vp, i32, vp, i64, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, C.c_size_t, i32, vp]
     lib.ckb_plan_backward.restype = C.c_int
+    lib.ckb_plan_param_ops.argtypes = [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), vp]
+    lib.ckb_plan_param_ops.restype = C.c_int
     lib.ckb_plan_last_launches.argtypes = [vp]
     lib.ckb_plan_last_launches.restype = i64
+    lib.ckb_sample_cdf_rows.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+    lib.ckb_sample_cdf_rows.restype = C.c_int
+    lib.ckb_plan_sample.argtypes = [C.POINTER(SampleStep), i32, i64, i64, C.c_uint64, i64, i32, i32, vp, vp, vp, i32, i32, vp]
+    lib.ckb_plan_sample.restype = C.c_int
     lib.ckb_set_option.argtypes = [i32, i32]
     lib.ckb_set_option.restype = C.c_int
     lib.ckb_debug_read.argtypes = [vp, C.c_size_t]

@@ -307,6 +307,22 @@ def _integrate_mask_of(module_fn):
     return None
 
 
+def _sampling_args_of(module_fn):
+    """(num_samples, mixture_samples list) when `module_fn` is what the reference's own
+    `SamplingQuery` hands to `evaluate` -- `functools.partial(query._layer_fn, num_samples=n,
+    mixture_samples=lst)`, cirkit/backend/torch/queries.py:233-241 -- else None."""
+    from cirkit.backend.torch.queries import SamplingQuery
+
+    if (
+        isinstance(module_fn, functools.partial)
+        and getattr(module_fn.func, "__func__", None) is SamplingQuery._layer_fn
+        and not module_fn.args
+        and set(module_fn.keywords) == {"num_samples", "mixture_samples"}
+    ):
+        return module_fn.keywords["num_samples"], module_fn.keywords["mixture_samples"]
+    return None
+
+
 def accelerate(tc, *, strict: bool = False):
     """Re-route `tc(x)` to the CUDA runtime, in place; returns `tc`.
 
@@ -379,6 +395,14 @@ def accelerate(tc, *, strict: bool = False):
             # evaluation (queries.py:112-143).  Any other callback is arbitrary Python per layer
             # and runs on the reference's own executor, on the circuit's device.
             mask = _integrate_mask_of(module_fn)
+            sampling = _sampling_args_of(module_fn) if x is None else None
+            if sampling is not None and not lowered.externals:
+                # `SamplingQuery(circuit)(num_samples)` of the reference package: ancestral
+                # sampling on the device; the caller expects (O, K, N, D) and takes [0, 0]
+                # (queries.py:242-246)
+                samples, mixtures = runtime.sample(sampling[0], lowered.leaves)
+                sampling[1].extend(mixtures)
+                return samples.unsqueeze(0).unsqueeze(0)
             if module_fn is not None and mask is None:
                 return super().evaluate(x, module_fn)
             leaves, ext = _tensors(self, x, mask)
@@ -387,6 +411,11 @@ def accelerate(tc, *, strict: bool = False):
         def integrate_query(self, x, mask):
             leaves, ext = _tensors(self, x, mask)
             return runtime.evaluate(x, leaves, ext, integrate_mask=mask)
+
+        def sample_query(self, num_samples, *, seed=None):
+            if lowered.externals:
+                raise TypeError("Sampling needs every layer and parameter on the CUDA runtime")
+            return runtime.sample(num_samples, lowered.leaves, seed=seed)
 
     B200Circuit.__name__ = f"B200{base.__name__}"
     tc.__class__ = B200Circuit

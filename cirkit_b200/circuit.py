@@ -114,3 +114,7 @@ class B200Circuit(nn.Module):
 
     def integrate_query(self, x: Tensor, mask: Tensor) -> Tensor:
         return self.runtime.evaluate(x, list(self.leaves), integrate_mask=mask)
+
+    def sample_query(self, num_samples: int, *, seed: int | None = None) -> tuple[Tensor, list[Tensor]]:
+        """(samples (N, D), mixture_samples): see `PlanRuntime.sample`."""
+        return self.runtime.sample(num_samples, list(self.leaves), seed=seed)

@@ -551,8 +551,9 @@ static int launch_dense_bwd_small(const DenseArgs& a, int F, int splits, Ctx& c)
   return CKB_OK;
 }
 
-// backward, any shape: one warp per (fold, sample); dW through global atomics (slow path).
-__global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float* dW) {
+// backward, any shape, part 1: one warp per (fold, sample) writes du and keeps the row shift m[f,b]
+// for part 2.
+__global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float* mrow) {
   extern __shared__ __align__(16) float smem[];
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -571,6 +572,7 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
     float m = -INFINITY;
     for (int k = lane; k < a.Kred; k += 32) m = fmaxf(m, e[k]);
     m = clamp_max(warp_max(m));
+    if (mrow && lane == 0) mrow[(int64_t)f * a.B + b] = m;
     for (int k = lane; k < a.Kred; k += 32) e[k] = expf(e[k] - m);
     for (int o = lane; o < a.Ko; o += 32) {
       const float g = pull_grad(a.gs, f, b, a.Ko, o);
@@ -587,12 +589,73 @@ __global__ void dense_bwd_generic(DenseArgs a, int e_stride, int r_stride, float
         const int h = i / a.Ki;
         a.gin[(((int64_t)f * a.H + h) * a.B + b) * a.Ki + (i - h * a.Ki)] = du;
       }
-      if (dW)
-        for (int o = 0; o < a.Ko; ++o)
-          if (r[o] != 0.f) atomicAdd(&dW[((int64_t)f * a.Ko + o) * a.Kred + i], r[o] * e[i]);
     }
     __syncwarp();
   }
+}
+
+// part 2: dW[f,o,i] = sum_b r[b,o] e[b,i] with r = g exp(m - y), e = exp(u - m) rebuilt from the
+// stored row shifts.  A CTA owns a 32 x 64 tile of one fold's dW and walks the batch in order, a
+// thread owns 2 x 4 of its entries: no atomics, the sum over samples has one fixed order.
+constexpr int kDwTo = 32, kDwTi = 64, kDwTb = 32;
+__global__ void __launch_bounds__(256) dense_dw_generic(DenseArgs a, const float* __restrict__ mrow,
+                                                        float* __restrict__ dW) {
+  __shared__ float rs[kDwTb][kDwTo + 1];
+  __shared__ __align__(16) float es[kDwTb][kDwTi + 4];
+  const int f = blockIdx.z, o0 = blockIdx.y * kDwTo, i0 = blockIdx.x * kDwTi;
+  const int tid = threadIdx.x;
+  const int to = (tid >> 4) * 2, ti = (tid & 15) * 4;  // 16 x 16 threads -> 2 x 4 entries each
+  float acc[2][4] = {};
+  for (int64_t b0 = 0; b0 < a.B; b0 += kDwTb) {
+    for (int q = tid; q < kDwTb * kDwTo; q += 256) {
+      const int bb = q / kDwTo, o = o0 + q % kDwTo;
+      const int64_t b = b0 + bb;
+      float r = 0.f;
+      if (b < a.B && o < a.Ko) {
+        const float g = pull_grad(a.gs, f, b, a.Ko, o);
+        if (g != 0.f) r = g * expf(mrow[(int64_t)f * a.B + b] - a.y[((int64_t)f * a.B + b) * a.Ko + o]);
+      }
+      rs[bb][q % kDwTo] = r;
+    }
+    for (int q = tid; q < kDwTb * kDwTi; q += 256) {
+      const int bb = q / kDwTi, i = i0 + q % kDwTi;
+      const int64_t b = b0 + bb;
+      float e = 0.f;
+      if (b < a.B && i < a.Kred) {
+        float u;
+        if (a.concat) {
+          const int h = i / a.Ki;
+          u = in_row(a, f, h)[b * a.Ki + (i - h * a.Ki)];
+        } else {
+          u = 0.f;
+          for (int h = 0; h < a.H; ++h) u += in_row(a, f, h)[b * a.Ki + i];
+        }
+        e = expf(u - mrow[(int64_t)f * a.B + b]);
+      }
+      es[bb][q % kDwTi] = e;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int bb = 0; bb < kDwTb; ++bb) {
+      const float r0 = rs[bb][to], r1 = rs[bb][to + 1];
+      const float4 ev = *reinterpret_cast<const float4*>(&es[bb][ti]);
+      acc[0][0] = fmaf(r0, ev.x, acc[0][0]);
+      acc[0][1] = fmaf(r0, ev.y, acc[0][1]);
+      acc[0][2] = fmaf(r0, ev.z, acc[0][2]);
+      acc[0][3] = fmaf(r0, ev.w, acc[0][3]);
+      acc[1][0] = fmaf(r1, ev.x, acc[1][0]);
+      acc[1][1] = fmaf(r1, ev.y, acc[1][1]);
+      acc[1][2] = fmaf(r1, ev.z, acc[1][2]);
+      acc[1][3] = fmaf(r1, ev.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (o0 + to + p < a.Ko && i0 + ti + q < a.Kred)
+        dW[((int64_t)f * a.Ko + o0 + to + p) * a.Kred + i0 + ti + q] = acc[p][q];
 }
 
 static size_t run_dense_bwd_ws_default(int F, int H, int Ko, int Kred, int64_t B);
@@ -609,7 +672,7 @@ static size_t run_dense_bwd_ws_default(int F, int H, int Ko, int Kred, int64_t B
   if (Ko == 1 && Kred <= 32 * kKo1MaxPerLane) return (size_t)dense_ko1_blocks(F, B) * F * Kred * 4;
   const size_t tc = dense_tc_bwd_ws(F, H, Ko, Kred, B);
   if (Ko == 32 && Kred == 32 && H <= 2) return dense32_bwd_ws(F, B);
-  if (!dense_small_ok(H, Ko, Kred)) return tc;
+  if (!dense_small_ok(H, Ko, Kred)) return max64(tc, (size_t)F * B * 4);  // row shifts of the generic path
   int SW, splits;
   int64_t chunk;
   dense_bwd_config(F, Ko, Kred, B, SW, splits, chunk);
@@ -680,11 +743,24 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_bwd_generic,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  if (dW) CKB_CUDA_CHECK(cudaMemsetAsync(dW, 0, n * 4, c.stream));
+  float* mrow = nullptr;
+  if (dW) {
+    if (ws_bytes < (size_t)F * a.B * 4) {
+      set_error("dense_bwd: workspace too small (%zu < %zu)", ws_bytes, (size_t)F * a.B * 4);
+      return CKB_ERR_WORKSPACE;
+    }
+    mrow = (float*)ws;
+  }
   dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
-  dense_bwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride, r_stride, dW);
+  dense_bwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride, r_stride, mrow);
   CKB_LAUNCH_CHECK();
   c.launches++;
+  if (dW) {
+    dim3 g2(ceil_div(a.Kred, kDwTi), ceil_div(a.Ko, kDwTo), F);
+    dense_dw_generic<<<g2, 256, 0, c.stream>>>(a, mrow, dW);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+  }
   return CKB_OK;
 }
 

@@ -171,16 +171,19 @@ int mixing_fwd(const ckb_step_desc_t& d, Ctx& c) {
 }
 
 // r[o] = g[o] / S[o] with S[o] = exp(y[o] - m);  dx_h[o] = r[o] w[o,h] e_h[o];
-// dw[o,h] = sum_b r[o] e_h[o]  (CTA-level shared accumulators, then a split reduce).
+// dw[o,h] = sum_b r[o] e_h[o].  Deterministic: a lane owns the units k = lane, lane + 32, ... of
+// its warp's private accumulator block (no two threads ever add to the same word), the warps'
+// blocks are summed in warp order at the end, and the CTAs' slabs by reduce_partials.
 __global__ void mixing_bwd_kernel(const float* __restrict__ arena, const int64_t* __restrict__ in_rows,
                                   const float* __restrict__ w, const float* __restrict__ y, GradSrc gs,
                                   float* __restrict__ gin, float* __restrict__ dw_out, int64_t B, int H,
                                   int K, int64_t chunk) {
-  extern __shared__ float dw_s[];  // [K][H]
+  extern __shared__ float dw_s[];  // [nwarps][K][H]
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* wf = w + (int64_t)f * K * H;
-  for (int i = threadIdx.x; i < K * H; i += blockDim.x) dw_s[i] = 0.f;
+  float* mine = dw_s + (size_t)warp * K * H;
+  for (int i = threadIdx.x; i < nwarps * K * H; i += blockDim.x) dw_s[i] = 0.f;
   __syncthreads();
   const int64_t b_begin = (int64_t)blockIdx.x * chunk, b_end = min(B, b_begin + chunk);
   for (int64_t b = b_begin + warp; b < b_end; b += nwarps) {
@@ -196,14 +199,18 @@ __global__ void mixing_bwd_kernel(const float* __restrict__ arena, const int64_t
       for (int h = 0; h < H; ++h) {
         const float e = expf(arena[B * in_rows[f * H + h] + b * K + k] - m);
         gin[(((int64_t)f * H + h) * B + b) * K + k] = r * wf[k * H + h] * e;
-        if (dw_out) atomicAdd(&dw_s[k * H + h], r * e);
+        if (dw_out) mine[k * H + h] += r * e;
       }
     }
   }
   __syncthreads();
   if (dw_out) {
     float* o = dw_out + ((int64_t)blockIdx.x * gridDim.y + f) * K * H;
-    for (int i = threadIdx.x; i < K * H; i += blockDim.x) o[i] = dw_s[i];
+    for (int i = threadIdx.x; i < K * H; i += blockDim.x) {
+      float acc = 0.f;
+      for (int q = 0; q < nwarps; ++q) acc += dw_s[(size_t)q * K * H + i];
+      o[i] = acc;
+    }
   }
 }
 
@@ -235,14 +242,16 @@ int mixing_bwd(const ckb_step_desc_t& d, Ctx& c) {
     }
     out = (float*)c.ws;
   }
-  const size_t smem = (size_t)d.k_out * d.arity * 4;
+  int nwarps = 8;  // one private (K, H) accumulator block per warp
+  while (nwarps > 1 && (size_t)nwarps * d.k_out * d.arity * 4 > 48 * 1024) nwarps >>= 1;
+  const size_t smem = (size_t)nwarps * d.k_out * d.arity * 4;
   if (smem > 48 * 1024) {
     set_error("mixing_bwd: K*H = %d*%d exceeds the shared accumulator", d.k_out, d.arity);
     return CKB_ERR_UNSUPPORTED;
   }
   GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
   dim3 grid(splits, d.num_folds);
-  mixing_bwd_kernel<<<grid, 256, smem, c.stream>>>(c.arena, d.in_rows, c.tensors[d.slot[0]],
+  mixing_bwd_kernel<<<grid, 32 * nwarps, smem, c.stream>>>(c.arena, d.in_rows, c.tensors[d.slot[0]],
                                                    c.arena + c.B * d.out_off, gs,
                                                    c.garena + c.B * d.gin_off, out, c.B, d.arity,
                                                    d.k_out, chunk);

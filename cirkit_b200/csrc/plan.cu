@@ -228,6 +228,40 @@ static int make_ctx(ckb_plan_t* plan, int32_t s0, int32_t s1, int64_t batch, con
   return CKB_OK;
 }
 
+// Parameter ops [o0, o1): forward in list order, backward in reverse.  The ops are independent of
+// each other except that a logsumexp op ADDS to the gradient its table op has written (list
+// order: lse first), so a caller-chosen sub-range must keep such a pair together.
+static int run_param_ops(ckb_plan_t* plan, int o0, int o1, bool bwd, Ctx& c) {
+  const ckb_param_op_t* ops = plan->ops.data();
+  // softmaxes go out as one batch
+  if (int rc = multi_softmax(ops + o0, o1 - o0, bwd, c)) return rc;
+  if (!bwd) {
+    for (int i = o0; i < o1; ++i) {
+      const ckb_param_op_t& op = ops[i];
+      if (op.kind == CKB_POP_CONJ) {
+        if (int rc = complex_conj(c.tensors[op.src], c.tensors[op.dst], op.rows * op.cols, c)) return rc;
+      } else if (op.kind != CKB_POP_SOFTMAX) {
+        if (int rc = param_op_fwd(op, c)) return rc;
+      }
+    }
+    return CKB_OK;
+  }
+  for (int i = o1 - 1; i >= o0; --i) {
+    const ckb_param_op_t& op = ops[i];
+    if (op.kind == CKB_POP_CONJ) {
+      if (c.grads[op.src] == nullptr) continue;
+      if (c.grads[op.dst] == nullptr) {
+        set_error("conj op: gradient of slot %d requested but slot %d has none", op.src, op.dst);
+        return CKB_ERR_INVALID;
+      }
+      if (int rc = complex_conj(c.grads[op.dst], c.grads[op.src], op.rows * op.cols, c)) return rc;
+    } else if (op.kind != CKB_POP_SOFTMAX) {
+      if (int rc = param_op_bwd(op, c)) return rc;
+    }
+  }
+  return CKB_OK;
+}
+
 int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
                      const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
                      float* const* tensors, float* arena, void* workspace, size_t workspace_bytes,
@@ -236,17 +270,8 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
   if (int rc = make_ctx(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows,
                         tensors, nullptr, arena, nullptr, workspace, workspace_bytes, stream, c))
     return rc;
-  if (flags & CKB_RUN_PARAM_OPS) {
-    // ops are independent of each other (one per parameter): softmaxes go out as one batch
-    if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), false, c)) return rc;
-    for (const ckb_param_op_t& op : plan->ops) {
-      if (op.kind == CKB_POP_CONJ) {
-        if (int rc = complex_conj(c.tensors[op.src], c.tensors[op.dst], op.rows * op.cols, c)) return rc;
-      } else if (op.kind != CKB_POP_SOFTMAX) {
-        if (int rc = param_op_fwd(op, c)) return rc;
-      }
-    }
-  }
+  if (flags & CKB_RUN_PARAM_OPS)
+    if (int rc = run_param_ops(plan, 0, (int)plan->ops.size(), false, c)) return rc;
   for (int i = step_begin; i < step_end; ++i) {
     const ckb_step_desc_t& d = plan->steps[i];
     int rc = CKB_OK;
@@ -307,21 +332,25 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
     }
     if (rc != CKB_OK) return rc;
   }
-  if (flags & CKB_RUN_PARAM_OPS) {
-    if (int rc = multi_softmax(plan->ops.data(), (int)plan->ops.size(), true, c)) return rc;
-    for (auto it = plan->ops.rbegin(); it != plan->ops.rend(); ++it) {
-      if (it->kind == CKB_POP_CONJ) {
-        if (c.grads[it->src] == nullptr) continue;
-        if (c.grads[it->dst] == nullptr) {
-          set_error("conj op: gradient of slot %d requested but slot %d has none", it->src, it->dst);
-          return CKB_ERR_INVALID;
-        }
-        if (int rc = complex_conj(c.grads[it->dst], c.grads[it->src], it->rows * it->cols, c)) return rc;
-      } else if (it->kind != CKB_POP_SOFTMAX) {
-        if (int rc = param_op_bwd(*it, c)) return rc;
-      }
-    }
+  if (flags & CKB_RUN_PARAM_OPS)
+    if (int rc = run_param_ops(plan, 0, (int)plan->ops.size(), true, c)) return rc;
+  plan->last_launches = c.launches;
+  return CKB_OK;
+}
+
+int ckb_plan_param_ops(ckb_plan_t* plan, int32_t op_begin, int32_t op_end, int32_t backward,
+                       float* const* tensors, float* const* grads, void* stream) {
+  if (plan == nullptr || tensors == nullptr || op_begin < 0 || op_end > (int)plan->ops.size() ||
+      op_begin > op_end || (backward && grads == nullptr)) {
+    set_error("ckb_plan_param_ops: bad plan / range / tables");
+    return CKB_ERR_INVALID;
   }
+  Ctx c{};
+  c.B = 1;
+  c.tensors = tensors;
+  c.grads = grads;
+  c.stream = (cudaStream_t)stream;
+  if (int rc = run_param_ops(plan, op_begin, op_end, backward != 0, c)) return rc;
   plan->last_launches = c.launches;
   return CKB_OK;
 }

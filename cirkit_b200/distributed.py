@@ -38,15 +38,34 @@ def _world(group) -> tuple[int, int]:
     return dist.get_world_size(group), dist.get_rank(group)
 
 
+class _GatheredRows:
+    """Handle of an all-gather in flight: `wait()` returns the global tensor."""
+
+    def __init__(self, work, finish):
+        self._work, self._finish = work, finish
+
+    def wait(self) -> Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self._finish()
+
+
 def all_gather_rows(local: Tensor, num_rows: int, group=None) -> Tensor:
     """Concatenate the row blocks of all ranks (the blocks of `shard_rows(num_rows, ...)`) into
     the global (num_rows, ...) tensor, on every rank.  One collective; blocks that are one row
     short are padded for the exchange and trimmed afterwards."""
+    return all_gather_rows_async(local, num_rows, group).wait()
+
+
+def all_gather_rows_async(local: Tensor, num_rows: int, group=None) -> _GatheredRows:
+    """`all_gather_rows` issued asynchronously (on the process group's communication stream for
+    NCCL): work enqueued afterwards, e.g. the backward pass, does not wait for the exchange."""
     world, rank = _world(group)
     if world == 1:
         if local.shape[0] != num_rows:
             raise ValueError(f"expected {num_rows} rows, got {local.shape[0]}")
-        return local
+        return _GatheredRows(None, lambda: local)
     begin, end = shard_rows(num_rows, world, rank)
     if local.shape[0] != end - begin:
         raise ValueError(f"rank {rank} holds {local.shape[0]} rows, its block has {end - begin}")
@@ -56,14 +75,18 @@ def all_gather_rows(local: Tensor, num_rows: int, group=None) -> Tensor:
     if send.shape[0] < rows_max:  # uneven split: pad to the common block size
         send = torch.cat([send, send.new_zeros((rows_max - send.shape[0], *tail))])
     recv = send.new_empty((world * rows_max, *tail))
-    dist.all_gather_into_tensor(recv, send, group=group)
-    if num_rows == world * rows_max:
-        return recv
-    blocks = []
-    for r in range(world):
-        b, e = shard_rows(num_rows, world, r)
-        blocks.append(recv[r * rows_max : r * rows_max + (e - b)])
-    return torch.cat(blocks)
+    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
+
+    def finish() -> Tensor:
+        if num_rows == world * rows_max:
+            return recv
+        blocks = []
+        for r in range(world):
+            b, e = shard_rows(num_rows, world, r)
+            blocks.append(recv[r * rows_max : r * rows_max + (e - b)])
+        return torch.cat(blocks)
+
+    return _GatheredRows(work, finish)
 
 
 def _flat_gradient(params: list, flat: Tensor | None) -> Tensor | None:
@@ -120,6 +143,50 @@ def all_reduce_gradients(params: Iterable[Tensor], *, average: bool = False, gro
     return total
 
 
+class OverlappedGradientReducer:
+    """Sums gradient pieces over the ranks while the backward pass is still running.
+
+    The CUDA runtime calls it once per stage of its staged backward pass
+    (`PlanRuntime.enable_gradient_stages`) with the slices of the flat gradient buffer that have
+    just become final.  Each slice goes out as an asynchronous all-reduce: the process group's
+    communication stream waits for the kernels enqueued so far on the compute stream and runs
+    next to the stages that follow; `finish()` (end of the backward pass) makes the compute stream
+    wait for all of them.  Only the last group's collective is exposed."""
+
+    def __init__(self, group=None, average: bool = False) -> None:
+        self.group = group
+        self.average = average
+        self._works: list = []
+        self._pieces: list[Tensor] = []
+        self.bytes = 0
+
+    def __call__(self, pieces: Iterable[Tensor]) -> None:
+        world, _ = _world(self.group)
+        for t in pieces:
+            if t.numel() == 0:
+                continue
+            self.bytes += t.numel() * t.element_size()
+            if world > 1:
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                self._pieces.append(t)
+
+    def finish(self) -> int:
+        world, _ = _world(self.group)
+        for w in self._works:
+            w.wait()
+        if self.average and world > 1:
+            for t in self._pieces:
+                t.div_(world)
+        self._works.clear()
+        self._pieces.clear()
+        n, self.bytes = self.bytes, 0
+        return n
+
+
+def _runtime_of(circuit):
+    return getattr(circuit, "runtime", None) or getattr(circuit, "_b200_runtime", None)
+
+
 class BatchShardedCircuit(nn.Module):
     """A replica of `circuit` that evaluates this rank's rows of a global batch.
 
@@ -161,8 +228,26 @@ class BatchShardedCircuit(nn.Module):
     def loss(self, x_local: Tensor, num_rows: int) -> Tensor:
         return -self.circuit(x_local).sum() / num_rows
 
+    def overlap_gradient_sync(self, chunks: int = 4, *, average: bool = False,
+                              bucket_bytes: int = 8 << 20) -> bool:
+        """Sum the parameter gradients over the ranks INSIDE the backward pass, stage by stage
+        (see `OverlappedGradientReducer`); `sync_gradients()` then only reports the bytes.  Returns
+        False when the circuit has no CUDA runtime or its plan has per-sample inputs from PyTorch
+        layers (external steps), in which case `sync_gradients()` keeps doing the collective."""
+        rt = _runtime_of(self.circuit)
+        if rt is None or not hasattr(rt, "enable_gradient_stages") or rt.needs_batch or rt.is_complex:
+            return False
+        rt.enable_gradient_stages(chunks, bucket_bytes)
+        rt.grad_sync = OverlappedGradientReducer(self.group, average)
+        return True
+
     def sync_gradients(self, *, average: bool = False) -> int:
-        flat = getattr(getattr(self.circuit, "runtime", None), "last_flat_grad", None)
+        rt = _runtime_of(self.circuit)
+        if rt is not None and getattr(rt, "grad_sync", None) is not None and rt.last_synced_bytes:
+            if average != rt.grad_sync.average:
+                raise ValueError("overlap_gradient_sync was set up with a different `average`")
+            return rt.last_synced_bytes  # already reduced inside the backward pass
+        flat = getattr(rt, "last_flat_grad", None)
         return all_reduce_gradients(self.circuit.parameters(), average=average, group=self.group, flat=flat)
 
     def broadcast_parameters(self, src: int = 0) -> None:
@@ -170,6 +255,6 @@ class BatchShardedCircuit(nn.Module):
         if self.world_size > 1:
             for p in self.circuit.parameters():
                 dist.broadcast(p.data, src=src, group=self.group)
-            rt = getattr(self.circuit, "runtime", None)
+            rt = _runtime_of(self.circuit)
             if rt is not None and hasattr(rt, "invalidate_parameter_cache"):
                 rt.invalidate_parameter_cache()  # `.data` writes do not bump the version counter

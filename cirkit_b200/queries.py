@@ -1,4 +1,4 @@
-"""Integration (marginal) queries, mirroring `cirkit.backend.torch.queries.IntegrateQuery`
+"""Integration (marginal) and sampling queries, mirroring `cirkit.backend.torch.queries.IntegrateQuery`
 (cirkit/backend/torch/queries.py:19-184): same constructor, call signature, mask formats and
 error messages; the per-layer `torch.where(mask, layer.integrate(), output)` of `_layer_fn`
 (:112-143) is folded into the input-layer kernels (the mask selects, per sample and variable,
@@ -69,3 +69,26 @@ class IntegrateQuery:
             if idxs:
                 mask[i, idxs] = True
         return mask
+
+
+class SamplingQuery:
+    """Mirror of `cirkit.backend.torch.queries.SamplingQuery` (queries.py:187-275): same
+    constructor check, call signature and errors.  `query(num_samples)` returns
+    `(samples, mixture_samples)` with samples of shape (num_samples, D) drawn from the joint
+    distribution of the circuit by ancestral sampling on the device
+    (`csrc/sampling_kernels.cu`); see `PlanRuntime.sample` for the form of `mixture_samples`."""
+
+    def __init__(self, circuit) -> None:
+        props = getattr(circuit, "properties", None)
+        if props is not None and (not props.smooth or not props.decomposable):
+            raise ValueError(
+                f"The circuit to sample from must be smooth and decomposable, but found {props}"
+            )
+        if not hasattr(circuit, "sample_query"):
+            raise TypeError("SamplingQuery needs a circuit evaluated by cirkit_b200")
+        self._circuit = circuit
+
+    def __call__(self, num_samples: int = 1, *, seed: int | None = None):
+        if num_samples <= 0:
+            raise ValueError("The number of samples must be a positive number")
+        return self._circuit.sample_query(num_samples, seed=seed)

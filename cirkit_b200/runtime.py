@@ -209,6 +209,17 @@ class ExecStep:
     out_sid: int  # plan step whose arena block / consumer lists it uses
     slots: list = field(default_factory=list)
     scratch: tuple | None = None  # (slot, shape) of a runtime-owned buffer (TABLE_DENSE: T2)
+    folds: tuple | None = None  # (f0, f1): the step covers this fold range only (staged backward)
+
+
+@dataclass
+class GradStage:
+    """One stage of a staged backward pass (`PlanRuntime.enable_gradient_stages`): the steps and
+    parameter ops after which a group of parameter gradients is final and may be all-reduced."""
+
+    steps: tuple  # [begin, end) in the "fused_sync" execution plan
+    ops: tuple  # [begin, end) in that plan's parameter-op list
+    pieces: list  # (binding index, fold begin, fold end) of the gradients that become final
 
 
 def _rows64(lay, sid: int) -> bool:
@@ -294,6 +305,28 @@ class _DeviceState:
         # buffers in `eff` (and the logsumexp buffers of the masked plan) were last computed from
         self.param_key: tuple | None = None
         self.lse_key: tuple | None = None
+        # SamplingQuery: CDF buffers per step (valid for sample_key) and the selection-arena tables
+        self.cdf: dict[int, Tensor] = {}
+        self.sample_key: tuple | None = None
+        self._sampling: dict | None = None
+
+    def sampling_tables(self) -> dict:
+        """Selection arena of the sampler: one row per (step, fold); per inner step the rows of
+        its inputs as a device (F*H) int32 table."""
+        if self._sampling is None:
+            plan = self.rt.plan
+            row0 = np.concatenate([[0], np.cumsum([s.num_folds for s in plan.steps])]).astype(np.int64)
+            in_rows = []
+            for s in plan.steps:
+                if s.is_input:
+                    in_rows.append(None)
+                    continue
+                r = row0[s.in_step.astype(np.int64)] + s.in_fold.astype(np.int64)  # (F, H)
+                t = torch.from_numpy(np.ascontiguousarray(r.astype(np.int32))).to(self.device)
+                self.keep.append(t)
+                in_rows.append(t.data_ptr())
+            self._sampling = {"row0": row0, "rows": int(row0[-1]), "in_rows": in_rows}
+        return self._sampling
 
     def grad_buffer(self, slot: int) -> Tensor:
         g = self.eff_grad.get(slot)
@@ -317,7 +350,8 @@ class _DeviceState:
             t_out, t_first = self.tables[es.out_sid], self.tables[es.sids[0]]
             d = descs[i]
             d.kind = es.kind
-            d.num_folds, d.arity = s.num_folds, s.arity
+            f0, f1 = es.folds if es.folds is not None else (0, s.num_folds)
+            d.num_folds, d.arity = f1 - f0, s.arity
             d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
             d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
             if _rows64(lay, es.out_sid):
@@ -330,11 +364,13 @@ class _DeviceState:
             if s.kind == "tensordot":
                 d.num_states = int(s.config["kq"])  # vectors interleaved in a sample row
             d.gin_h = int(lay.gin_h[es.out_sid])
-            d.out_off = int(lay.out_off[es.out_sid])
+            d.out_off = int(lay.out_off[es.out_sid]) + f0 * s.num_output_units
             d.gin_off = int(lay.gin_off[es.out_sid])
             d.in_rows = t_out["in_rows"] if es.kind != STEP_TABLE_DENSE else None
-            d.scope_var = t_first["scope_var"]
-            d.cons_ptr = t_out["cons_ptr"]
+            # a fold range of an input step: the per-fold tables start at f0 (int32 entries; the
+            # CSR values index cons_rows absolutely)
+            d.scope_var = t_first["scope_var"] + 4 * f0 if t_first["scope_var"] else None
+            d.cons_ptr = t_out["cons_ptr"] + 4 * f0
             d.cons_rows = t_out["cons_rows"]
             for j in range(4):
                 d.slot[j] = es.slots[j] if j < len(es.slots) else -1
@@ -345,8 +381,11 @@ class _DeviceState:
         # to the logits gradient the table op has written by then
         op_list = [(L.POP_LSE_ROWS, src, dst, rows, cols, 0, 0.0, 0.0)
                    for src, dst, rows, cols in (rt.lse_ops if which == "masked" else [])]
-        op_list += [(kind, b.src_slot, b.dst_slot, rows, cols, aux, a, bb)
-                    for b, (kind, rows, cols, aux, a, bb) in rt.native_ops]
+        if which in rt.sync_ops:
+            op_list += rt.sync_ops[which]
+        else:
+            op_list += [(kind, b.src_slot, b.dst_slot, rows, cols, aux, a, bb)
+                        for b, (kind, rows, cols, aux, a, bb) in rt.native_ops]
         ops = (L.ParamOp * max(1, len(op_list)))()
         for i, (kind, src, dst, rows, cols, aux, a, bb) in enumerate(op_list):
             ops[i].kind, ops[i].src, ops[i].dst = kind, src, dst
@@ -362,6 +401,9 @@ class _DeviceState:
 
     def workspace(self, which: str, batch: int) -> Tensor:
         need = int(self.lib.ckb_plan_workspace_bytes(self.handle(which), batch))
+        if which + "_sync" in self.rt.exec_plans:
+            # a fold chunk is a smaller launch and may be cut into more split-K slabs
+            need = max(need, int(self.lib.ckb_plan_workspace_bytes(self.handle(which + "_sync"), batch)))
         if self.ws is None or self.ws.numel() < need:
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self.ws
@@ -473,6 +515,118 @@ class PlanRuntime:
         self.keep_arena = False
         self.last_arena: Tensor | None = None
         self.last_flat_grad: Tensor | None = None  # flat buffer behind the last backward's gradients
+        # staged backward (data-parallel overlap, see enable_gradient_stages)
+        self.aliases: dict[int, tuple] = {}  # slot -> (base slot, float offset) into the same buffer
+        self.sync_ops: dict[str, list] = {}
+        self.grad_stages: dict[str, list] = {}  # execution plan -> [GradStage] in backward order
+        self.grad_sync = None  # callable(list of gradient tensors) with a .finish() method
+        self.last_synced_bytes = 0
+
+    # ------------------------------------------------------------------ staged backward
+    def enable_gradient_stages(self, chunks: int = 4, bucket_bytes: int = 8 << 20) -> bool:
+        """Prepare a backward pass that finishes the parameter gradients GROUP BY GROUP, so that a
+        data-parallel wrapper can all-reduce one group while the next is still being computed
+        ("bottom layers hold most of the bytes and finish last, so bucket
+        top-down").  The inner layers go first, in backward order, cut into stages of at least
+        `bucket_bytes` of gradients (each stage = some steps + the parameter ops of their
+        weights); the large input tables (Categorical / Embedding, alone or fused with their
+        dense sum: the bulk of the parameters, and last in the backward pass) follow in `chunks`
+        fold ranges, each with the parameter ops of its slice.  The stages live in extra
+        execution plans ("fused_sync", "plain_sync") used by the backward pass only while
+        `grad_sync` is set; values are bit-equal to the unstaged pass (same kernels, same order
+        within every fold).  Returns False (nothing changes) for complex plans and plans with
+        per-sample PyTorch inputs."""
+        if self.grad_stages:
+            return True
+        if self.is_complex or self.needs_batch:
+            return False
+        bidx = {id(b): i for i, b in enumerate(self.bindings)}
+        by_sid: dict[int, list] = {}
+        for b in self.bindings:
+            by_sid.setdefault(b.sid, []).append(b)
+
+        def gbytes(es: ExecStep) -> int:
+            return sum(4 * int(np.prod(b.src_shape)) for sid in es.sids for b in by_sid.get(sid, []))
+
+        def op_of(b, src=None, dst=None, rows=None):
+            kind, r, cols, aux, a, bb = b.native
+            return (kind, b.src_slot if src is None else src, b.dst_slot if dst is None else dst,
+                    r if rows is None else rows, cols, aux, a, bb)
+
+        n = self.n_slots
+
+        def alias(base: int, off: int) -> int:
+            nonlocal n
+            if off == 0:
+                return base
+            self.aliases[n] = (base, off)
+            n += 1
+            return n - 1
+
+        for which in ("fused", "plain"):
+            base = self.exec_plans[which]
+            if which == "fused" and not self.table_pairs:
+                continue
+
+            def chunkable(es: ExecStep) -> bool:
+                if es.kind not in (STEP_TABLE_DENSE, L.STEP_TABLE) or gbytes(es) < bucket_bytes:
+                    return False
+                bs = [b for sid in es.sids for b in by_sid.get(sid, [])]
+                return self.plan.steps[es.out_sid].num_folds >= chunks and all(
+                    b.native is not None and b.spec.fold_idx is None for b in bs)
+
+            big = [es for es in base if chunkable(es)] if chunks > 1 else []
+            rest = [es for es in base if not any(es is t for t in big)]
+            steps: list[ExecStep] = []
+            ops: list[tuple] = []
+            chunk_stages = []
+            for c in range(chunks if big else 0):
+                s0, o0, pieces = len(steps), len(ops), []
+                for es in big:
+                    F = self.plan.steps[es.out_sid].num_folds
+                    f0, f1 = c * F // chunks, (c + 1) * F // chunks
+                    slots = []
+                    for slot in es.slots:
+                        owner = [b for sid in es.sids for b in by_sid.get(sid, []) if b.dst_slot == slot]
+                        if owner:
+                            (b,) = owner
+                            src = alias(b.src_slot, f0 * int(np.prod(b.src_shape[1:])))
+                            dst = alias(b.dst_slot, f0 * int(np.prod(b.eff_shape[1:])))
+                            ops.append(op_of(b, src, dst, b.native[1] // F * (f1 - f0)))
+                            pieces.append((bidx[id(b)], f0, f1))
+                            slots.append(dst)
+                        elif es.scratch is not None and slot == es.scratch[0]:
+                            slots.append(alias(slot, f0 * int(np.prod(es.scratch[1][1:]))))
+                        else:
+                            slots.append(slot)
+                    steps.append(ExecStep(es.kind, f"{es.label}[{f0}:{f1}]", es.sids, es.out_sid, slots,
+                                          scratch=es.scratch, folds=(f0, f1)))
+                chunk_stages.append(GradStage((s0, len(steps)), (o0, len(ops)), pieces))
+            # the other steps keep their order; stages are cut walking them backwards
+            n_big = len(steps)
+            steps += rest
+            stages, hi, acc = [], len(steps), 0
+            for i in range(len(steps) - 1, n_big - 1, -1):
+                acc += gbytes(steps[i])
+                if acc >= bucket_bytes or i == n_big:
+                    o0, pieces = len(ops), []
+                    for es in steps[i:hi]:
+                        for sid in es.sids:
+                            for b in by_sid.get(sid, []):
+                                if b.native is not None:
+                                    ops.append(op_of(b))
+                                pieces.append((bidx[id(b)], 0, b.src_shape[0]))
+                    if pieces or not stages:
+                        stages.append(GradStage((i, hi), (o0, len(ops)), pieces))
+                    else:  # steps without parameters: extend the previous stage downwards
+                        last = stages[-1]
+                        stages[-1] = GradStage((i, last.steps[1]), last.ops, last.pieces)
+                    hi, acc = i, 0
+            self.exec_plans[which + "_sync"] = steps
+            self.grad_stages[which] = stages + chunk_stages[::-1]
+            self.sync_ops[which + "_sync"] = ops
+        self.n_slots = n
+        return True
 
     def invalidate_parameter_cache(self) -> None:
         """Forget the cached effective parameters (call after changing parameter storage behind
@@ -536,6 +690,129 @@ class PlanRuntime:
                 )
             out.append(t.resolve_conj().contiguous() if t.is_complex() else t.contiguous())
         return out
+
+    # ------------------------------------------------------------------ sampling
+    _SAMPLE_KINDS = ("categorical", "gaussian", "sum", "cpt", "mixing", "hadamard", "kronecker", "tucker")
+
+    def sample(self, num_samples: int, leaves: Sequence[Tensor], externals: dict | None = None, *,
+               seed: int | None = None, return_mixtures: bool = True,
+               chunk: int = 1 << 16) -> tuple[Tensor, list[Tensor]]:
+        """SamplingQuery (cirkit/backend/torch/queries.py:187-275) by ancestral sampling on the
+        device (csrc/sampling_kernels.cu).  Returns (samples (N, D), mixture_samples): the latter
+        holds, per sum-type layer in plan order, an (F, N) int32 tensor with the mixture component
+        sample n drew in fold f, or -1 when the sample's path does not visit that fold (the
+        reference returns the draws of EVERY unit, (F, Ko, N); only the ones on the path take
+        part in the sample).  `seed` defaults to a draw from torch's global generator, so
+        `torch.manual_seed` makes the query reproducible."""
+        if num_samples <= 0:
+            raise ValueError("The number of samples must be a positive number")
+        if self.is_complex:
+            raise TypeError("Sampling needs a monotonic circuit (semiring 'lse-sum')")
+        plan = self.plan
+        for sid, s in enumerate(plan.steps):
+            if s.kind not in self._SAMPLE_KINDS:
+                raise TypeError(f"Sampling is not supported for layers of type {s.kind} (step {sid})")
+            if s.kind in ("kronecker", "tucker") and s.arity != 2:
+                raise TypeError(f"Sampling {s.kind} layers of arity {s.arity} is not supported")
+        if seed is None:
+            seed = int(torch.randint(0, 2**62, (1,)).item())
+        with torch.no_grad():
+            P = self.parameter_tensors(leaves, externals)
+            st = self.state(P[0].device)
+            lib, dev = st.lib, st.device
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                tensors = (C.c_void_p * self.n_slots)()
+                for b, p in zip(self.bindings, P):
+                    tensors[b.src_slot] = p.data_ptr()
+                for slot, buf in st.eff.items():
+                    tensors[slot] = buf.data_ptr()
+                key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in P)
+                if st.param_key != key:
+                    L.check(lib.ckb_plan_param_ops(st.handle("plain"), 0, len(self.native_ops), 0,
+                                                   tensors, None, stream), "ckb_plan_param_ops")
+                    st.param_key = key
+                    st.sample_key = None
+                tab = st.sampling_tables()
+                if st.sample_key != key:
+                    self._sampling_cdfs(st, tensors, P, stream)
+                    st.sample_key = key
+                descs = (L.SampleStep * len(plan.steps))()
+                by_sid = {}
+                for b, p in zip(self.bindings, P):
+                    by_sid.setdefault(b.sid, {})[b.name] = (b, p)
+                for sid, s in enumerate(plan.steps):
+                    d = descs[sid]
+                    d.kind = _KIND[s.kind]
+                    d.num_folds, d.arity = s.num_folds, s.arity
+                    d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
+                    d.num_states = int(s.config.get("num_categories", 0))
+                    d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
+                    d.sel_row = int(tab["row0"][sid])
+                    d.in_sel_rows = tab["in_rows"][sid]
+                    d.scope_var = st.tables[sid]["scope_var"]
+                    if sid in st.cdf:
+                        d.cdf = st.cdf[sid].data_ptr()
+                    if s.kind == "gaussian":
+                        d.p0 = tensors[by_sid[sid]["mean"][0].dst_slot]
+                        d.p1 = tensors[by_sid[sid]["stddev"][0].dst_slot]
+                R, D = int(tab["rows"]), plan.num_variables
+                is_float = any(s.kind == "gaussian" for s in plan.steps)
+                x = torch.zeros((num_samples, D), dtype=torch.float32 if is_float else torch.int64, device=dev)
+                sum_sids = [sid for sid, s in enumerate(plan.steps) if s.kind in ("sum", "cpt", "mixing", "tucker")]
+                mixes: list[list[Tensor]] = [[] for _ in sum_sids]
+                root = int(tab["row0"][int(plan.out_step[0])]) + int(plan.out_fold[0])
+                n_launch = 0
+                for base in range(0, num_samples, chunk):
+                    n = min(chunk, num_samples - base)
+                    sel = torch.empty((R, n), dtype=torch.int32, device=dev)
+                    mix = torch.empty((R, n), dtype=torch.int32, device=dev) if return_mixtures else None
+                    L.check(lib.ckb_plan_sample(descs, len(plan.steps), n, base, seed, R, root, 0,
+                                                sel.data_ptr(), mix.data_ptr() if mix is not None else None,
+                                                x[base : base + n].data_ptr(), D, 1 if is_float else 0, stream),
+                            "ckb_plan_sample")
+                    n_launch += len(plan.steps) + 1
+                    if mix is not None:
+                        for i, sid in enumerate(sum_sids):
+                            r0 = int(tab["row0"][sid])
+                            mixes[i].append(mix[r0 : r0 + plan.steps[sid].num_folds])
+                self.last_launches = n_launch
+        mixture = [torch.cat(m, dim=1) if len(m) > 1 else m[0] for m in mixes] if return_mixtures else []
+        return x, mixture
+
+    def _sampling_cdfs(self, st: "_DeviceState", tensors, P, stream) -> None:
+        """Row-wise CDFs of every mixture / category distribution (one small kernel per layer,
+        batch-free) and the reference's admissibility checks on sum weights
+        (layers/inner.py:277-281, layers/optimized.py:182-188)."""
+        lib, dev, plan = st.lib, st.device, self.plan
+        st.cdf = {}
+        for b, p in zip(self.bindings, P):
+            s = plan.steps[b.sid]
+            src = st.eff[b.dst_slot] if b.native is not None else p
+            if s.kind == "categorical":
+                F, K, V = b.src_shape
+                if b.native is None or b.eff_shape != (F, V, K):
+                    raise TypeError(f"step {b.sid}: categorical table without a device layout")
+                out = torch.empty((F, K, V), dtype=torch.float32, device=dev)
+                L.check(lib.ckb_sample_cdf_rows(src.data_ptr(), out.data_ptr(), F * K, V, 1, K, stream),
+                        "ckb_sample_cdf_rows")
+            elif s.kind in ("sum", "cpt", "mixing", "tucker") and b.name == "weight":
+                w = src.contiguous()
+                cols = int(w.shape[-1])
+                rows = w.numel() // cols
+                # the reference raises TypeError in TorchSumLayer.sample, ValueError in TorchCPTLayer.sample
+                exc = TypeError if s.kind in ("sum", "mixing") else ValueError
+                if bool((w < 0.0).any()):
+                    raise exc("Sampling only works with positive weights")
+                out = torch.empty_like(w)
+                L.check(lib.ckb_sample_cdf_rows(w.data_ptr(), out.data_ptr(), rows, cols, 0, 0, stream),
+                        "ckb_sample_cdf_rows")
+                total = out.reshape(rows, cols)[:, -1]
+                if not torch.allclose(total, torch.ones(1, device=dev)):
+                    raise exc("Sampling only works with a normalized parametrization")
+            else:
+                continue
+            st.cdf[b.sid] = out
 
     # ------------------------------------------------------------------ evaluation
     def evaluate(
@@ -644,6 +921,9 @@ def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Cal
     for sid, slot in rt.int_slots.items():
         if sid in st.int_buf:
             tensors[slot] = st.int_buf[sid].data_ptr()
+    for slot, (base, off) in rt.aliases.items():
+        if tensors[base]:
+            tensors[slot] = tensors[base] + 4 * off
     return _Call(which, B, xT, x_is_float, maskT, mask_rows, tensors, len(rt.exec_plans[which]))
 
 
@@ -656,8 +936,10 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
     sizes = [(-(-n // 4) * 4) if nd else 0 for n, nd in zip(nfl, need)]
     flat = torch.empty(sum(sizes), dtype=torch.float32, device=st.device) if sum(sizes) else None
     rt.last_flat_grad = flat
+    rt.last_flat_offsets = offs = []  # float offset of every binding's gradient in `flat` (-1: none)
     off = 0
     for b, p, nd, sz, n in zip(rt.bindings, P, need, sizes, nfl):
+        offs.append(off if nd else -1)
         if not nd:
             outs.append(None)
             continue
@@ -681,7 +963,31 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
             t_slot = es.slots[0]
             if not grads[t_slot]:
                 grads[t_slot] = st.grad_buffer(t_slot).data_ptr()
+    for slot, (base, off) in rt.aliases.items():
+        if grads[base]:
+            grads[slot] = grads[base] + 4 * off
     return grads, outs
+
+
+def _stage_pieces(rt: "PlanRuntime", stage: GradStage, flat: Tensor, offs: list) -> list[Tensor]:
+    """The slices of the flat gradient buffer that are final after `stage`, adjacent ones merged."""
+    spans = []
+    for bi, f0, f1 in stage.pieces:
+        b = rt.bindings[bi]
+        row = int(np.prod(b.src_shape[1:])) * (2 if b.is_complex else 1)
+        F = b.src_shape[0]
+        lo, hi = offs[bi] + f0 * row, offs[bi] + f1 * row
+        if f1 == F:
+            hi = offs[bi] + -(-F * row // 4) * 4  # the padding up to the next piece travels along
+        spans.append((lo, hi))
+    spans.sort()
+    merged = []
+    for lo, hi in spans:
+        if merged and merged[-1][1] == lo:
+            merged[-1][1] = hi
+        else:
+            merged.append([lo, hi])
+    return [flat[lo:hi] for lo, hi in merged]
 
 
 class _PlanFn(torch.autograd.Function):
@@ -742,6 +1048,7 @@ class _PlanFn(torch.autograd.Function):
         lay, plan = rt.layout, rt.plan
         B = call.B
         need = ctx.needs_input_grad[5:]
+        rt.last_synced_bytes = 0
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             cpx = 2 if rt.is_complex else 1
@@ -756,16 +1063,42 @@ class _PlanFn(torch.autograd.Function):
                 go.copy_(gout.to(torch.float32).transpose(0, 1))
             grads, outs = _grad_table(rt, st, call, ctx.P, need)
             ws = st.workspace(call.which, B)
-            L.check(
-                lib.ckb_plan_backward(
-                    st.handle(call.which), 0, call.n_steps, B,
-                    call.xT.data_ptr() if call.xT is not None else None, call.x_is_float,
-                    call.maskT.data_ptr() if call.maskT is not None else None, call.mask_rows,
-                    call.tensors, grads, ctx.arena.data_ptr(), garena.data_ptr(),
-                    ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
-                "ckb_plan_backward",
-            )
-            rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which)))
+            xp = call.xT.data_ptr() if call.xT is not None else None
+            mp = call.maskT.data_ptr() if call.maskT is not None else None
+            sync = rt.grad_sync if rt.last_flat_grad is not None else None
+            if sync is not None and call.which in rt.grad_stages and all(need):
+                # staged: a group of gradients is final after each stage; its all-reduce (issued by
+                # `sync` on the communication stream) overlaps the stages that follow
+                h = st.handle(call.which + "_sync")
+                flat, offs, n = rt.last_flat_grad, rt.last_flat_offsets, 0
+                for stage in rt.grad_stages[call.which]:
+                    L.check(
+                        lib.ckb_plan_backward(h, stage.steps[0], stage.steps[1], B, xp, call.x_is_float,
+                                              mp, call.mask_rows, call.tensors, grads,
+                                              ctx.arena.data_ptr(), garena.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), 0, stream), "ckb_plan_backward")
+                    n += int(lib.ckb_plan_last_launches(h))
+                    L.check(lib.ckb_plan_param_ops(h, stage.ops[0], stage.ops[1], 1, call.tensors,
+                                                   grads, stream), "ckb_plan_param_ops")
+                    n += int(lib.ckb_plan_last_launches(h))
+                    sync(_stage_pieces(rt, stage, flat, offs))
+                rt.last_launches = n
+            else:
+                L.check(
+                    lib.ckb_plan_backward(
+                        st.handle(call.which), 0, call.n_steps, B, xp, call.x_is_float,
+                        mp, call.mask_rows,
+                        call.tensors, grads, ctx.arena.data_ptr(), garena.data_ptr(),
+                        ws.data_ptr(), ws.numel(), L.RUN_PARAM_OPS, stream),
+                    "ckb_plan_backward",
+                )
+                rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which)))
+                if sync is not None and not rt.needs_batch:
+                    sync([rt.last_flat_grad])
+            if sync is not None and not rt.needs_batch:
+                # the reduced gradients are consumed on this stream (autograd accumulates them
+                # into .grad right after this function returns)
+                rt.last_synced_bytes = sync.finish()
         ctx.arena = None
         return (None, None, None, None, None, *outs)
 

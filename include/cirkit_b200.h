@@ -184,6 +184,52 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
                       float* garena, void* workspace, size_t workspace_bytes, int32_t flags,
                       void* stream);
 
+/* The parameter ops [op_begin, op_end) of the plan alone (the ops CKB_RUN_PARAM_OPS runs as a
+ * whole): backward == 0 evaluates them (TorchParameter.forward, parameters/parameter.py:180-188),
+ * backward != 0 back-propagates them (grads as for ckb_plan_backward).  Lets a data-parallel
+ * caller finish the gradient of a GROUP of parameters -- and start its all-reduce -- while the
+ * backward pass of the remaining steps is still running. */
+int ckb_plan_param_ops(ckb_plan_t* plan, int32_t op_begin, int32_t op_end, int32_t backward,
+                       float* const* tensors, float* const* grads, void* stream);
+
+/* ---- SamplingQuery (cirkit/backend/torch/queries.py:187-275): ancestral sampling, root first.
+ * One descriptor per layer, in the plan's (topological) order.  The "selection arena" sel is
+ * (num_rows, num_samples) int32 with one row per (layer, fold): the unit a sample's path goes
+ * through, -1 when the path does not visit the row.  Stateless: no plan handle involved. */
+typedef struct {
+  int32_t kind;       /* ckb_step_kind: TABLE (Categorical), GAUSSIAN, DENSE, MIXING, HADAMARD,
+                         KRONECKER, TUCKER; anything else is refused (the reference raises
+                         TypeError for layers without a sample(), layers/input.py:94-108)      */
+  int32_t num_folds, arity, k_in, k_out;
+  int32_t num_states; /* TABLE: categories V                                                   */
+  int32_t flags;      /* CKB_DENSE_CONCAT as in ckb_step_desc_t                                */
+  int32_t sel_row;    /* arena row of fold 0 of this layer                                     */
+  const int32_t* in_sel_rows; /* device (F*H): arena rows of the inputs (inner layers)         */
+  const int32_t* scope_var;   /* device (F): variable of every fold (input layers)             */
+  const float* cdf;   /* device: row-wise inclusive CDFs (ckb_sample_cdf_rows) of the mixture
+                         weights -- DENSE/TUCKER (F, Ko, Kred), MIXING (F, K, H) -- or of the
+                         category probabilities, TABLE (F, K, V); rows need not sum to 1        */
+  const float* p0;    /* GAUSSIAN: mean (F, K)                                                 */
+  const float* p1;    /* GAUSSIAN: stddev (F, K)                                               */
+} ckb_sample_step_t;
+
+/* dst[r, :] = inclusive prefix sums of row r, left to right in fp32.  mode 0: src (rows, cols)
+ * weights.  mode 1: src is a log-probability table laid out (F, V, K) with K = units, dst is
+ * (F, K, V): rows = F * K, cols = V (Categorical: layers/input.py:423-434). */
+int ckb_sample_cdf_rows(const float* src, float* dst, int64_t rows, int32_t cols, int32_t mode,
+                        int32_t units, void* stream);
+
+/* Draw num_samples joint samples: x (num_samples, num_vars) int64 (x_is_float == 0) or float32,
+ * zero-initialised by the caller (variables outside the scope stay 0, as the reference's padded
+ * samples do, queries.py:258-275).  The path of sample n starts at unit root_unit of arena row
+ * root_row; its random numbers are the Philox4x32-10 blocks (counter = (sample_base + n, row),
+ * key = seed), so a batch may be drawn in several calls.  mix (same shape as sel, may be NULL)
+ * receives the mixture component each visited sum row drew (-1 elsewhere). */
+int ckb_plan_sample(const ckb_sample_step_t* steps, int32_t n_steps, int64_t num_samples,
+                    int64_t sample_base, uint64_t seed, int64_t num_rows, int32_t root_row,
+                    int32_t root_unit, int32_t* sel, int32_t* mix, void* x, int32_t num_vars,
+                    int32_t x_is_float, void* stream);
+
 /* Number of kernels the last forward/backward call on this plan enqueued (bench bookkeeping). */
 int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 

@@ -23,6 +23,40 @@ from cirkit_b200 import B200Circuit  # noqa: E402
 from cirkit_b200.distributed import BatchShardedCircuit  # noqa: E402
 
 
+def overlap_check(dev, rank: int, world: int) -> None:
+    """The staged backward pass with its per-stage asynchronous all-reduces
+    (`overlap_gradient_sync`) against one all-reduce after the backward pass, same data: equal up
+    to the summation order of the collective (bit-equal on two ranks)."""
+    import dataclasses
+
+    for name, units, rows in (("qt8_cp_k4", 64, 640), ("pd32_cp_k4", 16, 96), ("qt8_cp_k4", 4, 40)):
+        g = Golden(name)
+        plan = dataclasses.replace(g.plan, meta={"units": 4}).with_units(units)
+        x = torch.randint(0, 256, (world * rows, plan.num_variables),
+                          generator=torch.Generator().manual_seed(9))
+        grads = []
+        for overlap in (False, True):
+            cc = B200Circuit(plan, seed=21).to(dev)
+            sharded = BatchShardedCircuit(cc)
+            if overlap:
+                assert sharded.overlap_gradient_sync(4, bucket_bytes=1 << 16)
+            for _ in range(2):  # the second pass re-uses buffers the first one's collectives read
+                for p in cc.leaves:
+                    p.grad = None
+                sharded.loss(sharded.shard(x).to(dev), x.shape[0]).backward()
+                nbytes = sharded.sync_gradients()
+            assert nbytes >= sum(4 * p.numel() for p in cc.leaves)
+            grads.append([p.grad.clone() for p in cc.leaves])
+        for i, (a, b) in enumerate(zip(*grads)):
+            # equal up to summation order: a fold chunk sums its split-K slabs in a different
+            # grouping, host-side (PyTorch) parameter ops scatter-add pointer slices with atomics,
+            # and beyond two ranks the collective's own order depends on the message size
+            err, tol = float((a - b).abs().max()), 1e-5 * float(a.abs().max()) + 1e-12
+            assert err <= tol, f"{name} leaf {i}: overlapped != serial ({err:.3e} > {tol:.3e})"
+        if rank == 0:
+            print(f"dist overlap ok {name} K={units}: world {world}, {nbytes} bytes reduced in stages", flush=True)
+
+
 def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
@@ -51,6 +85,7 @@ def main() -> None:
             assert e <= grad_tolerance(gr), f"{name} leaf {i}: grad err {e:.3e} > {grad_tolerance(gr):.3e}"
         if rank == 0:
             print(f"dist ok {name}: world {world}, batch {n}, forward err {err:.2e}", flush=True)
+    overlap_check(dev, rank, world)
     dist.barrier()
     dist.destroy_process_group()
 

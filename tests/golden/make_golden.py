@@ -314,7 +314,58 @@ def case_complex():
         write_full(name, tc, torch.randint(0, 16, (B, D)), kind="complex")
 
 
+def case_sampling():
+    """Fixtures of kind "sampling" (SamplingQuery, queries.py:187-275): small circuits over a few
+    categorical variables with x = EVERY joint state, so that `y` is the reference's exact joint
+    log-distribution -- what the sampler's empirical frequencies are compared with, exactly as the
+    reference's own test does (tests/backend/torch/test_queries/test_sampling.py:18-53).  Also
+    stored: what the reference's SamplingQuery itself returns for 20000 samples under seed 123
+    (its empirical world frequencies; the CUDA sampler uses another random stream)."""
+    import functools
+
+    from cirkit.backend.torch.queries import SamplingQuery
+    from cirkit.symbolic.parameters import mixing_weight_factory
+    from cirkit.templates.region_graph import PoonDomingos, QuadGraph, QuadTree, RandomBinaryTree
+    from cirkit.templates.utils import name_to_input_layer_factory, parameterization_to_factory
+
+    soft = utils.Parameterization(activation="softmax", initialization="normal")
+
+    def build(rg, spl, K, V, mixing=True):
+        wf = parameterization_to_factory(soft)
+        return rg.build_circuit(
+            input_factory=name_to_input_layer_factory("categorical", num_categories=V, probs_factory=wf),
+            sum_product=spl, sum_weight_factory=wf,
+            nary_sum_weight_factory=functools.partial(mixing_weight_factory, param_factory=wf) if mixing else wf,
+            num_input_units=K, num_sum_units=K, num_classes=1, factorize_multivariate=True)
+
+    cases = [
+        ("smp_qt16_cp_k3", QuadTree((1, 4, 4), num_patch_splits=2), "cp", 3, 2, True, True, True),
+        ("smp_qg9_cp_k3_unopt", QuadGraph((1, 3, 3)), "cp", 3, 3, True, True, False),
+        ("smp_qg9_cpt_k4", QuadGraph((1, 3, 3)), "cp-t", 4, 3, True, True, True),
+        ("smp_pd16_cp_k2", PoonDomingos((1, 4, 4), delta=1), "cp", 2, 2, True, True, True),
+        ("smp_pd9_cp_k3_concat", PoonDomingos((1, 3, 3), delta=1), "cp", 3, 3, False, True, True),
+        ("smp_rbt8_tucker_k3", RandomBinaryTree(8), "tucker", 3, 3, True, True, True),
+        ("smp_qt4_tucker_k3_unopt", QuadTree((1, 2, 2), num_patch_splits=2), "tucker", 3, 5, True, True, False),
+    ]
+    for name, rg, spl, K, V, mixing, fold, optimize in cases:
+        if NAMES is not None and name not in NAMES:
+            continue
+        _, tc = compile_ref(build(rg, spl, K, V, mixing), fold=fold, optimize=optimize)
+        D = tc.num_variables
+        worlds = torch.tensor(list(itertools.product(range(V), repeat=D)), dtype=torch.int64)
+        extra = {"num_categories": V}
+        try:  # the reference has no sample() for Tucker layers (layers/inner.py:66-71)
+            torch.manual_seed(123)
+            smp, _ = SamplingQuery(tc)(num_samples=20000)
+            idx = (smp * torch.tensor([V ** (D - 1 - i) for i in range(D)])).sum(dim=1)
+            extra["ref_counts"] = torch.bincount(idx, minlength=V ** D).tolist()
+        except (TypeError, NotImplementedError, RuntimeError) as exc:  # Kronecker.sample: shape bug -> 76 GB alloc
+            extra["ref_sampling_error"] = type(exc).__name__
+        write_full(name, tc, worlds, kind="sampling", extra=extra)
+
+
 CASES = {
+    "sampling": case_sampling,
     "complex": case_complex,
     "pd32": case_pd32,
     "ka_categorical": case_ka_categorical,

@@ -123,3 +123,117 @@ def test_flat_gradient_detection():
     # ... and so does a buffer that holds more than these parameters' gradients
     params[1].grad = flat[sizes[0] : sizes[0] + 7]
     assert _flat_gradient(params[:2], flat) is None
+
+
+def _reducer_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    from cirkit_b200.distributed import OverlappedGradientReducer
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat = torch.arange(40.0, dtype=torch.float64) * (rank + 1)
+        red = OverlappedGradientReducer(average=False)
+        red([flat[24:40]])  # stage 0: the tail of the buffer is final first
+        red([flat[0:8], flat[16:24]])
+        red([flat[8:16], flat[0:0]])  # an empty piece is skipped on every rank alike
+        nbytes = red.finish()
+        avg = torch.ones(6) * (rank + 1)
+        red2 = OverlappedGradientReducer(average=True)
+        red2([avg])
+        red2.finish()
+        torch.save({"flat": flat, "nbytes": nbytes, "avg": avg}, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_reducer_sums_pieces_stage_by_stage(tmp_path):
+    """The reducer the staged CUDA backward calls once per stage: every piece is summed over the
+    ranks by its own asynchronous all-reduce, `finish()` waits for all of them and returns the
+    bytes reduced (2 gloo ranks)."""
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = torch.arange(40.0, dtype=torch.float64) * 3
+    for r in range(world):
+        o = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert torch.equal(o["flat"], want)
+        assert o["nbytes"] == 40 * 8
+        assert torch.equal(o["avg"], torch.full((6,), 1.5))
+
+
+def test_gradient_stages_partition_the_backward_pass():
+    """`PlanRuntime.enable_gradient_stages` (host logic only, no device): the staged execution
+    plan runs every step exactly once, its parameter-op ranges partition the op list, and the
+    gradient pieces of the stages tile the flat gradient buffer without gaps or overlaps."""
+    import numpy as np
+
+    from cirkit_b200.runtime import STEP_TABLE_DENSE, PlanRuntime, _stage_pieces
+
+    g = Golden("qt28_cp_k64")
+    rt = PlanRuntime(g.plan)
+    assert rt.enable_gradient_stages(4)
+    fused, sync = rt.exec_plans["fused"], rt.exec_plans["fused_sync"]
+    td = [es for es in fused if es.kind == STEP_TABLE_DENSE]
+    assert len(td) == 1 and len(sync) == len(fused) + 3
+    F = g.plan.steps[td[0].out_sid].num_folds
+    chunks = [es for es in sync if es.folds is not None]
+    assert [es.folds for es in chunks] == [(c * F // 4, (c + 1) * F // 4) for c in range(4)]
+    # step ranges: disjoint, cover the list; backward order = inner layers first, then the chunks
+    stages = rt.grad_stages["fused"]
+    covered = sorted(i for st in stages for i in range(*st.steps))
+    assert covered == list(range(len(sync)))
+    assert stages[0].steps == (4, len(sync)) and len(stages) == 5
+    ops_cov = sorted(i for st in stages for i in range(*st.ops))
+    assert ops_cov == list(range(len(rt.sync_ops["fused_sync"])))
+    # alias slots point into the base buffers at the fold offset
+    V, K = 256, 64
+    for es in chunks:
+        f0 = es.folds[0]
+        for slot, per_fold in zip(es.slots, (V * K, K * K, V * K)):
+            if f0 == 0:
+                assert slot not in rt.aliases
+            else:
+                assert rt.aliases[slot][1] == f0 * per_fold
+    # the pieces of all stages tile the flat buffer (as laid out by _grad_table)
+    sizes = [-(-int(np.prod(b.src_shape)) // 4) * 4 for b in rt.bindings]
+    offs = list(np.cumsum([0] + sizes[:-1]))
+    flat = torch.zeros(sum(sizes))
+    for st in stages:
+        for piece in _stage_pieces(rt, st, flat, offs):
+            piece += 1
+    assert torch.equal(flat, torch.ones_like(flat))
+    # the bulk of the bytes is in the chunk stages, the inner layers' weights come first
+    first = sum(p.numel() for p in _stage_pieces(rt, stages[0], flat, offs))
+    assert first < 0.2 * flat.numel()
+
+
+@pytest.mark.parametrize("name,which", [("pd32_cp_k4", "plain"), ("qt28_cp_k64", "plain"),
+                                        ("qg8_cp_k4", "plain"), ("rbt12_gaussian_k5", "plain")])
+def test_gradient_stages_of_other_plans(name, which):
+    """Bucketed stages for plans without a fused input step (PoonDomingos: the Categorical table
+    feeds a Hadamard layer) and for the plain plan of small batches: steps and ops are partitioned,
+    the pieces tile the flat buffer, inner layers are cut into several stages when large."""
+    import numpy as np
+
+    from cirkit_b200.runtime import PlanRuntime, _stage_pieces
+
+    g = Golden(name)
+    import dataclasses
+
+    plan = dataclasses.replace(g.plan, meta={"units": 4}).with_units(32) if name == "pd32_cp_k4" else g.plan
+    rt = PlanRuntime(plan)
+    assert rt.enable_gradient_stages(4, bucket_bytes=1 << 20 if name != "qg8_cp_k4" else 1 << 10)
+    stages, sync = rt.grad_stages[which], rt.exec_plans[which + "_sync"]
+    assert sorted(i for st in stages for i in range(*st.steps)) == list(range(len(sync)))
+    assert sorted(i for st in stages for i in range(*st.ops)) == list(range(len(rt.sync_ops[which + "_sync"])))
+    # backward order: every stage lies below the previous one in the step list
+    his = [st.steps[1] for st in stages]
+    assert his == sorted(his, reverse=True)
+    sizes = [-(-int(np.prod(b.src_shape)) // 4) * 4 for b in rt.bindings]
+    offs = list(np.cumsum([0] + sizes[:-1]))
+    flat = torch.zeros(sum(sizes))
+    for st in stages:
+        for piece in _stage_pieces(rt, st, flat, offs):
+            piece += 1
+    assert torch.equal(flat, torch.ones_like(flat))
+    if name == "pd32_cp_k4":
+        assert len(stages) > 5 and any(es.folds is not None for es in sync)

@@ -277,3 +277,36 @@ def test_squared_circuit_matches_reference(cirkit, dev):
         err = (p.grad.cpu().to(gr.dtype) - gr).abs().max().item()
         tol = max(2e-6, 1e-4 * gr.abs().max().item())
         assert err <= tol, f"{name}: {err:.3e} > {tol:.3e}"
+
+
+def test_reference_sampling_query_runs_the_cuda_sampler(cirkit, dev):
+    """The reference's own `SamplingQuery(cc)(num_samples)` (queries.py:187-275) on an accelerated
+    circuit: its per-layer callback is recognised in `evaluate` and replaced by the device
+    sampler.  Shapes as the reference returns them; every pixel's marginal frequency against the
+    marginal the reference computes in fp64 (IntegrateQuery) for the same parameters."""
+    import numpy as np
+    from cirkit.backend.torch.queries import IntegrateQuery, SamplingQuery
+
+    from test_sampling_oracle import chi_square_ok
+
+    sc = _image(4, "quad-graph", shape=(1, 3, 3))
+    ctx, cc, rctx, ref = _compile_pair(sc, dev, fold=True, optimize=True)
+    assert type(cc).__name__ == "B200TorchCircuit", getattr(cc, "_b200_reason", "")
+    torch.manual_seed(0)
+    N = 300_000
+    samples, mixtures = SamplingQuery(cc)(num_samples=N)
+    assert samples.shape == (N, 9) and samples.dtype == torch.int64 and samples.is_cuda
+    assert len(mixtures) > 0 and all(m.shape[1] == N for m in mixtures)
+    assert cc._b200_runtime.last_launches > 0
+    xs = torch.zeros(256, 9, dtype=torch.int64)
+    for var in range(9):
+        xs.zero_()
+        xs[:, var] = torch.arange(256)
+        mask = torch.ones(1, 9, dtype=torch.bool)
+        mask[0, var] = False
+        with torch.no_grad():
+            p = torch.exp(IntegrateQuery(ref)(xs, integrate_vars=mask).reshape(-1)).numpy()
+        assert abs(p.sum() - 1.0) < 1e-9
+        counts = np.bincount(samples[:, var].cpu().numpy(), minlength=256)
+        stat, bound = chi_square_ok(counts, p)
+        assert stat < bound, f"pixel {var}: chi-square {stat:.1f} >= {bound:.1f}"

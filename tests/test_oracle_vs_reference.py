@@ -196,3 +196,42 @@ def test_complex_semiring_circuits(reference, spl, fold, optimize):
     assert any(op == "conj" for s in lowc.plan.steps for p in s.params.values() for op, _ in p.ops)
     # the conjugate circuit reads the very same leaf tensors
     assert {id(t) for t in lowc.leaves} == {id(t) for t in low.leaves}
+
+
+@pytest.mark.parametrize("rg,spl,fold,optimize", [
+    ("quad-tree-2", "cp", True, True), ("quad-tree-2", "cp", True, False),
+    ("quad-graph", "cp", True, True), ("quad-graph", "cp", False, False),
+    ("quad-tree-2", "cp-t", True, True), ("poon-domingos", "cp", True, True),
+])
+def test_sampling_oracle_draws_the_references_samples(reference, rg, spl, fold, optimize):
+    """oracle/sampling.py::reference_sample restates SamplingQuery (queries.py:187-275) call by
+    call: under the same torch seed it returns the reference's samples and mixture samples bit for
+    bit."""
+    from cirkit.backend.torch.queries import SamplingQuery
+    from cirkit.pipeline import PipelineContext
+    from cirkit_b200.adapter import plan_from_torch
+    from oracle.sampling import reference_sample
+
+    sc = _image(reference, (1, 4, 4), rg, spl, 3, num_categories=5) if False else None
+    from cirkit.templates import data_modalities, utils
+
+    sc = data_modalities.image_data(
+        (1, 4, 4), region_graph=rg, input_layer="categorical", num_input_units=3,
+        sum_product_layer=spl, num_sum_units=3, input_params={"probs": utils.Parameterization(
+            activation="softmax", initialization="normal")},
+        sum_weight_param=utils.Parameterization(activation="softmax", initialization="normal"))
+    tc = PipelineContext(backend="torch", semiring="lse-sum", fold=fold, optimize=optimize).compile(sc)
+    low = plan_from_torch(tc)
+    oc = OracleCircuit(low.plan, dtype=torch.float64)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, low.leaves):
+            p.copy_(v)
+    torch.manual_seed(7)
+    ref_samples, ref_mix = SamplingQuery(tc)(num_samples=50)
+    torch.manual_seed(7)
+    samples, mix = reference_sample(oc, 50)
+    assert samples.shape == ref_samples.shape == (50, 16)
+    assert torch.equal(samples, ref_samples)
+    assert len(mix) == len(ref_mix)
+    for a, b in zip(mix, ref_mix):
+        assert torch.equal(a, b)
