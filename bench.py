@@ -154,8 +154,8 @@ def make_config(args, world, plan):
             "" if args.no_grad_allreduce or world == 1 else
             " + all_reduce(param grads, sum)" + (
                 " after the backward pass" if args.grad_chunks <= 0 else
-                f", overlapped: issued per stage of the backward pass (inner layers, then {args.grad_chunks} "
-                "fold chunks of the input table)")),
+                f", overlapped: issued per stage of the backward pass (inner layers, input layers, then the "
+                f"parameter ops of the input table in {args.grad_chunks} fold ranges)")),
         "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
         "leaves": "seeded N(0,1), seed 1234",
         **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
@@ -365,7 +365,7 @@ def run_b200(args):
 
     sharded = BatchShardedCircuit(cc)  # this rank's replica: rows [rank*B, (rank+1)*B) of the job
     if world > 1 and not args.no_grad_allreduce and args.grad_chunks > 0 and z_runtime is None:
-        sharded.overlap_gradient_sync(args.grad_chunks)
+        sharded.overlap_gradient_sync(args.grad_chunks, chunk_steps=args.chunk_steps)
     if args.stage_only:  # developer A/B: the staged backward pass without any collective
         from cirkit_b200.distributed import OverlappedGradientReducer
 
@@ -373,7 +373,7 @@ def run_b200(args):
             def __call__(self, pieces):
                 self.bytes += sum(t.numel() * 4 for t in pieces)
 
-        runtime.enable_gradient_stages(args.grad_chunks)
+        runtime.enable_gradient_stages(args.grad_chunks, chunk_steps=args.chunk_steps)
         runtime.grad_sync = _NoReduce()
 
     def step(x):
@@ -575,6 +575,7 @@ def main():
                          "gradient all-reduces overlap the remaining backward work (0: one all-reduce after backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-only", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--chunk-steps", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--profile-out", default=None)
     ap.add_argument("--tc-flags", type=int, default=None,
                     help="developer switch: value for CKB_OPT_TC_FAST_MATH (3 = default kernels; "

@@ -20,6 +20,8 @@ DENSE_CONCAT = 1
 STEP_ROWS64 = 2
 STEP_COMPLEX = 4
 STEP_REAL_TABLE = 8
+STEP_TABLE_INPUT = 16
+STEP_NO_GATHER = 32
 POP_SOFTMAX, POP_LOG_SOFTMAX_T, POP_LOG_T, POP_COPY_T, POP_SCALED_SIGMOID, POP_LOG, POP_LSE_ROWS, POP_CONJ = range(8)
 U8, I32, I64, F32, F64, I16 = range(6)
 RUN_PARAM_OPS = 1
@@ -76,6 +78,7 @@ class StepDesc(C.Structure):
         ("slot", C.c_int32 * 4),
         ("int_slot", C.c_int32),
         ("max_consumers", C.c_int32),
+        ("aux_off", C.c_int64),
     ]
 
 

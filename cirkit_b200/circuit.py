@@ -39,10 +39,11 @@ class LayerInfo:
 
 
 class B200Circuit(nn.Module):
-    def __init__(self, plan: CircuitPlan, *, seed: int | None = None, fuse_tables: bool = True):
+    def __init__(self, plan: CircuitPlan, *, seed: int | None = None, fuse_tables: bool = True,
+                 fuse_table_inputs: bool = True):
         super().__init__()
         self.plan = plan
-        self.runtime = PlanRuntime(plan, fuse_tables=fuse_tables)
+        self.runtime = PlanRuntime(plan, fuse_tables=fuse_tables, fuse_table_inputs=fuse_table_inputs)
         self.leaves = nn.ParameterList(
             [nn.Parameter(torch.empty(l.shape, dtype=torch.complex64 if l.dtype == "complex" else torch.float32),
                           requires_grad=l.requires_grad)

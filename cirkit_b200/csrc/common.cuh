@@ -74,6 +74,7 @@ int dense_fwd(const ckb_step_desc_t& d, Ctx& c);
 int dense_bwd(const ckb_step_desc_t& d, Ctx& c);
 int tucker_fwd(const ckb_step_desc_t& d, Ctx& c);
 int tucker_bwd(const ckb_step_desc_t& d, Ctx& c);
+int table_pair_gather(const ckb_step_desc_t& d, Ctx& c, float* u);
 int table_dense_fwd(const ckb_step_desc_t& d, Ctx& c);
 int table_dense_bwd(const ckb_step_desc_t& d, Ctx& c);
 size_t table_dense_ws(const ckb_step_desc_t& d, int64_t B);

@@ -782,7 +782,24 @@ static DenseArgs make_args(const ckb_step_desc_t& d, Ctx& c) {
   return a;
 }
 
+// CKB_STEP_TABLE_INPUT: the layer runs on the gathered block u (arity 1, rows f*B*Ki)
+static DenseArgs table_input_args(const ckb_step_desc_t& d, Ctx& c) {
+  DenseArgs a = make_args(d, c);
+  a.in_rows = nullptr;
+  a.arena = c.arena + c.B * d.aux_off;
+  a.H = 1;
+  return a;
+}
+
 int dense_fwd(const ckb_step_desc_t& d, Ctx& c) {
+  if (d.flags & CKB_STEP_TABLE_INPUT) {
+    if (d.flags & CKB_DENSE_CONCAT) {
+      set_error("table-input step over concatenated inputs");
+      return CKB_ERR_UNSUPPORTED;
+    }
+    if (int rc = table_pair_gather(d, c, c.arena + c.B * d.aux_off)) return rc;
+    return run_dense_fwd(table_input_args(d, c), d.num_folds, c);
+  }
   return run_dense_fwd(make_args(d, c), d.num_folds, c);
 }
 
@@ -792,7 +809,7 @@ size_t dense_bwd_ws(const ckb_step_desc_t& d, int64_t B) {
 }
 
 int dense_bwd(const ckb_step_desc_t& d, Ctx& c) {
-  DenseArgs a = make_args(d, c);
+  DenseArgs a = (d.flags & CKB_STEP_TABLE_INPUT) ? table_input_args(d, c) : make_args(d, c);
   a.gs = GradSrc{c.garena, d.cons_ptr, d.cons_rows, c.B};
   a.gin = c.garena + c.B * d.gin_off;
   a.max_cons = d.max_consumers;
@@ -920,6 +937,7 @@ int table_dense_fwd(const ckb_step_desc_t& d, Ctx& c) {
     return CKB_ERR_UNSUPPORTED;
   }
   if (int rc = run_dense_fwd(table_dense_args(d, c), d.num_folds, c)) return rc;
+  if (d.flags & CKB_STEP_NO_GATHER) return CKB_OK;  // the consumer gathers T2 rows itself
   return table_fwd(as_table(d), c);
 }
 

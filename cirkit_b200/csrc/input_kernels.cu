@@ -131,6 +131,166 @@ int table_fwd(const ckb_step_desc_t& d, Ctx& c) {
   return CKB_OK;
 }
 
+// u[f,b,:] = sum_h T2[fold(f,h), x[b, var(fold(f,h))], :] -- the Hadamard product (log space) of
+// H table rows, gathered in one pass (CKB_STEP_TABLE_INPUT).  A group of G lanes owns a row, a
+// warp works on U batches of rows at once: all state loads, then all table loads (L2: the table
+// is V*K*4 bytes per fold), then the stores.
+constexpr int kPairU = 4, kPairMaxH = 4;
+__global__ void table_pair_gather_kernel(const float* __restrict__ T2, const int32_t* __restrict__ scope_var,
+                                         const int64_t* __restrict__ folds, const void* __restrict__ xT,
+                                         int x_is_float, float* __restrict__ u, int64_t B, int K, int V,
+                                         int H) {
+  const int f = blockIdx.y;
+  const int K4 = K >> 2;
+  int G = 1;
+  while (G < K4 && G < 32) G <<= 1;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), rpw = 32 / G;
+  const float* Th[kPairMaxH];
+  int var[kPairMaxH];
+#pragma unroll
+  for (int h = 0; h < kPairMaxH; ++h) {
+    const int64_t tf = h < H ? folds[(int64_t)f * H + h] : 0;
+    Th[h] = T2 + tf * V * K;
+    var[h] = h < H ? scope_var[tf] : 0;
+  }
+  float* uf = u + (int64_t)f * B * K;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t step = (int64_t)rpw * kPairU;
+  for (int64_t b0 = warp_global * step; b0 < B; b0 += n_warps * step) {
+    int v[kPairU][kPairMaxH];
+#pragma unroll
+    for (int q = 0; q < kPairU; ++q) {
+      const int64_t b = b0 + q * rpw + lane / G;
+#pragma unroll
+      for (int h = 0; h < kPairMaxH; ++h)
+        v[q][h] = (h < H && b < B) ? min(max(read_state(xT, x_is_float, (int64_t)var[h] * B + b), 0), V - 1) : 0;
+    }
+    for (int k4 = gl; k4 < K4; k4 += G) {
+      float4 acc[kPairU];
+#pragma unroll
+      for (int q = 0; q < kPairU; ++q) {
+        acc[q] = __ldg(reinterpret_cast<const float4*>(Th[0] + (int64_t)v[q][0] * K) + k4);
+#pragma unroll
+        for (int h = 1; h < kPairMaxH; ++h)
+          if (h < H) {
+            const float4 z = __ldg(reinterpret_cast<const float4*>(Th[h] + (int64_t)v[q][h] * K) + k4);
+            acc[q].x += z.x; acc[q].y += z.y; acc[q].z += z.z; acc[q].w += z.w;
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < kPairU; ++q) {
+        const int64_t b = b0 + q * rpw + lane / G;
+        if (b < B) __stcs(reinterpret_cast<float4*>(uf + b * K) + k4, acc[q]);
+      }
+    }
+  }
+}
+
+// Same result through shared memory: a CTA owns (fold, tile of KT <= 32 units), stages the H table
+// slices it gathers from -- H*V*KT floats, 64 KB for two 256-state tables -- once, and then serves
+// every sample of the fold from there.  The table rows are read from L2 / HBM once per CTA instead
+// of once per sample (2*B*K*4 bytes per fold at the far-die L2 rate, which is what bounded the
+// kernel above: 125 us for the 392 x 2048 north-star level); what remains is the u stream.
+// States are fetched 256 samples at a time, coalesced, one chunk ahead (double-buffered).
+constexpr int kStageRows = 256;
+__global__ void __launch_bounds__(256) table_pair_gather_smem_kernel(
+    const float* __restrict__ T2, const int32_t* __restrict__ scope_var, const int64_t* __restrict__ folds,
+    const void* __restrict__ xT, int x_is_float, float* __restrict__ u, int64_t B, int K, int V, int H,
+    int KT) {
+  extern __shared__ __align__(16) float tab[];                     // [H][V][KT]
+  int* st = reinterpret_cast<int*>(tab + (size_t)H * V * KT);      // [2][H][kStageRows] row offsets
+  const int f = blockIdx.y, k0 = blockIdx.x * KT;
+  const int tid = threadIdx.x;
+  const int KT4 = KT >> 2;  // float4 chunks per staged row: 8 for KT = 32
+  int var[kPairMaxH];
+#pragma unroll
+  for (int h = 0; h < kPairMaxH; ++h) {
+    const int64_t tf = h < H ? folds[(int64_t)f * H + h] : 0;
+    var[h] = h < H ? scope_var[tf] : 0;
+    if (h < H) {
+      const float* src = T2 + tf * V * K + k0;
+      for (int i = tid; i < V * KT4; i += 256) {
+        const int v = i / KT4, c = i - v * KT4;
+        reinterpret_cast<float4*>(tab)[((size_t)h * V + v) * KT4 + c] =
+            __ldg(reinterpret_cast<const float4*>(src + (int64_t)v * K) + c);
+      }
+    }
+  }
+  auto fetch = [&](int64_t b0, int* dst) {  // thread = sample b0 + tid: its H staged-row offsets
+    int r[kPairMaxH];
+#pragma unroll
+    for (int h = 0; h < kPairMaxH; ++h) {
+      r[h] = 0;
+      if (h < H && b0 + tid < B)
+        r[h] = (h * V + min(max(read_state(xT, x_is_float, (int64_t)var[h] * B + b0 + tid), 0), V - 1)) * KT4;
+    }
+#pragma unroll
+    for (int h = 0; h < kPairMaxH; ++h)
+      if (h < H) dst[h * kStageRows + tid] = r[h];
+  };
+  fetch(0, st);
+  __syncthreads();
+  const int rows_per_pass = 256 / KT4;  // 32 for KT = 32
+  const int gl = tid % KT4, rl = tid / KT4;
+  float* uf = u + (int64_t)f * B * K + k0;
+  int buf = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += kStageRows, buf ^= 1) {
+    const int* cur = st + buf * kPairMaxH * kStageRows;
+    if (b0 + kStageRows < B) fetch(b0 + kStageRows, st + (buf ^ 1) * kPairMaxH * kStageRows);
+#pragma unroll 4
+    for (int r0 = 0; r0 < kStageRows; r0 += rows_per_pass) {
+      const int r = r0 + rl;
+      const int64_t b = b0 + r;
+      if (b >= B) break;
+      float4 acc = reinterpret_cast<const float4*>(tab)[cur[r] + gl];
+#pragma unroll
+      for (int h = 1; h < kPairMaxH; ++h)
+        if (h < H) {
+          const float4 z = reinterpret_cast<const float4*>(tab)[cur[h * kStageRows + r] + gl];
+          acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+        }
+      __stcs(reinterpret_cast<float4*>(uf + b * K) + gl, acc);
+    }
+    __syncthreads();  // the next chunk's offsets are in place, this chunk's are free
+  }
+}
+
+int table_pair_gather(const ckb_step_desc_t& d, Ctx& c, float* u) {
+  if (d.slot[1] < 0 || d.scope_var == nullptr || d.in_rows == nullptr || d.num_states <= 0 ||
+      d.arity > kPairMaxH || (d.k_in & 3) || c.xT == nullptr) {
+    set_error("table-input step: needs T2, table variables, fold table, V, arity <= %d, Ki %% 4 == 0 and x",
+              kPairMaxH);
+    return CKB_ERR_INVALID;
+  }
+  // shared-memory version: unit tiles of 32 (or all K <= 32 units), the staged slices within 72 KB
+  // so that three CTAs share an SM
+  const int KT = d.k_in % 32 == 0 ? 32 : (d.k_in <= 32 ? d.k_in : 0);
+  const size_t smem = KT ? (size_t)d.arity * d.num_states * KT * 4 + 2 * kPairMaxH * kStageRows * 4 : 0;
+  if (KT && 256 % (KT / 4) == 0 && smem <= 72 * 1024 && c.B >= 2 * d.num_states) {
+    static PerDeviceOnce attr;
+    if (attr.first())
+      CKB_CUDA_CHECK(cudaFuncSetAttribute(table_pair_gather_smem_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    dim3 grid(d.k_in / KT, d.num_folds);
+    table_pair_gather_smem_kernel<<<grid, 256, smem, c.stream>>>(
+        c.tensors[d.slot[1]], d.scope_var, d.in_rows, c.xT, c.x_is_float, u, c.B, d.k_in, d.num_states,
+        d.arity, KT);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+    return CKB_OK;
+  }
+  int G = 1;
+  while (G < d.k_in / 4 && G < 32) G <<= 1;
+  const int64_t rows_per_block = 8 * (32 / G) * kPairU;
+  dim3 grid((int)max64(1, min64(ceil_div(c.B, rows_per_block), 2 * kNumSMs)), d.num_folds);
+  table_pair_gather_kernel<<<grid, 256, 0, c.stream>>>(c.tensors[d.slot[1]], d.scope_var, d.in_rows, c.xT,
+                                                       c.x_is_float, u, c.B, d.k_in, d.num_states, d.arity);
+  CKB_LAUNCH_CHECK();
+  c.launches++;
+  return CKB_OK;
+}
+
 // Backward of the lookup: dT[f,v,:] = sum over samples with x=v of g[f,b,:]  (the reference gets
 // this from autograd as an `index_put_`, 26 % of its CPU step -- SURVEY §3(b)).
 //

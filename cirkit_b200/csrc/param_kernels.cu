@@ -139,6 +139,132 @@ __global__ void table_bwd_t_kernel(const float* __restrict__ src, const float* _
   }
 }
 
+// ---- the same two ops with the whole (32 units x V states) tile of a fold in shared memory ----
+// One CTA per (fold, 32-unit tile): every element is read from global memory ONCE, with all of a
+// thread's loads in flight together, and both directions of the transpose go through one padded
+// tile (row stride V + 1: row-wise and column-wise accesses are bank-conflict free).  The versions
+// above walk the tile in 32 x 32 pieces with two barriers each and re-read the source for the
+// log-sum-exp: 45 / 60 us for the 51 MB north-star table against 16 / 24 us of HBM time.
+template <int MODE>
+__global__ void __launch_bounds__(256) table_fwd_t_smem_kernel(const float* __restrict__ src,
+                                                               float* __restrict__ dst, int K, int V) {
+  extern __shared__ float tile[];  // [32][V + 1]
+  __shared__ float lse[32];
+  const int f = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = min(32, K - k0), ld = V + 1;
+  const float* s = src + ((int64_t)f * K + k0) * V;  // nk contiguous rows of V floats
+  float* d = dst + (int64_t)f * V * K + k0;
+  const int64_t n = (int64_t)nk * V;
+  if ((V & 3) == 0) {
+    for (int64_t i = 4 * (int64_t)tid; i < n; i += 1024) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(s + i));
+      const int k = (int)(i / V), v = (int)(i - (int64_t)k * V);
+      float* t = tile + k * ld + v;
+      t[0] = x.x; t[1] = x.y; t[2] = x.z; t[3] = x.w;
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += 256) tile[(i / V) * ld + (i % V)] = __ldg(s + i);
+  }
+  __syncthreads();
+  if (MODE == 0) {
+    for (int k = warp; k < nk; k += 8) {
+      float m = -INFINITY, z = 0.f;
+      for (int v = lane; v < V; v += 32) m = fmaxf(m, tile[k * ld + v]);
+      m = warp_max(m);
+      for (int v = lane; v < V; v += 32) z += expf(tile[k * ld + v] - m);
+      z = warp_sum(z);
+      if (lane == 0) lse[k] = m + logf(z);
+    }
+    __syncthreads();
+  }
+  if (lane < nk) {
+    const float shift = MODE == 0 ? lse[lane] : 0.f;
+    for (int v = warp; v < V; v += 8) {
+      float val = tile[lane * ld + v];
+      if (MODE == 0) val -= shift;
+      if (MODE == 1) val = logf(val);
+      d[(int64_t)v * K + lane] = val;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) table_bwd_t_smem_kernel(const float* __restrict__ src,
+                                                               const float* __restrict__ T,
+                                                               const float* __restrict__ dT,
+                                                               float* __restrict__ dsrc, int K, int V) {
+  extern __shared__ float tile[];  // g [32][V + 1], then (MODE 0) exp(T) [32][V + 1]
+  __shared__ float colsum[32];
+  const int f = blockIdx.y, k0 = blockIdx.x * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = min(32, K - k0), ld = V + 1;
+  float* tg = tile;
+  float* te = tile + 32 * ld;
+  const float* g = dT + (int64_t)f * V * K + k0;
+  const float* t = T + (int64_t)f * V * K + k0;
+  if (lane < nk) {
+    for (int v = warp; v < V; v += 8) {
+      tg[lane * ld + v] = __ldg(g + (int64_t)v * K + lane);
+      if (MODE == 0) te[lane * ld + v] = __ldg(t + (int64_t)v * K + lane);
+    }
+  }
+  __syncthreads();
+  if (MODE == 0) {
+    for (int k = warp; k < nk; k += 8) {  // fixed order: lanes stride the states, then the shuffle tree
+      float a = 0.f;
+      for (int v = lane; v < V; v += 32) a += tg[k * ld + v];
+      a = warp_sum(a);
+      if (lane == 0) colsum[k] = a;
+    }
+    __syncthreads();
+  }
+  float* d = dsrc + ((int64_t)f * K + k0) * V;
+  const float* s = src + ((int64_t)f * K + k0) * V;
+  for (int k = warp; k < nk; k += 8) {
+    const float cs = MODE == 0 ? colsum[k] : 0.f;
+    for (int v = lane; v < V; v += 32) {
+      float val = tg[k * ld + v];
+      if (MODE == 0) val -= expf(te[k * ld + v]) * cs;
+      if (MODE == 1) val /= __ldg(s + (int64_t)k * V + v);
+      d[(int64_t)k * V + v] = val;
+    }
+  }
+}
+
+// launchers: shared-memory tiles when they fit (V up to ~850 states), else the tiled versions
+template <int MODE>
+static int launch_table_fwd_t(const float* src, float* dst, int64_t F, int K, int V, cudaStream_t st) {
+  const size_t smem = (size_t)32 * (V + 1) * 4;
+  dim3 grid(ceil_div(K, 32), (unsigned)F);
+  if (smem <= 64 * 1024) {
+    static PerDeviceOnce attr;
+    if (attr.first())
+      CKB_CUDA_CHECK(cudaFuncSetAttribute(table_fwd_t_smem_kernel<MODE>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    table_fwd_t_smem_kernel<MODE><<<grid, 256, smem, st>>>(src, dst, K, V);
+  } else {
+    table_fwd_t_kernel<MODE><<<grid, dim3(32, 8), 0, st>>>(src, dst, K, V);
+  }
+  return CKB_OK;
+}
+template <int MODE>
+static int launch_table_bwd_t(const float* src, const float* T, const float* dT, float* dsrc, int64_t F,
+                              int K, int V, cudaStream_t st) {
+  const size_t smem = (size_t)(MODE == 0 ? 2 : 1) * 32 * (V + 1) * 4;
+  dim3 grid(ceil_div(K, 32), (unsigned)F);
+  if (smem <= 72 * 1024) {
+    static PerDeviceOnce attr;
+    if (attr.first())
+      CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_t_smem_kernel<MODE>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    table_bwd_t_smem_kernel<MODE><<<grid, 256, smem, st>>>(src, T, dT, dsrc, K, V);
+  } else {
+    table_bwd_t_kernel<MODE><<<grid, dim3(32, 8), 0, st>>>(src, T, dT, dsrc, K, V);
+  }
+  return CKB_OK;
+}
+
 // ---- elementwise ------------------------------------------------------------------------------
 __global__ void scaled_sigmoid_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                           int64_t n, float a, float b) {
@@ -369,16 +495,13 @@ int param_op_fwd(const ckb_param_op_t& op, Ctx& c) {
       softmax_fwd_kernel<<<grid1d(op.rows, 8), 256, 0, c.stream>>>(src, dst, op.rows, op.cols);
       break;
     case CKB_POP_LOG_SOFTMAX_T:
-      table_fwd_t_kernel<0><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, op.aux, op.cols);
+      if (int rc = launch_table_fwd_t<0>(src, dst, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_LOG_T:
-      table_fwd_t_kernel<1><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, op.aux, op.cols);
+      if (int rc = launch_table_fwd_t<1>(src, dst, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_COPY_T:
-      table_fwd_t_kernel<2><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, op.aux, op.cols);
+      if (int rc = launch_table_fwd_t<2>(src, dst, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_SCALED_SIGMOID:
       scaled_sigmoid_fwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, dst, n, op.a, op.b);
@@ -416,16 +539,13 @@ int param_op_bwd(const ckb_param_op_t& op, Ctx& c) {
       softmax_bwd_kernel<<<grid1d(op.rows, 8), 256, 0, c.stream>>>(dst, g, dsrc, op.rows, op.cols);
       break;
     case CKB_POP_LOG_SOFTMAX_T:
-      table_bwd_t_kernel<0><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, g, dsrc, op.aux, op.cols);
+      if (int rc = launch_table_bwd_t<0>(src, dst, g, dsrc, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_LOG_T:
-      table_bwd_t_kernel<1><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, g, dsrc, op.aux, op.cols);
+      if (int rc = launch_table_bwd_t<1>(src, dst, g, dsrc, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_COPY_T:
-      table_bwd_t_kernel<2><<<dim3(ceil_div(op.aux, 32), (unsigned)op.rows), dim3(32, 8), 0, c.stream>>>(
-          src, dst, g, dsrc, op.aux, op.cols);
+      if (int rc = launch_table_bwd_t<2>(src, dst, g, dsrc, op.rows, op.aux, op.cols, c.stream)) return rc;
       break;
     case CKB_POP_SCALED_SIGMOID:
       scaled_sigmoid_bwd_kernel<<<grid1d(n, 256), 256, 0, c.stream>>>(src, g, dsrc, n, op.a, op.b);

@@ -229,7 +229,7 @@ class BatchShardedCircuit(nn.Module):
         return -self.circuit(x_local).sum() / num_rows
 
     def overlap_gradient_sync(self, chunks: int = 4, *, average: bool = False,
-                              bucket_bytes: int = 8 << 20) -> bool:
+                              bucket_bytes: int = 8 << 20, chunk_steps: bool = False) -> bool:
         """Sum the parameter gradients over the ranks INSIDE the backward pass, stage by stage
         (see `OverlappedGradientReducer`); `sync_gradients()` then only reports the bytes.  Returns
         False when the circuit has no CUDA runtime or its plan has per-sample inputs from PyTorch
@@ -237,7 +237,7 @@ class BatchShardedCircuit(nn.Module):
         rt = _runtime_of(self.circuit)
         if rt is None or not hasattr(rt, "enable_gradient_stages") or rt.needs_batch or rt.is_complex:
             return False
-        rt.enable_gradient_stages(chunks, bucket_bytes)
+        rt.enable_gradient_stages(chunks, bucket_bytes, chunk_steps)
         rt.grad_sync = OverlappedGradientReducer(self.group, average)
         return True
 

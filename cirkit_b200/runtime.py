@@ -22,6 +22,7 @@ Execution plans.  The same circuit is lowered to two step lists:
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass, field
 from typing import Sequence
 
@@ -210,6 +211,9 @@ class ExecStep:
     slots: list = field(default_factory=list)
     scratch: tuple | None = None  # (slot, shape) of a runtime-owned buffer (TABLE_DENSE: T2)
     folds: tuple | None = None  # (f0, f1): the step covers this fold range only (staged backward)
+    flags: int = 0  # extra ckb_step_desc_t flags (CKB_STEP_NO_GATHER / CKB_STEP_TABLE_INPUT)
+    # CKB_STEP_TABLE_INPUT: (table step id, absorbed sum step id, T2 slot) of the fused input pair
+    table_input: tuple | None = None
 
 
 @dataclass
@@ -222,10 +226,10 @@ class GradStage:
     pieces: list  # (binding index, fold begin, fold end) of the gradients that become final
 
 
-def _rows64(lay, sid: int) -> bool:
+def _rows64(lay, sid: int, gathered: bool = True) -> bool:
     """All arena / gradient-arena row offsets of step `sid` are multiples of 64 floats
     (CKB_STEP_ROWS64: the TMA-fed kernels address the arenas as matrices of 64-float rows)."""
-    for arr in (lay.in_rows[sid], lay.cons_rows[sid]):
+    for arr in ((lay.in_rows[sid] if gathered else None), lay.cons_rows[sid]):
         if arr is not None and arr.size and np.any(arr % 64):
             return False
     return lay.out_off[sid] % 64 == 0 and (lay.gin_off[sid] < 0 or lay.gin_off[sid] % 64 == 0)
@@ -328,6 +332,16 @@ class _DeviceState:
             self._sampling = {"row0": row0, "rows": int(row0[-1]), "in_rows": in_rows}
         return self._sampling
 
+    def table_folds(self, sid: int) -> int:
+        """Device (F*H) int64 table of the folds step `sid` reads (CKB_STEP_TABLE_INPUT)."""
+        key = ("table_folds", sid)
+        if key not in self.tables[sid]:
+            a = np.ascontiguousarray(self.rt.plan.steps[sid].in_fold.astype(np.int64))
+            t = torch.from_numpy(a).to(self.device)
+            self.keep.append(t)
+            self.tables[sid][key] = t.data_ptr()
+        return self.tables[sid][key]
+
     def grad_buffer(self, slot: int) -> Tensor:
         g = self.eff_grad.get(slot)
         if g is None:
@@ -353,8 +367,8 @@ class _DeviceState:
             f0, f1 = es.folds if es.folds is not None else (0, s.num_folds)
             d.num_folds, d.arity = f1 - f0, s.arity
             d.k_in, d.k_out = max(s.num_input_units, 0), s.num_output_units
-            d.flags = L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0
-            if _rows64(lay, es.out_sid):
+            d.flags = (L.DENSE_CONCAT if (s.kind == "sum" and s.arity > 1) else 0) | es.flags
+            if _rows64(lay, es.out_sid, gathered=es.table_input is None):
                 d.flags |= L.STEP_ROWS64
             if rt.is_complex:
                 d.flags |= L.STEP_COMPLEX
@@ -377,6 +391,15 @@ class _DeviceState:
             d.int_slot = rt.int_slots.get(es.sids[0], -1) if es.kind != STEP_TABLE_DENSE else -1
             cp = lay.cons_ptr[es.out_sid]
             d.max_consumers = int(np.max(np.diff(cp))) if len(cp) > 1 else 0
+            if es.table_input is not None:
+                # the layer gathers rows of the pair's T2 table: in_rows = table FOLDS, u lives in
+                # the arena block of the absorbed sum layer (never materialised in this plan)
+                tsid, cid, t2 = es.table_input
+                d.slot[1] = t2
+                d.scope_var = self.tables[tsid]["scope_var"]
+                d.in_rows = self.table_folds(es.out_sid)
+                d.num_states = int(plan.steps[tsid].config.get("num_categories", plan.steps[tsid].config.get("num_states", 0)))
+                d.aux_off = int(lay.out_off[cid])
         # the logsumexp ops come first: the backward pass runs the ops in reverse, and theirs ADDS
         # to the logits gradient the table op has written by then
         op_list = [(L.POP_LSE_ROWS, src, dst, rows, cols, 0, 0.0, 0.0)
@@ -417,7 +440,7 @@ class _DeviceState:
 
 
 class PlanRuntime:
-    def __init__(self, plan: CircuitPlan, *, fuse_tables: bool = True):
+    def __init__(self, plan: CircuitPlan, *, fuse_tables: bool = True, fuse_table_inputs: bool = True):
         plan.validate()
         self.is_complex = plan.semiring == "complex-lse-sum"
         if not self.is_complex and any(s.kind == "tensordot" for s in plan.steps):
@@ -503,6 +526,8 @@ class PlanRuntime:
                                       scratch=(t2, (c.num_folds, V, c.num_output_units))))
             else:
                 fused.append(plain[sid])
+        if fuse_table_inputs:
+            self._fuse_table_inputs(fused)
         # "masked": the plain step list plus the logsumexp ops of unnormalised categoricals
         self.exec_plans = {"plain": plain, "fused": fused, "masked": plain}
         self.n_slots = n
@@ -523,7 +548,8 @@ class PlanRuntime:
         self.last_synced_bytes = 0
 
     # ------------------------------------------------------------------ staged backward
-    def enable_gradient_stages(self, chunks: int = 4, bucket_bytes: int = 8 << 20) -> bool:
+    def enable_gradient_stages(self, chunks: int = 4, bucket_bytes: int = 8 << 20,
+                               chunk_steps: bool = False) -> bool:
         """Prepare a backward pass that finishes the parameter gradients GROUP BY GROUP, so that a
         data-parallel wrapper can all-reduce one group while the next is still being computed
         ("bottom layers hold most of the bytes and finish last, so bucket
@@ -531,7 +557,11 @@ class PlanRuntime:
         `bucket_bytes` of gradients (each stage = some steps + the parameter ops of their
         weights); the large input tables (Categorical / Embedding, alone or fused with their
         dense sum: the bulk of the parameters, and last in the backward pass) follow in `chunks`
-        fold ranges, each with the parameter ops of its slice.  The stages live in extra
+        fold ranges, each with the parameter ops of its slice -- by default only the PARAMETER OP
+        of a large table is cut into fold ranges (its gradient leaves in `chunks` pieces while the
+        next range is transformed); `chunk_steps` also cuts the layer's own backward kernels, which
+        starts the first collective earlier but runs them as smaller, less efficient launches
+        (measured on 2 GPUs: not worth it at the north-star shape).  The stages live in extra
         execution plans ("fused_sync", "plain_sync") used by the backward pass only while
         `grad_sync` is set; values are bit-equal to the unstaged pass (same kernels, same order
         within every fold).  Returns False (nothing changes) for complex plans and plans with
@@ -579,29 +609,54 @@ class PlanRuntime:
             rest = [es for es in base if not any(es is t for t in big)]
             steps: list[ExecStep] = []
             ops: list[tuple] = []
-            chunk_stages = []
-            for c in range(chunks if big else 0):
-                s0, o0, pieces = len(steps), len(ops), []
+            tail_stages = []  # stages of the big input steps, in backward order
+            if big and chunk_steps:
+                for c in range(chunks):
+                    s0, o0, pieces = len(steps), len(ops), []
+                    for es in big:
+                        F = self.plan.steps[es.out_sid].num_folds
+                        f0, f1 = c * F // chunks, (c + 1) * F // chunks
+                        slots = []
+                        for slot in es.slots:
+                            owner = [b for sid in es.sids for b in by_sid.get(sid, []) if b.dst_slot == slot]
+                            if owner:
+                                (b,) = owner
+                                src = alias(b.src_slot, f0 * int(np.prod(b.src_shape[1:])))
+                                dst = alias(b.dst_slot, f0 * int(np.prod(b.eff_shape[1:])))
+                                ops.append(op_of(b, src, dst, b.native[1] // F * (f1 - f0)))
+                                pieces.append((bidx[id(b)], f0, f1))
+                                slots.append(dst)
+                            elif es.scratch is not None and slot == es.scratch[0]:
+                                slots.append(alias(slot, f0 * int(np.prod(es.scratch[1][1:]))))
+                            else:
+                                slots.append(slot)
+                        steps.append(ExecStep(es.kind, f"{es.label}[{f0}:{f1}]", es.sids, es.out_sid, slots,
+                                              scratch=es.scratch, folds=(f0, f1), flags=es.flags))
+                    tail_stages.insert(0, GradStage((s0, len(steps)), (o0, len(ops)), pieces))
+            elif big:
+                # whole steps; the parameter op of every large tensor in `chunks` fold ranges
+                steps = list(big)
+                o0, pieces, split = 0, [], []
                 for es in big:
-                    F = self.plan.steps[es.out_sid].num_folds
-                    f0, f1 = c * F // chunks, (c + 1) * F // chunks
-                    slots = []
-                    for slot in es.slots:
-                        owner = [b for sid in es.sids for b in by_sid.get(sid, []) if b.dst_slot == slot]
-                        if owner:
-                            (b,) = owner
-                            src = alias(b.src_slot, f0 * int(np.prod(b.src_shape[1:])))
-                            dst = alias(b.dst_slot, f0 * int(np.prod(b.eff_shape[1:])))
-                            ops.append(op_of(b, src, dst, b.native[1] // F * (f1 - f0)))
-                            pieces.append((bidx[id(b)], f0, f1))
-                            slots.append(dst)
-                        elif es.scratch is not None and slot == es.scratch[0]:
-                            slots.append(alias(slot, f0 * int(np.prod(es.scratch[1][1:]))))
-                        else:
-                            slots.append(slot)
-                    steps.append(ExecStep(es.kind, f"{es.label}[{f0}:{f1}]", es.sids, es.out_sid, slots,
-                                          scratch=es.scratch, folds=(f0, f1)))
-                chunk_stages.append(GradStage((s0, len(steps)), (o0, len(ops)), pieces))
+                    for sid in es.sids:
+                        for b in by_sid.get(sid, []):
+                            if 4 * int(np.prod(b.src_shape)) >= bucket_bytes and b.src_shape[0] >= chunks:
+                                split.append(b)
+                                continue
+                            if b.native is not None:
+                                ops.append(op_of(b))
+                            pieces.append((bidx[id(b)], 0, b.src_shape[0]))
+                tail_stages.append(GradStage((0, len(steps)), (o0, len(ops)), pieces))
+                for c in range(chunks):
+                    o0, pieces = len(ops), []
+                    for b in split:
+                        F = b.src_shape[0]
+                        f0, f1 = c * F // chunks, (c + 1) * F // chunks
+                        src = alias(b.src_slot, f0 * int(np.prod(b.src_shape[1:])))
+                        dst = alias(b.dst_slot, f0 * int(np.prod(b.eff_shape[1:])))
+                        ops.append(op_of(b, src, dst, b.native[1] // F * (f1 - f0)))
+                        pieces.append((bidx[id(b)], f0, f1))
+                    tail_stages.append(GradStage((0, 0), (o0, len(ops)), pieces))
             # the other steps keep their order; stages are cut walking them backwards
             n_big = len(steps)
             steps += rest
@@ -623,10 +678,38 @@ class PlanRuntime:
                         stages[-1] = GradStage((i, last.steps[1]), last.ops, last.pieces)
                     hi, acc = i, 0
             self.exec_plans[which + "_sync"] = steps
-            self.grad_stages[which] = stages + chunk_stages[::-1]
+            self.grad_stages[which] = stages + tail_stages
             self.sync_ops[which + "_sync"] = ops
         self.n_slots = n
         return True
+
+    def _fuse_table_inputs(self, fused: list) -> None:
+        """A CP-T layer (Hadamard + dense) all of whose inputs are rows of ONE fused table pair, and
+        which is that pair's only reader, gathers the table rows itself (CKB_STEP_TABLE_INPUT): the
+        pair's (F', B, K) output block is never written -- the sum of the H gathered rows goes into
+        it instead, (F, B, K), and both passes of the layer read that."""
+        plan, lay = self.plan, self.layout
+        readers: dict[int, set] = {}
+        for cid, c in enumerate(plan.steps):
+            if not c.is_input:
+                for p in np.unique(c.in_step):
+                    readers.setdefault(int(p), set()).add(cid)
+        outs = set(int(s) for s in plan.out_step)
+        by_out = {es.out_sid: es for es in fused}
+        for td in [es for es in fused if es.kind == STEP_TABLE_DENSE]:
+            tsid, cid = td.sids
+            if cid in outs or len(readers.get(cid, ())) != 1:
+                continue
+            (rid,) = readers[cid]
+            r, es = plan.steps[rid], by_out.get(rid)
+            if (es is None or r.kind != "cpt" or not 1 < r.arity <= 4 or r.num_input_units % 4
+                    or r.num_folds * r.arity > 2 * plan.steps[cid].num_folds
+                    or lay.out_off[cid] % 64 or lay.gin_h[rid] != 1):
+                continue
+            td.flags |= L.STEP_NO_GATHER
+            # (the plain plan shares its ExecStep objects with the fused one: replace, not mutate)
+            fused[fused.index(es)] = dataclasses.replace(
+                es, flags=es.flags | L.STEP_TABLE_INPUT, table_input=(tsid, cid, td.scratch[0]))
 
     def invalidate_parameter_cache(self) -> None:
         """Forget the cached effective parameters (call after changing parameter storage behind
@@ -1072,15 +1155,17 @@ class _PlanFn(torch.autograd.Function):
                 h = st.handle(call.which + "_sync")
                 flat, offs, n = rt.last_flat_grad, rt.last_flat_offsets, 0
                 for stage in rt.grad_stages[call.which]:
-                    L.check(
-                        lib.ckb_plan_backward(h, stage.steps[0], stage.steps[1], B, xp, call.x_is_float,
-                                              mp, call.mask_rows, call.tensors, grads,
-                                              ctx.arena.data_ptr(), garena.data_ptr(), ws.data_ptr(),
-                                              ws.numel(), 0, stream), "ckb_plan_backward")
-                    n += int(lib.ckb_plan_last_launches(h))
-                    L.check(lib.ckb_plan_param_ops(h, stage.ops[0], stage.ops[1], 1, call.tensors,
-                                                   grads, stream), "ckb_plan_param_ops")
-                    n += int(lib.ckb_plan_last_launches(h))
+                    if stage.steps[1] > stage.steps[0]:
+                        L.check(
+                            lib.ckb_plan_backward(h, stage.steps[0], stage.steps[1], B, xp, call.x_is_float,
+                                                  mp, call.mask_rows, call.tensors, grads,
+                                                  ctx.arena.data_ptr(), garena.data_ptr(), ws.data_ptr(),
+                                                  ws.numel(), 0, stream), "ckb_plan_backward")
+                        n += int(lib.ckb_plan_last_launches(h))
+                    if stage.ops[1] > stage.ops[0]:
+                        L.check(lib.ckb_plan_param_ops(h, stage.ops[0], stage.ops[1], 1, call.tensors,
+                                                       grads, stream), "ckb_plan_param_ops")
+                        n += int(lib.ckb_plan_last_launches(h))
                     sync(_stage_pieces(rt, stage, flat, offs))
                 rt.last_launches = n
             else:

@@ -83,6 +83,18 @@ typedef enum {
                               offsets stay in units per sample.  Kinds: TABLE (Embedding
                               layers/input.py:258-266, weights (F,K,V) complex), DENSE without
                               CONCAT, TUCKER (arity 2), HADAMARD, CONSTANT (log-space value)       */
+#define CKB_STEP_TABLE_INPUT 16 /* on a DENSE step without CONCAT: its H inputs per fold are rows of
+                              the (F', V, Ki) table T2 of a TABLE_DENSE step, selected by the
+                              evidence -- slot[1] = T2, scope_var = the variables of the F' table
+                              folds, in_rows (F*H) = TABLE FOLD indices (not arena offsets),
+                              num_states = V.  Forward: u[f,b,:] = sum_h T2[fold_h, x[b,var_h], :]
+                              is gathered once into the arena block at aux_off (the block of the
+                              layer that is no longer materialised) and the layer runs on u with
+                              arity 1; backward re-reads u.  Half the traffic of gathering the
+                              rows and re-reading them (Hadamard of table rows,
+                              layers/optimized.py:171-178 over layers/input.py:399-412)           */
+#define CKB_STEP_NO_GATHER 32 /* on a TABLE_DENSE step: forward only builds T2; its consumer gathers
+                              (CKB_STEP_TABLE_INPUT).  Backward unchanged.                        */
 #define CKB_STEP_REAL_TABLE 8 /* with CKB_STEP_COMPLEX on a TABLE step: the table is the REAL (F,V,K)
                               log-table of a Categorical layer, cast to complex (semiring.py:511-514) */
 
@@ -106,6 +118,7 @@ typedef struct {
                            CONSTANT: {value}   DENSE/TUCKER: {W (F,Ko,Kred)}   MIXING: {w (F,K,H)} */
   int32_t int_slot;   /* slot of the (F,Ko) values an integrated variable yields, -1 = zeros   */
   int32_t max_consumers; /* largest cons_ptr[f+1]-cons_ptr[f] (lets kernels pick a fast path)   */
+  int64_t aux_off;    /* CKB_STEP_TABLE_INPUT: per-sample float offset of the (F,B,Ki) block u   */
 } ckb_step_desc_t;
 
 /* Parameter re-parameterisation ops, run before the layers (forward) and after them (backward).

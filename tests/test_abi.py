@@ -39,11 +39,12 @@ def test_struct_layouts_match_header(lib):
     from cirkit_b200 import _lib
 
     # sizes the C compiler gives the two descriptor structs (natural alignment, LP64)
-    assert ctypes.sizeof(_lib.StepDesc) == 104
+    assert ctypes.sizeof(_lib.StepDesc) == 112
     assert ctypes.sizeof(_lib.ParamOp) == 40
     assert _lib.StepDesc.out_off.offset == 32 and _lib.StepDesc.in_rows.offset == 48
     assert _lib.StepDesc.slot.offset == 80 and _lib.StepDesc.int_slot.offset == 96
-    assert _lib.StepDesc.max_consumers.offset == 100
+    assert _lib.StepDesc.max_consumers.offset == 100 and _lib.StepDesc.aux_off.offset == 104
+    assert ctypes.sizeof(_lib.SampleStep) == 72 and _lib.SampleStep.in_sel_rows.offset == 32
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):

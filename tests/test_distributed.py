@@ -170,7 +170,7 @@ def test_gradient_stages_partition_the_backward_pass():
 
     g = Golden("qt28_cp_k64")
     rt = PlanRuntime(g.plan)
-    assert rt.enable_gradient_stages(4)
+    assert rt.enable_gradient_stages(4, chunk_steps=True)
     fused, sync = rt.exec_plans["fused"], rt.exec_plans["fused_sync"]
     td = [es for es in fused if es.kind == STEP_TABLE_DENSE]
     assert len(td) == 1 and len(sync) == len(fused) + 3
@@ -206,6 +206,30 @@ def test_gradient_stages_partition_the_backward_pass():
     assert first < 0.2 * flat.numel()
 
 
+def test_gradient_stages_default_cuts_only_the_parameter_ops():
+    """Default staging: the layers' own backward kernels stay whole launches; only the parameter
+    ops of the large input tensors (Categorical table, first sum weights) go out in fold ranges."""
+    import numpy as np
+
+    from cirkit_b200.runtime import PlanRuntime, _stage_pieces
+
+    g = Golden("qt28_cp_k64")
+    rt = PlanRuntime(g.plan)
+    assert rt.enable_gradient_stages(4)
+    fused, sync, stages = rt.exec_plans["fused"], rt.exec_plans["fused_sync"], rt.grad_stages["fused"]
+    assert len(sync) == len(fused) and all(es.folds is None for es in sync)
+    assert [st.steps for st in stages] == [(1, len(sync)), (0, 1)] + [(0, 0)] * 4
+    assert sorted(i for st in stages for i in range(*st.ops)) == list(range(len(rt.sync_ops["fused_sync"])))
+    assert all(len(st.pieces) == 2 for st in stages[2:])  # table rows + sum-weight rows of a fold range
+    sizes = [-(-int(np.prod(b.src_shape)) // 4) * 4 for b in rt.bindings]
+    offs = list(np.cumsum([0] + sizes[:-1]))
+    flat = torch.zeros(sum(sizes))
+    for st in stages:
+        for piece in _stage_pieces(rt, st, flat, offs):
+            piece += 1
+    assert torch.equal(flat, torch.ones_like(flat))
+
+
 @pytest.mark.parametrize("name,which", [("pd32_cp_k4", "plain"), ("qt28_cp_k64", "plain"),
                                         ("qg8_cp_k4", "plain"), ("rbt12_gaussian_k5", "plain")])
 def test_gradient_stages_of_other_plans(name, which):
@@ -221,7 +245,8 @@ def test_gradient_stages_of_other_plans(name, which):
 
     plan = dataclasses.replace(g.plan, meta={"units": 4}).with_units(32) if name == "pd32_cp_k4" else g.plan
     rt = PlanRuntime(plan)
-    assert rt.enable_gradient_stages(4, bucket_bytes=1 << 20 if name != "qg8_cp_k4" else 1 << 10)
+    assert rt.enable_gradient_stages(4, bucket_bytes=1 << 20 if name != "qg8_cp_k4" else 1 << 10,
+                                     chunk_steps=name == "pd32_cp_k4")
     stages, sync = rt.grad_stages[which], rt.exec_plans[which + "_sync"]
     assert sorted(i for st in stages for i in range(*st.steps)) == list(range(len(sync)))
     assert sorted(i for st in stages for i in range(*st.ops)) == list(range(len(rt.sync_ops[which + "_sync"])))

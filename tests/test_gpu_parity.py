@@ -215,6 +215,52 @@ def test_table_fusion_matches_layer_by_layer_plan(name, dev):
         assert (a - b).abs().max().item() <= max(2e-6, 1e-4 * b.abs().max().item())
 
 
+@pytest.mark.parametrize("name,units,batch", [
+    ("qt8_cp_k4", None, 300), ("qt8_cp_k4", 64, 128), ("qt8_cp_k4", 64, 333), ("qt8_cp_k4", 32, 257),
+    ("qt8_cp_k4", 12, 130), ("qt28_cp_k64", None, 256),
+    # batches of at least 2 V: the gather serves the samples from table slices staged in shared memory
+    ("qt8_cp_k4", 64, 700), ("qt8_cp_k4", 32, 513), ("qt8_cp_k4", 8, 600), ("qt8_cp_k4", 128, 512),
+    ("qt28_cp_k64", None, 1024),
+])
+def test_table_rows_gathered_by_their_consumer(name, units, batch, dev):
+    """CKB_STEP_TABLE_INPUT: the CP-T layer over the fused input pair gathers the table rows itself
+    (one (F, B, K) block u = x0 + x1 instead of the pair's (2F, B, K) output).  Against the plan
+    that materialises the pair's output (same kernels otherwise) and against the float64 oracle;
+    ragged and tile-aligned batches, tcgen05 (K = 64), K = 32 and generic shapes."""
+    import dataclasses
+
+    from cirkit_b200 import B200Circuit, _lib
+    from oracle import OracleCircuit
+    from oracle.reference_eval import make_inputs
+
+    g = Golden(name)
+    plan = g.plan if units is None else dataclasses.replace(g.plan, meta={"units": 4}).with_units(units)
+    x = make_inputs(plan, batch, seed=6)
+    res = []
+    for fuse in (True, False):
+        cc = B200Circuit(plan, seed=17, fuse_table_inputs=fuse).to(dev)
+        steps = cc.runtime.exec_plans["fused"]
+        assert any(es.flags & _lib.STEP_TABLE_INPUT for es in steps) == fuse
+        y = cc(x.to(dev))
+        (-y.mean()).backward()
+        res.append((cc, y.detach(), [p.grad for p in cc.leaves]))
+    (cc, yf, gf), (_, yp, gp) = res
+    assert (yf - yp).abs().max().item() <= 5e-7 * yp.abs().max().item() + 1e-5
+    for a, b in zip(gf, gp):
+        assert (a - b).abs().max().item() <= max(2e-6, 1e-4 * b.abs().max().item())
+    oc = OracleCircuit(plan, dtype=torch.float64)
+    with torch.no_grad():
+        for p, v in zip(oc.leaves, cc.leaves):
+            p.copy_(v.double().cpu())
+    yo = oc(x)
+    (-yo.mean()).backward()
+    _check_forward(yf, yo.detach())
+    for i, (a, p) in enumerate(zip(gf, oc.leaves)):
+        err = (a.double().cpu() - p.grad).abs().max().item()
+        tol = grad_tolerance(p.grad, ll_max=float(yo.detach().abs().max()))
+        assert err <= tol, f"leaf {i}: {err:.3e} > {tol:.3e}"
+
+
 @pytest.mark.parametrize("batch", [8, 128, 200, 1024])
 def test_tensor_core_path_matches_simt(batch, dev):
     """K=64 layers run on tcgen05 (3xTF32) by default; the FP32 SIMT kernels are the yardstick."""

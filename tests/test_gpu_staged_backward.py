@@ -42,6 +42,7 @@ class _Recorder:
         return n
 
 
+@pytest.mark.parametrize("chunk_steps", [False, True])
 @pytest.mark.parametrize("name,units,batch,chunks,bucket", [
     ("qt28_cp_k64", None, 256, 4, 8 << 20),
     ("qt28_cp_k64", None, 64, 4, 2 << 20),  # plain plan (batch < V / 2): chunked Categorical step
@@ -50,7 +51,7 @@ class _Recorder:
     ("pd32_cp_k4", 16, 200, 4, 1 << 18),  # no fused input step: buckets over the inner layers
     ("qg8_cp_k4", None, 150, 2, 1 << 8),
 ])
-def test_staged_backward_matches_unstaged(dev, name, units, batch, chunks, bucket):
+def test_staged_backward_matches_unstaged(dev, name, units, batch, chunks, bucket, chunk_steps):
     from cirkit_b200 import B200Circuit
 
     g = Golden(name)
@@ -62,7 +63,7 @@ def test_staged_backward_matches_unstaged(dev, name, units, batch, chunks, bucke
         cc = B200Circuit(plan, seed=11).to(dev)
         rec = None
         if stage:
-            assert cc.runtime.enable_gradient_stages(chunks, bucket_bytes=bucket)
+            assert cc.runtime.enable_gradient_stages(chunks, bucket_bytes=bucket, chunk_steps=chunk_steps)
             rec = cc.runtime.grad_sync = _Recorder()
         y = cc(x)
         (-y.mean()).backward()
