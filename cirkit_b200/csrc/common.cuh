@@ -38,6 +38,37 @@ struct PerDeviceOnce {
   }
 };
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The step is a chain of ~40 dependent launches, many of them 10-20 us long: with plain stream
+// order every boundary costs the drain of one grid plus the launch latency and prologue of the
+// next.  Kernels that opt in call pdl_launch_dependents() first (the next grid of the stream may
+// be scheduled as soon as every CTA of this one has started), do the part of their prologue that
+// touches no global memory written by earlier kernels of the step (barrier set-up, TMEM
+// allocation, weight staging), and call pdl_wait() before anything else: it returns when the
+// preceding grid has completed and its writes are visible.  Launch them with launch_pdl().
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // CKB_PDL=0 switches the launch attribute off (plain stream order)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------ per-call context
 struct Ctx {
   int64_t B;

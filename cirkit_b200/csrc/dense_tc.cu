@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   const int n_tiles_total = (int)((a.B + TM - 1) / TM);
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
+  pdl_launch_dependents();
   if (n_tiles <= 0) return;
 
   // input row pointers first: their (dependent) index loads overlap the rest of the setup
@@ -120,12 +121,15 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&s.tmem_base, 256);
+  // (the weights come out of the parameter ops, several launches back: no dependency on the
+  //  preceding grid, whose output -- this layer's input rows -- is read after pdl_wait())
   stage_weights<false, kThreads>(a.W + (int64_t)f * KK * KK, smem_u32(s.w), tid);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  pdl_wait();
 
   if (warp == kMmaWarp) {
     // ================= MMA issuer =================
@@ -1165,10 +1169,9 @@ int dense_tc_fwd(const DenseArgs& a, int F, Ctx& c) {
   splits = ceil_div(n_tiles, tiles_per_cta);
   dim3 grid(splits, F);
   if ((g_tc_flags & 3) == 3)
-    dense_tc_fwd_kernel<true><<<grid, kThreads, smem, c.stream>>>(a, tiles_per_cta);
+    CKB_CUDA_CHECK(launch_pdl(dense_tc_fwd_kernel<true>, grid, dim3(kThreads), smem, c.stream, a, tiles_per_cta));
   else
-    dense_tc_fwd_kernel<false><<<grid, kThreads, smem, c.stream>>>(a, tiles_per_cta);
-  CKB_LAUNCH_CHECK();
+    CKB_CUDA_CHECK(launch_pdl(dense_tc_fwd_kernel<false>, grid, dim3(kThreads), smem, c.stream, a, tiles_per_cta));
   c.launches++;
   return CKB_OK;
 }

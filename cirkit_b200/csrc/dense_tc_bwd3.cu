@@ -139,13 +139,43 @@ dense_tc_bwd3_kernel(DenseArgs a, const __grid_constant__ CUtensorMap tmX,
   const int n_tiles_total = (int)(a.B / TM3);
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
+  pdl_launch_dependents();
   if (n_tiles <= 0) return;
 
-  if (tid == 0) {
+  // The producer lane sets up its own ring barriers and puts the first kStages slots in flight
+  // BEFORE the weight image is staged: the HBM latency of the first tile (~2 us) then overlaps the
+  // CTA's set-up instead of following it (a CTA lives for 10-70 us, the set-up used to be ~8).
+  int64_t x0_row = 0, x1_row = 0, y_row = 0, g_row = 0;
+  int preissued = 0;
+  const uint32_t slot_bytes = (a.H == 2 ? 4u : 3u) * 2u * kStageRows * 128u;
+  auto issue_slot = [&](int i) {
+    const int slot = i % kStages;
+    mbar_arrive_expect_tx(&s.full[slot], slot_bytes);
+    const int row = (t_begin * TM3) + i * kStageRows;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      tma_load_2d(s.raw[slot][0][ch], &tmX, 32 * ch, (int)(x0_row + row), &s.full[slot]);
+      if (a.H == 2) tma_load_2d(s.raw[slot][1][ch], &tmX, 32 * ch, (int)(x1_row + row), &s.full[slot]);
+      tma_load_2d(s.raw[slot][2][ch], &tmY, 32 * ch, (int)(y_row + row), &s.full[slot]);
+      tma_load_2d(s.raw[slot][3][ch], &tmG, 32 * ch, (int)(g_row + row), &s.full[slot]);
+    }
+  };
+  if (warp == kLoadWarp3 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], kWorkers3);  // every worker passes every slot (see the ring protocol below)
     }
+    fence_barrier_init();
+    pdl_wait();  // y, g (and the arenas behind x) are outputs of earlier grids of the stream
+    // rows are addressed as rows of 64 floats relative to the base of each tensor map
+    x0_row = a.in_rows ? (a.B * a.in_rows[f * a.H]) / KK : (int64_t)f * a.B;
+    x1_row = a.H == 2 ? (a.B * a.in_rows[f * a.H + 1]) / KK : 0;
+    y_row = (int64_t)f * a.B;
+    g_row = a.gs.cons_ptr ? (a.gs.B * a.gs.cons_rows[a.gs.cons_ptr[f]]) / KK : (int64_t)f * a.gs.B;
+    preissued = min(kStages, 2 * n_tiles);
+    for (int i = 0; i < preissued; ++i) issue_slot(i);
+  }
+  if (tid == 0) {
     mbar_init(&s.ab_full, kWorkers3);
     mbar_init(&s.img_free, 1);
     mbar_init(&s.d1_full, 1);
@@ -162,30 +192,16 @@ dense_tc_bwd3_kernel(DenseArgs a, const __grid_constant__ CUtensorMap tmX,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  pdl_wait();  // everything below may touch global memory the preceding grid wrote (du, dW slabs)
   // TMEM columns: D1 [0,128) (main | correction), D2 [128,256), r_hi [256,320), r_lo [320,384)
   constexpr uint32_t kD2Col = 128, kRhiCol = 256, kRloCol = 320;
 
   if (warp == kLoadWarp3) {
     // ================= producer: TMA loads, 32 rows x 4 arrays per ring slot =================
     if (lane == 0) {
-      // rows are addressed as rows of 64 floats relative to the base of each tensor map
-      const int64_t x0_row = a.in_rows ? (a.B * a.in_rows[f * a.H]) / KK : (int64_t)f * a.B;
-      const int64_t x1_row = a.H == 2 ? (a.B * a.in_rows[f * a.H + 1]) / KK : 0;
-      const int64_t y_row = (int64_t)f * a.B;
-      const int64_t g_row = a.gs.cons_ptr ? (a.gs.B * a.gs.cons_rows[a.gs.cons_ptr[f]]) / KK : (int64_t)f * a.gs.B;
-      const uint32_t bytes = (a.H == 2 ? 4u : 3u) * 2u * kStageRows * 128u;
-      for (int i = 0; i < 2 * n_tiles; ++i) {
-        const int slot = i % kStages;
-        mbar_wait_relaxed(&s.empty[slot], ((i / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&s.full[slot], bytes);
-        const int row = (t_begin * TM3) + i * kStageRows;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          tma_load_2d(s.raw[slot][0][ch], &tmX, 32 * ch, (int)(x0_row + row), &s.full[slot]);
-          if (a.H == 2) tma_load_2d(s.raw[slot][1][ch], &tmX, 32 * ch, (int)(x1_row + row), &s.full[slot]);
-          tma_load_2d(s.raw[slot][2][ch], &tmY, 32 * ch, (int)(y_row + row), &s.full[slot]);
-          tma_load_2d(s.raw[slot][3][ch], &tmG, 32 * ch, (int)(g_row + row), &s.full[slot]);
-        }
+      for (int i = preissued; i < 2 * n_tiles; ++i) {
+        mbar_wait_relaxed(&s.empty[i % kStages], ((i / kStages) & 1) ^ 1);
+        issue_slot(i);
       }
     }
   } else if (warp == kStoreWarp3) {
@@ -573,9 +589,8 @@ int dense_tc_bwd3(const DenseArgs& a_in, int F, float* dW, Ctx& c, char* ws, siz
     CKB_CUDA_CHECK(cudaFuncSetAttribute(dense_tc_bwd3_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(splits, F);
-  dense_tc_bwd3_kernel<true><<<grid, kThreads3, smem, c.stream>>>(a, tmX, tmY, tmG, tmDU, tpc, dW ? 1 : 0,
-                                                                  tc_flags());
-  CKB_LAUNCH_CHECK();
+  CKB_CUDA_CHECK(launch_pdl(dense_tc_bwd3_kernel<true>, grid, dim3(kThreads3), smem, c.stream, a, tmX, tmY, tmG,
+                            tmDU, tpc, dW ? 1 : 0, tc_flags()));
   c.launches++;
   if (dW && splits > 1) return reduce_partials(a.dWp, dW, (int64_t)n, splits, c);
   return CKB_OK;

@@ -198,16 +198,23 @@ __global__ void __launch_bounds__(256) table_pair_gather_smem_kernel(
     const float* __restrict__ T2, const int32_t* __restrict__ scope_var, const int64_t* __restrict__ folds,
     const void* __restrict__ xT, int x_is_float, float* __restrict__ u, int64_t B, int K, int V, int H,
     int KT) {
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float tab[];                     // [H][V][KT]
   int* st = reinterpret_cast<int*>(tab + (size_t)H * V * KT);      // [2][H][kStageRows] row offsets
   const int f = blockIdx.y, k0 = blockIdx.x * KT;
   const int tid = threadIdx.x;
   const int KT4 = KT >> 2;  // float4 chunks per staged row: 8 for KT = 32
   int var[kPairMaxH];
+  int64_t tfs[kPairMaxH];
+#pragma unroll
+  for (int h = 0; h < kPairMaxH; ++h) {  // (index tables: static, not written inside the step)
+    tfs[h] = h < H ? folds[(int64_t)f * H + h] : 0;
+    var[h] = h < H ? scope_var[tfs[h]] : 0;
+  }
+  pdl_wait();
 #pragma unroll
   for (int h = 0; h < kPairMaxH; ++h) {
-    const int64_t tf = h < H ? folds[(int64_t)f * H + h] : 0;
-    var[h] = h < H ? scope_var[tf] : 0;
+    const int64_t tf = tfs[h];
     if (h < H) {
       const float* src = T2 + tf * V * K + k0;
       for (int i = tid; i < V * KT4; i += 256) {
@@ -273,10 +280,9 @@ int table_pair_gather(const ckb_step_desc_t& d, Ctx& c, float* u) {
       CKB_CUDA_CHECK(cudaFuncSetAttribute(table_pair_gather_smem_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     dim3 grid(d.k_in / KT, d.num_folds);
-    table_pair_gather_smem_kernel<<<grid, 256, smem, c.stream>>>(
-        c.tensors[d.slot[1]], d.scope_var, d.in_rows, c.xT, c.x_is_float, u, c.B, d.k_in, d.num_states,
-        d.arity, KT);
-    CKB_LAUNCH_CHECK();
+    CKB_CUDA_CHECK(launch_pdl(table_pair_gather_smem_kernel, grid, dim3(256), smem, c.stream,
+                              (const float*)c.tensors[d.slot[1]], d.scope_var, d.in_rows, c.xT, c.x_is_float, u,
+                              c.B, d.k_in, d.num_states, d.arity, KT));
     c.launches++;
     return CKB_OK;
   }
@@ -300,11 +306,14 @@ int table_pair_gather(const ckb_step_desc_t& d, Ctx& c, float* u) {
 // samples in ascending order -- and then each warp sums the gradient rows of whole buckets in
 // registers and writes each table row once.  No floating-point atomics: the result is
 // deterministic, and every g row is read exactly once as one contiguous segment.
-constexpr int kTableBwdThreads = 1024;
+constexpr int kTableBwdThreads = 1024;  // most warps a CTA of this kernel has (sizes its shared memory)
 constexpr int kTableMaxCons = 8;
 
-template <int NT>  // units per lane: a CTA covers 32*NT units
-__global__ void __launch_bounds__(kTableBwdThreads, 1)
+// THREADS = 1024: one CTA per SM, for chunks of up to 32768 samples; 512: three CTAs per SM, so the
+// bucket sort of one overlaps the row sums (the HBM stream) of the others -- the default for the
+// chunk sizes of a training batch.  Same bucket lists, same summation order: bit-identical results.
+template <int NT, int THREADS>  // NT units per lane: a CTA covers 32*NT units
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 3)
 table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* __restrict__ xT,
                  int x_is_float, const uint8_t* __restrict__ maskT, int64_t mask_ld,
                  float* __restrict__ out, int64_t B, int K, int V, int64_t chunk) {
@@ -514,16 +523,20 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   int64_t chunk;
   table_bwd_config(d, c.B, splits, chunk);
   const int V = d.num_states;
-  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 4 + (size_t)(kTableBwdThreads / 32) * V * 4 + 16;
+  const int threads = chunk <= 8192 ? 512 : kTableBwdThreads;
+  const size_t smem = (size_t)(2 * V + 1) * 4 + (size_t)chunk * 4 + (size_t)(threads / 32) * V * 4 + 16;
   if (smem > 200 * 1024) {
     set_error("table_bwd: %d states do not fit shared memory", V);
     return CKB_ERR_UNSUPPORTED;
   }
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   const size_t n = (size_t)d.num_folds * V * d.k_out;
   float* out = dT;
@@ -537,8 +550,10 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   GradSrc gs{c.garena, d.cons_ptr, d.cons_rows, c.B};
   const int nt = table_bwd_nt(d.k_out);
   dim3 grid(splits, d.num_folds, ceil_div(d.k_out, 32 * nt));
-  auto kern = nt == 1 ? table_bwd_kernel<1> : (nt == 2 ? table_bwd_kernel<2> : table_bwd_kernel<4>);
-  kern<<<grid, kTableBwdThreads, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
+  auto kern = threads == 512
+                  ? (nt == 1 ? table_bwd_kernel<1, 512> : (nt == 2 ? table_bwd_kernel<2, 512> : table_bwd_kernel<4, 512>))
+                  : (nt == 1 ? table_bwd_kernel<1, 1024> : (nt == 2 ? table_bwd_kernel<2, 1024> : table_bwd_kernel<4, 1024>));
+  kern<<<grid, threads, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
                                                   c.mask_ld, out, c.B, d.k_out, V, chunk);
   CKB_LAUNCH_CHECK();
   c.launches++;
@@ -742,6 +757,8 @@ int external_bwd(const ckb_step_desc_t& d, Ctx& c) {
 // ------------------------------------------------------------------------------------------
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                        int64_t n, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     // fixed left-to-right order (deterministic), but 16 independent loads in flight at a time
@@ -761,7 +778,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
 
 int reduce_partials(const float* partial, float* out, int64_t n, int splits, Ctx& c) {
   const int bx = (int)min64(ceil_div(n, 256), 8 * kNumSMs);
-  reduce_partials_kernel<<<max(bx, 1), 256, 0, c.stream>>>(partial, out, n, splits);
+  CKB_CUDA_CHECK(launch_pdl(reduce_partials_kernel, dim3(max(bx, 1)), dim3(256), 0, c.stream, partial, out, n, splits));
   CKB_LAUNCH_CHECK();
   c.launches++;
   return CKB_OK;

@@ -331,32 +331,94 @@ struct MultiSoftmax {
   float* out[kMultiOps];       // fwd: dst      bwd: dsrc
 };
 
+// A warp works on kMsRows rows at once and keeps each row in registers (up to 4 elements per lane,
+// rows of at most 128 columns -- every sum layer of width <= 128): one global read per element,
+// the loads of all rows in flight together.  Longer rows take the three-pass loop.
+constexpr int kMsRows = 4;
 template <bool BWD>
 __global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t total = m.row_end[m.n - 1];
-  for (int64_t gr = (int64_t)blockIdx.x * nwarps + warp; gr < total; gr += (int64_t)gridDim.x * nwarps) {
-    int op = 0;
-    while (gr >= m.row_end[op]) ++op;
-    const int64_t r = gr - (op ? m.row_end[op - 1] : 0);
-    const int cols = m.cols[op];
-    const float* a = m.a[op] + r * cols;
-    float* out = m.out[op] + r * cols;
-    if (!BWD) {
-      float mx = -INFINITY;
-      for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, a[c]);
-      mx = warp_max(mx);
-      float z = 0.f;
-      for (int c = lane; c < cols; c += 32) z += expf(a[c] - mx);
-      z = warp_sum(z);
-      const float inv = 1.f / z;
-      for (int c = lane; c < cols; c += 32) out[c] = expf(a[c] - mx) * inv;
-    } else {
-      const float* g = m.b[op] + r * cols;
-      float dot = 0.f;
-      for (int c = lane; c < cols; c += 32) dot = fmaf(a[c], g[c], dot);
-      dot = warp_sum(dot);
-      for (int c = lane; c < cols; c += 32) out[c] = a[c] * (g[c] - dot);
+  const int64_t stride = (int64_t)gridDim.x * nwarps * kMsRows;
+  for (int64_t g0 = ((int64_t)blockIdx.x * nwarps + warp) * kMsRows; g0 < total; g0 += stride) {
+    const float* a[kMsRows];
+    const float* g[kMsRows];
+    float* out[kMsRows];
+    int cols[kMsRows];
+    bool small = true;
+#pragma unroll
+    for (int r = 0; r < kMsRows; ++r) {
+      const int64_t gr = g0 + r;
+      cols[r] = 0;
+      a[r] = g[r] = nullptr;
+      out[r] = nullptr;
+      if (gr < total) {
+        int op = 0;
+        while (gr >= m.row_end[op]) ++op;
+        const int64_t row = gr - (op ? m.row_end[op - 1] : 0);
+        cols[r] = m.cols[op];
+        a[r] = m.a[op] + row * cols[r];
+        out[r] = m.out[op] + row * cols[r];
+        if (BWD) g[r] = m.b[op] + row * cols[r];
+        small &= cols[r] <= 128;
+      }
+    }
+    if (small) {
+      float x[kMsRows][4], y[kMsRows][4];
+#pragma unroll
+      for (int r = 0; r < kMsRows; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = lane + 32 * j;
+          const bool ok = c < cols[r];
+          x[r][j] = ok ? __ldg(a[r] + c) : (BWD ? 0.f : -INFINITY);
+          if (BWD) y[r][j] = ok ? __ldg(g[r] + c) : 0.f;
+        }
+#pragma unroll
+      for (int r = 0; r < kMsRows; ++r) {
+        if (cols[r] == 0) continue;  // warp-uniform
+        if (!BWD) {
+          const float mx = warp_max(fmaxf(fmaxf(x[r][0], x[r][1]), fmaxf(x[r][2], x[r][3])));
+          float e[4], z = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            e[j] = expf(x[r][j] - mx);  // exp(-inf) = 0 for the padding
+            z += e[j];
+          }
+          const float inv = 1.f / warp_sum(z);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < cols[r]) out[r][lane + 32 * j] = e[j] * inv;
+        } else {
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dot = fmaf(x[r][j], y[r][j], dot);
+          dot = warp_sum(dot);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < cols[r]) out[r][lane + 32 * j] = x[r][j] * (y[r][j] - dot);
+        }
+      }
+      continue;
+    }
+    for (int r = 0; r < kMsRows; ++r) {
+      if (cols[r] == 0) continue;
+      const int n = cols[r];
+      if (!BWD) {
+        float mx = -INFINITY;
+        for (int c = lane; c < n; c += 32) mx = fmaxf(mx, a[r][c]);
+        mx = warp_max(mx);
+        float z = 0.f;
+        for (int c = lane; c < n; c += 32) z += expf(a[r][c] - mx);
+        z = warp_sum(z);
+        const float inv = 1.f / z;
+        for (int c = lane; c < n; c += 32) out[r][c] = expf(a[r][c] - mx) * inv;
+      } else {
+        float dot = 0.f;
+        for (int c = lane; c < n; c += 32) dot = fmaf(a[r][c], g[r][c], dot);
+        dot = warp_sum(dot);
+        for (int c = lane; c < n; c += 32) out[r][c] = a[r][c] * (g[r][c] - dot);
+      }
     }
   }
 }
@@ -439,7 +501,7 @@ int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
   int64_t rows = 0;
   auto flush = [&]() -> int {
     if (m.n == 0) return CKB_OK;
-    const int blocks = (int)max64(1, min64(ceil_div(rows, 8), 8 * kNumSMs));
+    const int blocks = (int)max64(1, min64(ceil_div(rows, 8 * kMsRows), 8 * kNumSMs));
     if (bwd) multi_softmax_kernel<true><<<blocks, 256, 0, c.stream>>>(m);
     else multi_softmax_kernel<false><<<blocks, 256, 0, c.stream>>>(m);
     CKB_LAUNCH_CHECK();

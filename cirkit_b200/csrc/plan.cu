@@ -1,6 +1,7 @@
 // Plan object and the C ABI (include/cirkit_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -10,6 +11,15 @@
 namespace ckb {
 
 static thread_local char g_error[512] = "";
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CKB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
