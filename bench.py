@@ -570,7 +570,7 @@ def main():
                     help="batch of the CPU arm (default: the per-GPU batch, i.e. the same config; "
                          "256 for the Tucker workload and 32 for pd32_cp_k128, whose full batch takes minutes per step)")
     ap.add_argument("--no-grad-allreduce", action="store_true")
-    ap.add_argument("--grad-chunks", type=int, default=4,
+    ap.add_argument("--grad-chunks", type=int, default=1,
                     help="N > 1: fold chunks of the input table in the staged backward pass whose "
                          "gradient all-reduces overlap the remaining backward work (0: one all-reduce after backward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

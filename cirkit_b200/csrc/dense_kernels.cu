@@ -221,6 +221,8 @@ __device__ __forceinline__ float ko1_load(const DenseArgs& a, int f, int64_t b, 
 }
 
 __global__ void dense_ko1_fwd_kernel(DenseArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float w[kKo1MaxPerLane];
@@ -240,6 +242,8 @@ __global__ void dense_ko1_fwd_kernel(DenseArgs a) {
 }
 
 __global__ void dense_ko1_bwd_kernel(DenseArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][32 * kKo1MaxPerLane];
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -295,8 +299,7 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
   if (dense128_tc_ok(a)) return dense128_tc_fwd(a, F, c);  // experimental, off by default
   if (dense_ko1_ok(a)) {
     dim3 grid(dense_ko1_blocks(F, a.B), F);
-    dense_ko1_fwd_kernel<<<grid, 256, 0, c.stream>>>(a);
-    CKB_LAUNCH_CHECK();
+    CKB_CUDA_CHECK(launch_pdl(dense_ko1_fwd_kernel, grid, dim3(256), 0, c.stream, a));
     c.launches++;
     return CKB_OK;
   }
@@ -702,8 +705,7 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
       a.dWp = (float*)ws;
     }
     dim3 grid(blocks, F);
-    dense_ko1_bwd_kernel<<<grid, 256, 0, c.stream>>>(a);
-    CKB_LAUNCH_CHECK();
+    CKB_CUDA_CHECK(launch_pdl(dense_ko1_bwd_kernel, grid, dim3(256), 0, c.stream, a));
     c.launches++;
     if (dW && blocks > 1) return reduce_partials(a.dWp, dW, (int64_t)n, blocks, c);
     return CKB_OK;

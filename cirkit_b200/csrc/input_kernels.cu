@@ -324,6 +324,8 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
   uint16_t* list = xs + chunk;                           // [chunk] sample ids grouped by state
   __shared__ const float* grows[kTableMaxCons];
   __shared__ int n_cons_s;
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y;
   const int k0 = blockIdx.z * (32 * NT);
   const int var = scope_var[f];
@@ -553,9 +555,8 @@ int table_bwd(const ckb_step_desc_t& d, Ctx& c) {
   auto kern = threads == 512
                   ? (nt == 1 ? table_bwd_kernel<1, 512> : (nt == 2 ? table_bwd_kernel<2, 512> : table_bwd_kernel<4, 512>))
                   : (nt == 1 ? table_bwd_kernel<1, 1024> : (nt == 2 ? table_bwd_kernel<2, 1024> : table_bwd_kernel<4, 1024>));
-  kern<<<grid, threads, smem, c.stream>>>(gs, d.scope_var, c.xT, c.x_is_float, c.maskT,
-                                                  c.mask_ld, out, c.B, d.k_out, V, chunk);
-  CKB_LAUNCH_CHECK();
+  CKB_CUDA_CHECK(launch_pdl(kern, grid, dim3(threads), smem, c.stream, gs, d.scope_var, c.xT, c.x_is_float,
+                            c.maskT, c.mask_ld, out, c.B, d.k_out, V, chunk));
   c.launches++;
   if (splits > 1) return reduce_partials(out, dT, (int64_t)n, splits, c);
   return CKB_OK;

@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(256) table_fwd_t_smem_kernel(const float* __re
                                                                float* __restrict__ dst, int K, int V) {
   extern __shared__ float tile[];  // [32][V + 1]
   __shared__ float lse[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y, k0 = blockIdx.x * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = min(32, K - k0), ld = V + 1;
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(256) table_bwd_t_smem_kernel(const float* __re
                                                                float* __restrict__ dsrc, int K, int V) {
   extern __shared__ float tile[];  // g [32][V + 1], then (MODE 0) exp(T) [32][V + 1]
   __shared__ float colsum[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y, k0 = blockIdx.x * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = min(32, K - k0), ld = V + 1;
@@ -242,7 +246,7 @@ static int launch_table_fwd_t(const float* src, float* dst, int64_t F, int K, in
     if (attr.first())
       CKB_CUDA_CHECK(cudaFuncSetAttribute(table_fwd_t_smem_kernel<MODE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    table_fwd_t_smem_kernel<MODE><<<grid, 256, smem, st>>>(src, dst, K, V);
+    CKB_CUDA_CHECK(launch_pdl(table_fwd_t_smem_kernel<MODE>, grid, dim3(256), smem, st, src, dst, K, V));
   } else {
     table_fwd_t_kernel<MODE><<<grid, dim3(32, 8), 0, st>>>(src, dst, K, V);
   }
@@ -258,7 +262,7 @@ static int launch_table_bwd_t(const float* src, const float* T, const float* dT,
     if (attr.first())
       CKB_CUDA_CHECK(cudaFuncSetAttribute(table_bwd_t_smem_kernel<MODE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    table_bwd_t_smem_kernel<MODE><<<grid, 256, smem, st>>>(src, T, dT, dsrc, K, V);
+    CKB_CUDA_CHECK(launch_pdl(table_bwd_t_smem_kernel<MODE>, grid, dim3(256), smem, st, src, T, dT, dsrc, K, V));
   } else {
     table_bwd_t_kernel<MODE><<<grid, dim3(32, 8), 0, st>>>(src, T, dT, dsrc, K, V);
   }
@@ -337,6 +341,8 @@ struct MultiSoftmax {
 constexpr int kMsRows = 4;
 template <bool BWD>
 __global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t total = m.row_end[m.n - 1];
   const int64_t stride = (int64_t)gridDim.x * nwarps * kMsRows;
@@ -502,9 +508,8 @@ int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
   auto flush = [&]() -> int {
     if (m.n == 0) return CKB_OK;
     const int blocks = (int)max64(1, min64(ceil_div(rows, 8 * kMsRows), 8 * kNumSMs));
-    if (bwd) multi_softmax_kernel<true><<<blocks, 256, 0, c.stream>>>(m);
-    else multi_softmax_kernel<false><<<blocks, 256, 0, c.stream>>>(m);
-    CKB_LAUNCH_CHECK();
+    if (bwd) CKB_CUDA_CHECK(launch_pdl(multi_softmax_kernel<true>, dim3(blocks), dim3(256), 0, c.stream, m));
+    else CKB_CUDA_CHECK(launch_pdl(multi_softmax_kernel<false>, dim3(blocks), dim3(256), 0, c.stream, m));
     c.launches++;
     m.n = 0;
     rows = 0;
