@@ -150,12 +150,7 @@ def make_config(args, world, plan):
     return {
         "workload": WORKLOADS[args.workload], "batch_per_gpu": B, "global_batch": world * B,
         "x_dtype": "int64", "parallelism": f"dp{world} (batch-sharded replicas)",
-        "collectives": "all_gather(root ll)" + (
-            "" if args.no_grad_allreduce or world == 1 else
-            " + all_reduce(param grads, sum)" + (
-                " after the backward pass" if args.grad_chunks <= 0 else
-                f", overlapped: issued per stage of the backward pass (inner layers, input layers, then the "
-                f"parameter ops of the input table in {args.grad_chunks} fold ranges)")),
+        "collectives": "all_gather(root ll)" + ("" if args.no_grad_allreduce or world == 1 else " + all_reduce(param grads, sum)"),
         "l2": f"no flush: per-step working set {plan.algorithmic_bytes(B) / 5 / 1e9:.2f} GB of activations >> 126 MB L2; 4 rotating input batches",
         "leaves": "seeded N(0,1), seed 1234",
         **({"tc_flags": args.tc_flags} if args.tc_flags is not None else {}),
@@ -364,8 +359,19 @@ def run_b200(args):
     from cirkit_b200.distributed import BatchShardedCircuit, all_gather_rows_async
 
     sharded = BatchShardedCircuit(cc)  # this rank's replica: rows [rank*B, (rank+1)*B) of the job
-    if world > 1 and not args.no_grad_allreduce and args.grad_chunks > 0 and z_runtime is None:
-        sharded.overlap_gradient_sync(args.grad_chunks, chunk_steps=args.chunk_steps)
+    allreduce = "none" if (world == 1 or args.no_grad_allreduce) else "nccl"
+    if allreduce != "none" and z_runtime is None:
+        # auto: the in-switch kernel from 4 GPUs on (8 GPUs: 155 us for the 77 MB against NCCL's 312); on 2 GPUs
+        # each rank owns half of the buffer and NCCL's staged all-reduces behind the backward pass are faster
+        want_nvls = args.allreduce == "nvls" or (args.allreduce == "auto" and world >= 4)
+        if want_nvls and sharded.nvls_gradient_sync(num_ctas=args.nvls_ctas, fused=not args.nvls_unfused):
+            allreduce = "nvls"
+        elif args.allreduce == "nvls":
+            raise SystemExit("bench: --allreduce nvls needs NVLink multicast support")
+        elif args.grad_chunks > 0:
+            sharded.overlap_gradient_sync(args.grad_chunks, chunk_steps=args.chunk_steps)
+            allreduce = "nccl-staged"
+    args.allreduce_used = allreduce
     if args.stage_only:  # developer A/B: the staged backward pass without any collective
         from cirkit_b200.distributed import OverlappedGradientReducer
 
@@ -534,6 +540,9 @@ def run_b200(args):
                 "pipeline": "H2D of step i+1 on a copy stream overlaps step i (2 staging buffers)"},
         "gpu_launches": launches * args.steps,
         "host_issue_ms_per_step": host_issue_ms,  # CPU time to enqueue one step (must stay below ms_per_step)
+        # how the gradient sum ran: "nvls" = in-switch multimem kernel (csrc/nvls_allreduce.cu) at the end of
+        # backward(), "nccl-staged" = NCCL all-reduces issued per stage of the backward pass, "nccl", "none"
+        "allreduce": args.allreduce_used,
         "roofline": roofline,
     }
     if base is not None:
@@ -570,6 +579,11 @@ def main():
                     help="batch of the CPU arm (default: the per-GPU batch, i.e. the same config; "
                          "256 for the Tucker workload and 32 for pd32_cp_k128, whose full batch takes minutes per step)")
     ap.add_argument("--no-grad-allreduce", action="store_true")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="N > 1: how the replicas' gradients are summed (auto: the in-switch NVLS kernel when the "
+                         "GPUs support NVLink multicast, else NCCL)")
+    ap.add_argument("--nvls-ctas", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--nvls-unfused", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--grad-chunks", type=int, default=1,
                     help="N > 1: fold chunks of the input table in the staged backward pass whose "
                          "gradient all-reduces overlap the remaining backward work (0: one all-reduce after backward)")

@@ -40,6 +40,8 @@ EXPORTS = (
     "ckb_plan_last_launches",
     "ckb_sample_cdf_rows",
     "ckb_plan_sample",
+    "ckb_nvls_allreduce",
+    "ckb_nvls_allreduce_fused",
     "ckb_set_option",
     "ckb_debug_read",
     # experimental complex-semiring building blocks (not used by the plan executor)
@@ -155,6 +157,10 @@ def load():
     lib.ckb_sample_cdf_rows.restype = C.c_int
     lib.ckb_plan_sample.argtypes = [C.POINTER(SampleStep), i32, i64, i64, C.c_uint64, i64, i32, i32, vp, vp, vp, i32, i32, vp]
     lib.ckb_plan_sample.restype = C.c_int
+    lib.ckb_nvls_allreduce.argtypes = [vp, i64, i32, i32, i32, vp]
+    lib.ckb_nvls_allreduce.restype = C.c_int
+    lib.ckb_nvls_allreduce_fused.argtypes = [vp, vp, vp, i64, i32, i32, vp, C.c_uint32, vp, i32, vp]
+    lib.ckb_nvls_allreduce_fused.restype = C.c_int
     lib.ckb_set_option.argtypes = [i32, i32]
     lib.ckb_set_option.restype = C.c_int
     lib.ckb_debug_read.argtypes = [vp, C.c_size_t]

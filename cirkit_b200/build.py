@@ -10,7 +10,7 @@ REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcirkit_b200.so")
-SOURCES = ["plan.cu", "input_kernels.cu", "inner_kernels.cu", "dense_kernels.cu", "dense32_kernels.cu", "dense_tc.cu", "dense_tc_bwd3.cu", "tucker_tc.cu", "tucker_root.cu", "param_kernels.cu", "complex_kernels.cu", "complex_plan.cu", "dense128_tc.cu", "sampling_kernels.cu"]
+SOURCES = ["plan.cu", "input_kernels.cu", "inner_kernels.cu", "dense_kernels.cu", "dense32_kernels.cu", "dense_tc.cu", "dense_tc_bwd3.cu", "tucker_tc.cu", "tucker_root.cu", "param_kernels.cu", "complex_kernels.cu", "complex_plan.cu", "dense128_tc.cu", "sampling_kernels.cu", "nvls_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

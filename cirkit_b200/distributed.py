@@ -170,7 +170,7 @@ class OverlappedGradientReducer:
                 self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
                 self._pieces.append(t)
 
-    def finish(self) -> int:
+    def finish(self, target: Tensor | None = None, flat: Tensor | None = None) -> int:
         world, _ = _world(self.group)
         for w in self._works:
             w.wait()
@@ -180,6 +180,89 @@ class OverlappedGradientReducer:
         self._works.clear()
         self._pieces.clear()
         n, self.bytes = self.bytes, 0
+        return n
+
+
+class NvlsGradientReducer:
+    """Sums the replicas' gradients in the NVSwitch (`csrc/nvls_allreduce.cu`) instead of calling
+    NCCL.  The CUDA runtime writes its flat gradient buffer straight into a symmetric-memory
+    buffer this object owns (`alloc`, allocated once and exchanged between the ranks through
+    `torch.distributed._symmetric_memory`: plumbing); at the end of the backward pass `finish`
+    orders the ranks with a barrier on the stream, launches the in-place two-shot kernel (rank r
+    reduces its 1/N share with `multimem.ld_reduce` and broadcasts it with `multimem.st`), a second
+    barrier, and copies the result into the tensors autograd hands out -- those must not alias a
+    buffer that the next backward pass overwrites.  Every replica ends up with the same bits."""
+
+    def __init__(self, group=None, average: bool = False, num_ctas: int = 0, fused: bool = True) -> None:
+        self.group = group
+        self.average = average
+        self.num_ctas = num_ctas
+        self.fused = fused  # barriers and copy-out inside the reduction kernel (ckb_nvls_allreduce_fused)
+        self._epoch = 0
+        self._counter: Tensor | None = None
+        self._buf: Tensor | None = None
+        self._hdl = None
+        self.bytes = 0
+
+    @staticmethod
+    def available(device: torch.device) -> bool:
+        try:
+            from torch._C._distributed_c10d import _SymmetricMemory
+
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            return bool(_SymmetricMemory.has_multicast_support(torch._C._autograd.DeviceType.CUDA, idx))
+        except Exception:  # pragma: no cover - depends on the build
+            return False
+
+    def alloc(self, numel: int, device: torch.device) -> Tensor | None:
+        world, _ = _world(self.group)
+        if world == 1:
+            return None
+        n4 = -(-numel // 4) * 4
+        if self._buf is None or self._buf.numel() < n4 or self._buf.device != device:
+            import torch.distributed._symmetric_memory as symm
+
+            buf = symm.empty(n4, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("NvlsGradientReducer: this group has no NVLink multicast (NVLS) support")
+            if self.fused and (symm.get_signal_pad_size() < 1536 or hdl.world_size > 64):
+                self.fused = False  # the fused kernel keeps its flags at words 256..383 of the signal pads
+            self._buf, self._hdl = buf, hdl
+            self._counter = torch.zeros(4, dtype=torch.int32, device=device)
+            self._epoch = 0
+            hdl.barrier(channel=0)  # (also: nobody's first fused call can run ahead of a peer's rendezvous)
+        return self._buf[:numel]
+
+    def __call__(self, pieces: Iterable[Tensor]) -> None:
+        self.bytes += sum(t.numel() * t.element_size() for t in pieces)
+
+    def finish(self, target: Tensor | None = None, flat: Tensor | None = None) -> int:
+        n, self.bytes = self.bytes, 0
+        if target is None or flat is None:
+            return n  # world 1: nothing to exchange
+        from . import _lib as L
+
+        hdl, buf = self._hdl, self._buf
+        world, rank = hdl.world_size, hdl.rank
+        stream = torch.cuda.current_stream(buf.device).cuda_stream
+        n4 = -(-target.numel() // 4) * 4
+        mc = hdl.multicast_ptr + (buf.data_ptr() - hdl.buffer_ptrs[rank])
+        lib = L.load()
+        if self.fused and not self.average and flat.numel() == n4:
+            # one kernel: wait for the peers, reduce + broadcast, wait again, copy out
+            self._epoch += 1
+            L.check(lib.ckb_nvls_allreduce_fused(mc, buf.data_ptr(), flat.data_ptr(), n4, rank, world,
+                                                 hdl.signal_pad_ptrs_dev, self._epoch, self._counter.data_ptr(),
+                                                 self.num_ctas, stream), "ckb_nvls_allreduce_fused")
+            return n
+        hdl.barrier(channel=0)  # every replica's backward pass has written its gradients
+        L.check(lib.ckb_nvls_allreduce(mc, n4, rank, world, self.num_ctas, stream), "ckb_nvls_allreduce")
+        hdl.barrier(channel=1)  # every share has been broadcast
+        if self.average:
+            torch.mul(target, 1.0 / world, out=flat)
+        else:
+            flat.copy_(target)
         return n
 
 
@@ -227,6 +310,19 @@ class BatchShardedCircuit(nn.Module):
 
     def loss(self, x_local: Tensor, num_rows: int) -> Tensor:
         return -self.circuit(x_local).sum() / num_rows
+
+    def nvls_gradient_sync(self, *, average: bool = False, num_ctas: int = 0, fused: bool = True) -> bool:
+        """Sum the parameter gradients in the NVSwitch at the end of the backward pass (see
+        `NvlsGradientReducer`).  Returns False -- and changes nothing -- without a CUDA runtime,
+        without NVLink multicast support, or for plans with per-sample PyTorch inputs."""
+        rt = _runtime_of(self.circuit)
+        if rt is None or not hasattr(rt, "grad_sync") or rt.needs_batch or rt.is_complex:
+            return False
+        dev = next(self.circuit.parameters()).device
+        if dev.type != "cuda" or not NvlsGradientReducer.available(dev):
+            return False
+        rt.grad_sync = NvlsGradientReducer(self.group, average, num_ctas, fused)
+        return True
 
     def overlap_gradient_sync(self, chunks: int = 4, *, average: bool = False,
                               bucket_bytes: int = 8 << 20, chunk_steps: bool = False) -> bool:

@@ -540,6 +540,7 @@ class PlanRuntime:
         self.keep_arena = False
         self.last_arena: Tensor | None = None
         self.last_flat_grad: Tensor | None = None  # flat buffer behind the last backward's gradients
+        self.last_flat_target: Tensor | None = None  # where the kernels wrote them (the same, or the hook's buffer)
         # staged backward (data-parallel overlap, see enable_gradient_stages)
         self.aliases: dict[int, tuple] = {}  # slot -> (base slot, float offset) into the same buffer
         self.sync_ops: dict[str, list] = {}
@@ -1018,7 +1019,16 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
     nfl = [p.numel() * (2 if p.is_complex() else 1) for p in P]  # floats per tensor
     sizes = [(-(-n // 4) * 4) if nd else 0 for n, nd in zip(nfl, need)]
     flat = torch.empty(sum(sizes), dtype=torch.float32, device=st.device) if sum(sizes) else None
-    rt.last_flat_grad = flat
+    # A gradient-sync hook may own the memory the kernels write into (a symmetric-memory buffer for
+    # the in-switch all-reduce): the tensors handed to autograd stay views of the fresh `flat`,
+    # which the hook fills with the reduced values at the end of the backward pass.
+    target = flat
+    alloc = getattr(rt.grad_sync, "alloc", None)
+    if alloc is not None and flat is not None and not rt.needs_batch:
+        owned = alloc(flat.numel(), st.device)
+        if owned is not None:
+            target = owned
+    rt.last_flat_grad, rt.last_flat_target = flat, target
     rt.last_flat_offsets = offs = []  # float offset of every binding's gradient in `flat` (-1: none)
     off = 0
     for b, p, nd, sz, n in zip(rt.bindings, P, need, sizes, nfl):
@@ -1028,9 +1038,9 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
             continue
         g = flat[off : off + n]
         g = torch.view_as_complex(g.view(*p.shape, 2)) if p.is_complex() else g.view(p.shape)
-        off += sz
         outs.append(g)
-        grads[b.src_slot] = g.data_ptr()
+        grads[b.src_slot] = target.data_ptr() + 4 * off
+        off += sz
         if b.native is not None:
             grads[b.dst_slot] = st.grad_buffer(b.dst_slot).data_ptr()
     if call.which == "masked":
@@ -1154,6 +1164,7 @@ class _PlanFn(torch.autograd.Function):
                 # `sync` on the communication stream) overlaps the stages that follow
                 h = st.handle(call.which + "_sync")
                 flat, offs, n = rt.last_flat_grad, rt.last_flat_offsets, 0
+                flat = rt.last_flat_target
                 for stage in rt.grad_stages[call.which]:
                     if stage.steps[1] > stage.steps[0]:
                         L.check(
@@ -1179,11 +1190,14 @@ class _PlanFn(torch.autograd.Function):
                 )
                 rt.last_launches = int(lib.ckb_plan_last_launches(st.handle(call.which)))
                 if sync is not None and not rt.needs_batch:
-                    sync([rt.last_flat_grad])
+                    sync([rt.last_flat_target])
             if sync is not None and not rt.needs_batch:
                 # the reduced gradients are consumed on this stream (autograd accumulates them
                 # into .grad right after this function returns)
-                rt.last_synced_bytes = sync.finish()
+                if rt.last_flat_target is not rt.last_flat_grad:
+                    rt.last_synced_bytes = sync.finish(rt.last_flat_target, rt.last_flat_grad)
+                else:
+                    rt.last_synced_bytes = sync.finish()
         ctx.arena = None
         return (None, None, None, None, None, *outs)
 

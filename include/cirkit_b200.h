@@ -243,6 +243,26 @@ int ckb_plan_sample(const ckb_sample_step_t* steps, int32_t n_steps, int64_t num
                     int32_t root_unit, int32_t* sel, int32_t* mix, void* x, int32_t num_vars,
                     int32_t x_is_float, void* stream);
 
+/* Data-parallel gradient sum over NVLink / NVSwitch multicast (the reference has no
+ * multi-device path, this is what a user would otherwise get from DistributedDataParallel's
+ * all-reduce).  multicast_ptr: the multicast (NVLS) address of a buffer of num_floats floats
+ * that every rank has mapped at the same offset of one multicast object; in place, two-shot: rank
+ * r sums its 1/world share in the switch (multimem.ld_reduce) and broadcasts it (multimem.st).
+ * The caller orders it with a cross-GPU barrier on the stream before and after.  num_ctas <= 0:
+ * one CTA per SM. */
+int ckb_nvls_allreduce(void* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world,
+                           int32_t num_ctas, void* stream);
+
+/* The same sum as ONE kernel, cross-GPU ordering included: waits until every rank has reached
+ * the call (flags in the ranks' signal pads: signal_pads_dev is a device array of `world`
+ * pointers to peer-mapped uint32 pads of at least 2 KB, zero before the first call), reduces and
+ * broadcasts this rank's share, waits until every share has been broadcast and copies the
+ * complete buffer (local_ptr: this rank's mapping of it) into out.  epoch: 1, 2, 3, ... per call,
+ * the same on every rank; counter: a zero-initialised device uint32.  All ranks must call it. */
+int ckb_nvls_allreduce_fused(void* multicast_ptr, const float* local_ptr, float* out,
+                             int64_t num_floats, int32_t rank, int32_t world, void* signal_pads_dev,
+                             uint32_t epoch, void* counter, int32_t num_ctas, void* stream);
+
 /* Number of kernels the last forward/backward call on this plan enqueued (bench bookkeeping). */
 int64_t ckb_plan_last_launches(const ckb_plan_t* plan);
 

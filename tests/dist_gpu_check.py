@@ -35,10 +35,16 @@ def overlap_check(dev, rank: int, world: int) -> None:
         x = torch.randint(0, 256, (world * rows, plan.num_variables),
                           generator=torch.Generator().manual_seed(9))
         grads = []
-        for overlap in (False, True):
+        for overlap in (False, True, "nvls"):
             cc = B200Circuit(plan, seed=21).to(dev)
             sharded = BatchShardedCircuit(cc)
-            if overlap:
+            if overlap == "nvls":
+                # in-switch sum over NVLink multicast (csrc/nvls_allreduce.cu) instead of NCCL
+                if not sharded.nvls_gradient_sync():
+                    if rank == 0:
+                        print(f"dist nvls SKIPPED {name}: no NVLink multicast support", flush=True)
+                    continue
+            elif overlap:
                 assert sharded.overlap_gradient_sync(4, bucket_bytes=1 << 16)
             for _ in range(2):  # the second pass re-uses buffers the first one's collectives read
                 for p in cc.leaves:
@@ -47,14 +53,16 @@ def overlap_check(dev, rank: int, world: int) -> None:
                 nbytes = sharded.sync_gradients()
             assert nbytes >= sum(4 * p.numel() for p in cc.leaves)
             grads.append([p.grad.clone() for p in cc.leaves])
-        for i, (a, b) in enumerate(zip(*grads)):
+        for other in grads[1:]:
+          for i, (a, b) in enumerate(zip(grads[0], other)):
             # equal up to summation order: a fold chunk sums its split-K slabs in a different
             # grouping, host-side (PyTorch) parameter ops scatter-add pointer slices with atomics,
             # and beyond two ranks the collective's own order depends on the message size
             err, tol = float((a - b).abs().max()), 1e-5 * float(a.abs().max()) + 1e-12
-            assert err <= tol, f"{name} leaf {i}: overlapped != serial ({err:.3e} > {tol:.3e})"
+            assert err <= tol, f"{name} leaf {i}: overlapped / nvls != serial ({err:.3e} > {tol:.3e})"
         if rank == 0:
-            print(f"dist overlap ok {name} K={units}: world {world}, {nbytes} bytes reduced in stages", flush=True)
+            print(f"dist overlap ok {name} K={units}: world {world}, {nbytes} bytes reduced in stages; "
+                  f"{len(grads)} reduction modes agree", flush=True)
 
 
 def main() -> None:
