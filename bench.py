@@ -361,9 +361,10 @@ def run_b200(args):
     sharded = BatchShardedCircuit(cc)  # this rank's replica: rows [rank*B, (rank+1)*B) of the job
     allreduce = "none" if (world == 1 or args.no_grad_allreduce) else "nccl"
     if allreduce != "none" and z_runtime is None:
-        # auto: the in-switch kernel from 4 GPUs on (8 GPUs: 155 us for the 77 MB against NCCL's 312); on 2 GPUs
-        # each rank owns half of the buffer and NCCL's staged all-reduces behind the backward pass are faster
-        want_nvls = args.allreduce == "nvls" or (args.allreduce == "auto" and world >= 4)
+        # auto: the in-switch kernel on 8 GPUs (155 us for the 77 MB against NCCL's 312: 1.477 vs 1.511 ms per
+        # step); on 2 and 4 GPUs a rank owns a half / a quarter of the buffer and NCCL's staged all-reduces
+        # behind the backward pass are faster (N = 4: 1.425 vs 1.473 ms)
+        want_nvls = args.allreduce == "nvls" or (args.allreduce == "auto" and world >= 8)
         if want_nvls and sharded.nvls_gradient_sync(num_ctas=args.nvls_ctas, fused=not args.nvls_unfused):
             allreduce = "nvls"
         elif args.allreduce == "nvls":
