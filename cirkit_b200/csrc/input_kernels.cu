@@ -421,6 +421,39 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
     float acc[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    if (NT == 2 && K == 64 && n_cons >= 0) {
+      // K = 64 (the CTA covers the whole row): a lane owns columns 2*lane, 2*lane + 1 -- one 8-byte
+      // load per row and lane, 32-bit offsets inside the fold's block, whole groups of 4 rows
+      // without predicates.  Every column is still summed in bucket (= sample) order: same bits
+      // as the generic path below, at a seventh of its instructions (it was issue-bound).
+      float2 a2 = make_float2(0.f, 0.f);
+      for (int c = 0; c < n_cons; ++c) {
+        const float2* g0 = reinterpret_cast<const float2*>(grows[c] + b_begin * 64) + lane;
+        int j = s0;
+        for (; j + 4 <= s1; j += 4) {
+          float2 g[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u] = __ldg(g0 + (int)list[j + u] * 32);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a2.x += g[u].x;
+            a2.y += g[u].y;
+          }
+        }
+        float2 g[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          g[u] = j + u < s1 ? __ldg(g0 + (int)list[j + u] * 32) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (j + u < s1) {
+            a2.x += g[u].x;
+            a2.y += g[u].y;
+          }
+      }
+      reinterpret_cast<float2*>(o + (int64_t)v * 64)[lane] = a2;
+      continue;
+    }
     if (n_cons >= 0) {
       for (int c = 0; c < n_cons; ++c) {
         const float* g0 = grows[c] + k0 + lane;
@@ -776,8 +809,30 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
     out[i] = s;
   }
 }
-
+// Few outputs, many slabs (the Ko = 1 root layer: 64 weights, 256 slabs): a warp per output, lanes
+// over the slabs (each lane sums its slabs in order, then the shuffle tree: a fixed order), so the
+// sum is ~8 dependent loads deep instead of 256.
+__global__ void reduce_partials_wide_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                            int64_t n, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += n_warps) {
+    float s = 0.f;
+    for (int j = lane; j < splits; j += 32) s += __ldg(partial + (int64_t)j * n + i);
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
+  }
+}
 int reduce_partials(const float* partial, float* out, int64_t n, int splits, Ctx& c) {
+  if (splits >= 64 && n <= 16384) {
+    const int bw = (int)min64(ceil_div(n, 8), 8 * kNumSMs);
+    CKB_CUDA_CHECK(launch_pdl(reduce_partials_wide_kernel, dim3(max(bw, 1)), dim3(256), 0, c.stream, partial, out, n, splits));
+    c.launches++;
+    return CKB_OK;
+  }
   const int bx = (int)min64(ceil_div(n, 256), 8 * kNumSMs);
   CKB_CUDA_CHECK(launch_pdl(reduce_partials_kernel, dim3(max(bx, 1)), dim3(256), 0, c.stream, partial, out, n, splits));
   CKB_LAUNCH_CHECK();
