@@ -328,6 +328,7 @@ __global__ void lse_rows_bwd_kernel(const float* __restrict__ src, const float* 
 constexpr int kMultiOps = 24;
 struct MultiSoftmax {
   int n;
+  int all64;  // every op of the batch has 64 columns and 16-byte aligned tensors
   int cols[kMultiOps];
   int64_t row_end[kMultiOps];  // cumulative row counts
   const float* a[kMultiOps];   // fwd: src      bwd: W
@@ -345,6 +346,54 @@ __global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t total = m.row_end[m.n - 1];
+  if (m.all64) {
+    // every row has 64 columns (K = 64 circuits): a half-warp per row, one 16-byte load per lane,
+    // 8 rows per warp in flight, 4-step shuffle reductions inside the half-warps
+    const int half = lane >> 4, l16 = lane & 15;
+    const int64_t stride8 = (int64_t)gridDim.x * nwarps * 8;
+    for (int64_t g0 = ((int64_t)blockIdx.x * nwarps + warp) * 8; g0 < total; g0 += stride8) {
+      float4 x[4], y[4];
+      float4* dst[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t gr = g0 + 2 * q + half;
+        dst[q] = nullptr;
+        x[q] = BWD ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        y[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < total) {
+          int op = 0;
+          while (gr >= m.row_end[op]) ++op;
+          const int64_t at = (gr - (op ? m.row_end[op - 1] : 0)) * 64 + 4 * l16;
+          x[q] = __ldg(reinterpret_cast<const float4*>(m.a[op] + at));
+          if (BWD) y[q] = __ldg(reinterpret_cast<const float4*>(m.b[op] + at));
+          dst[q] = reinterpret_cast<float4*>(m.out[op] + at);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 r;
+        if (!BWD) {
+          float mx = fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          r = make_float4(expf(x[q].x - mx), expf(x[q].y - mx), expf(x[q].z - mx), expf(x[q].w - mx));
+          float z = (r.x + r.y) + (r.z + r.w);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+          const float inv = 1.f / z;
+          r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+        } else {
+          float dot = fmaf(x[q].x, y[q].x, fmaf(x[q].y, y[q].y, fmaf(x[q].z, y[q].z, x[q].w * y[q].w)));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          r = make_float4(x[q].x * (y[q].x - dot), x[q].y * (y[q].y - dot), x[q].z * (y[q].z - dot),
+                          x[q].w * (y[q].w - dot));
+        }
+        if (dst[q] != nullptr) *dst[q] = r;
+      }
+    }
+    return;
+  }
   const int64_t stride = (int64_t)gridDim.x * nwarps * kMsRows;
   for (int64_t g0 = ((int64_t)blockIdx.x * nwarps + warp) * kMsRows; g0 < total; g0 += stride) {
     const float* a[kMsRows];
@@ -507,6 +556,11 @@ int multi_softmax(const ckb_param_op_t* ops, int n_ops, bool bwd, Ctx& c) {
   int64_t rows = 0;
   auto flush = [&]() -> int {
     if (m.n == 0) return CKB_OK;
+    m.all64 = 1;
+    for (int i = 0; i < m.n; ++i)
+      if (m.cols[i] != 64 || ((uintptr_t)m.a[i] & 15) || ((uintptr_t)m.out[i] & 15) ||
+          (bwd && ((uintptr_t)m.b[i] & 15)))
+        m.all64 = 0;
     const int blocks = (int)max64(1, min64(ceil_div(rows, 8 * kMsRows), 8 * kNumSMs));
     if (bwd) CKB_CUDA_CHECK(launch_pdl(multi_softmax_kernel<true>, dim3(blocks), dim3(256), 0, c.stream, m));
     else CKB_CUDA_CHECK(launch_pdl(multi_softmax_kernel<false>, dim3(blocks), dim3(256), 0, c.stream, m));
