@@ -108,10 +108,20 @@ class B200Circuit(nn.Module):
     def forward(self, x: Tensor | None = None) -> Tensor:
         if self.plan.scope and x is None:
             raise ValueError(f"Expected some input 'x', as the circuit has scope '{self.plan.scope}'")
-        y = self.runtime.evaluate(x, list(self.leaves))  # (B, O, K)
+        y = self.runtime.evaluate(x, self._leaf_list())  # (B, O, K)
         if not self.plan.scope:
             y = y.squeeze(dim=0)
         return y
+
+    def _leaf_list(self) -> list:
+        # (iterating an nn.ParameterList costs ~3 us per entry: the list is rebuilt only when the
+        # module's parameters were re-assigned)
+        cached = self.__dict__.get("_leaves_cache")
+        if cached is None or len(cached) != len(self.leaves) or any(
+                a is not b for a, b in zip(cached, self.leaves._parameters.values())):
+            cached = list(self.leaves)
+            self.__dict__["_leaves_cache"] = cached
+        return cached
 
     def integrate_query(self, x: Tensor, mask: Tensor) -> Tensor:
         return self.runtime.evaluate(x, list(self.leaves), integrate_mask=mask)

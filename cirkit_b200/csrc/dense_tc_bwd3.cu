@@ -519,17 +519,40 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows][64] fp32 matrix at `base`, boxes of box_rows x 32 columns, 32-byte-atom 128-byte swizzle
+// [rows][64] fp32 matrix at `base`, boxes of box_rows x 32 columns, 32-byte-atom 128-byte swizzle.
+// A descriptor depends on (base, box_rows) only and the arenas come back at the same addresses step
+// after step (caching allocator): the last 64 encodings are kept per host thread -- the driver
+// call costs ~1.5 us and a step needs 40 of them.
 bool make_map(CUtensorMap* tm, const void* base, int box_rows) {
+  struct Entry {
+    const void* base;
+    int box_rows;
+    CUtensorMap map;
+  };
+  static thread_local Entry cache[64];
+  static thread_local int used = 0, next = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].base == base && cache[i].box_rows == box_rows) {
+      *tm = cache[i].map;
+      return true;
+    }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {64, (cuuint64_t)1 << 31};
   const cuuint64_t strides[1] = {256};
   const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  Entry& e = cache[next];
+  e.base = base;
+  e.box_rows = box_rows;
+  e.map = *tm;
+  next = (next + 1) % 64;
+  if (used < 64) ++used;
+  return true;
 }
 
 }  // namespace

@@ -309,6 +309,8 @@ class _DeviceState:
         # buffers in `eff` (and the logsumexp buffers of the masked plan) were last computed from
         self.param_key: tuple | None = None
         self.lse_key: tuple | None = None
+        self.tensor_table: tuple | None = None  # (parameter pointers, n_slots, ctypes table): see _prepare_call
+        self.grad_layouts: dict = {}  # cached gradient-table layouts: see _grad_table
         # SamplingQuery: CDF buffers per step (valid for sample_key) and the selection-arena tables
         self.cdf: dict[int, Tensor] = {}
         self.sample_key: tuple | None = None
@@ -997,21 +999,73 @@ def _prepare_call(rt: PlanRuntime, st: _DeviceState, x, mask, P, stream) -> _Cal
             "ckb_transpose_mask",
         )
     which = rt.choose_plan(B, mask is not None)
-    tensors = (C.c_void_p * rt.n_slots)()
-    for b, p in zip(rt.bindings, P):
-        tensors[b.src_slot] = p.data_ptr()  # complex64 storage = interleaved (re, im) floats
-    for slot, buf in st.eff.items():
-        tensors[slot] = buf.data_ptr()
-    for sid, slot in rt.int_slots.items():
-        if sid in st.int_buf:
-            tensors[slot] = st.int_buf[sid].data_ptr()
-    for slot, (base, off) in rt.aliases.items():
-        if tensors[base]:
-            tensors[slot] = tensors[base] + 4 * off
+    # the tensor table only changes when a parameter tensor moves (the effective-parameter and
+    # integrate buffers are persistent): rebuilt then, reused otherwise
+    ptrs = tuple(p.data_ptr() for p in P)
+    cached = st.tensor_table
+    if cached is not None and cached[0] == ptrs and cached[1] == rt.n_slots:
+        tensors = cached[2]
+    else:
+        tensors = (C.c_void_p * rt.n_slots)()
+        for b, ptr in zip(rt.bindings, ptrs):
+            tensors[b.src_slot] = ptr  # complex64 storage = interleaved (re, im) floats
+        for slot, buf in st.eff.items():
+            tensors[slot] = buf.data_ptr()
+        for sid, slot in rt.int_slots.items():
+            if sid in st.int_buf:
+                tensors[slot] = st.int_buf[sid].data_ptr()
+        for slot, (base, off) in rt.aliases.items():
+            if tensors[base]:
+                tensors[slot] = tensors[base] + 4 * off
+        st.tensor_table = (ptrs, rt.n_slots, tensors)
     return _Call(which, B, xT, x_is_float, maskT, mask_rows, tensors, len(rt.exec_plans[which]))
 
 
 def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tuple[object, list]:
+    if not rt.is_complex:
+        return _grad_table_cached(rt, st, call, P, need)
+    return _grad_table_build(rt, st, call, P, need)[:2]
+
+
+def _grad_table_cached(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tuple[object, list]:
+    """`_grad_table_build` with everything that does not depend on the call cached per (plan,
+    wanted gradients, shapes): the table itself (its entries for runtime-owned buffers never change),
+    the offsets into the flat buffer and the slots that follow it.  Per call: one allocation, one
+    split, one view per tensor, a few integer stores."""
+    key = (call.which, tuple(need), tuple(tuple(p.shape) for p in P), rt.n_slots)
+    lay = st.grad_layouts.get(key)
+    if lay is None:
+        grads, outs, flat_slots = _grad_table_build(rt, st, call, P, need)
+        st.grad_layouts[key] = {
+            "grads": grads, "sizes": [o.numel() if o is not None else 0 for o in outs],
+            "offs": list(rt.last_flat_offsets), "total": 0 if rt.last_flat_grad is None else rt.last_flat_grad.numel(),
+            "flat_slots": flat_slots, "shapes": [tuple(p.shape) for p in P],
+        }
+        return grads, outs
+    total = lay["total"]
+    flat = torch.empty(total, dtype=torch.float32, device=st.device) if total else None
+    target = flat
+    alloc = getattr(rt.grad_sync, "alloc", None)
+    if alloc is not None and flat is not None and not rt.needs_batch:
+        owned = alloc(total, st.device)
+        if owned is not None:
+            target = owned
+    rt.last_flat_grad, rt.last_flat_target = flat, target
+    rt.last_flat_offsets = lay["offs"]
+    grads = lay["grads"]
+    outs: list[Tensor | None] = []
+    if flat is not None:
+        base = target.data_ptr()
+        for slot, off in lay["flat_slots"]:
+            grads[slot] = base + 4 * off
+        for off, n, shape in zip(lay["offs"], lay["sizes"], lay["shapes"]):
+            outs.append(None if off < 0 else flat.narrow(0, off, n).view(shape))
+    else:
+        outs = [None] * len(P)
+    return grads, outs
+
+
+def _grad_table_build(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tuple[object, list, list]:
     grads = (C.c_void_p * rt.n_slots)()
     outs: list[Tensor | None] = []
     # all requested parameter gradients are views of ONE flat buffer (16-byte aligned pieces), so
@@ -1059,7 +1113,11 @@ def _grad_table(rt: PlanRuntime, st: _DeviceState, call: _Call, P, need) -> tupl
     for slot, (base, off) in rt.aliases.items():
         if grads[base]:
             grads[slot] = grads[base] + 4 * off
-    return grads, outs
+    # the entries that point into the flat buffer (they move with every call): (slot, float offset)
+    flat_slots = [(b.src_slot, o) for b, o in zip(rt.bindings, offs) if o >= 0]
+    src_off = dict(flat_slots)
+    flat_slots += [(slot, src_off[base] + off) for slot, (base, off) in rt.aliases.items() if base in src_off]
+    return grads, outs, flat_slots
 
 
 def _stage_pieces(rt: "PlanRuntime", stage: GradStage, flat: Tensor, offs: list) -> list[Tensor]:
