@@ -539,6 +539,7 @@ class PlanRuntime:
         self._states: dict[torch.device, _DeviceState] = {}
         self.last_launches = 0
         self.cache_parameters = True  # skip the parameter ops of no_grad calls on unchanged parameters
+        self.check_evidence = False  # validate integer evidence against the number of states (costs a sync)
         self.keep_arena = False
         self.last_arena: Tensor | None = None
         self.last_flat_grad: Tensor | None = None  # flat buffer behind the last backward's gradients
@@ -924,6 +925,17 @@ class PlanRuntime:
                 f"the circuit reads variable {self.plan.num_variables - 1} but the input has "
                 f"{x.shape[1]} columns"
             )
+        if self.check_evidence and x is not None and not x.is_floating_point():
+            # The table kernels clamp a state to [0, V) instead of faulting; the reference's fancy
+            # index (layers/input.py:399-412) raises on such evidence.  Opt-in: the check costs a
+            # pass over x and a device synchronisation per call.
+            for sid, s in enumerate(self.plan.steps):
+                V = int(s.config.get("num_categories", s.config.get("num_states", 0)))
+                if s.kind in ("categorical", "embedding") and V > 0:
+                    cols = torch.as_tensor(s.scope_idx, dtype=torch.int64, device=x.device)
+                    xs = x.index_select(1, cols)
+                    if bool(((xs < 0) | (xs >= V)).any()):
+                        raise IndexError(f"evidence out of range for step {sid}: states must lie in [0, {V})")
         if integrate_mask is not None and self.is_complex:
             raise NotImplementedError("integration masks are not implemented for 'complex-lse-sum' plans")
         if integrate_mask is not None:

@@ -293,3 +293,24 @@ def test_effective_parameters_are_cached_between_no_grad_calls(dev):
     assert rt.last_launches == n0 and torch.equal(y3.detach(), y2)
     (-y3.mean()).backward()
     assert all(p.grad is not None for p in cc.leaves)
+
+
+def test_out_of_range_evidence_is_reported_on_request(dev):
+    """The kernels clamp a state to [0, V); with `check_evidence` the runtime raises like the
+    reference's indexing does (layers/input.py:399-412)."""
+    from cirkit_b200 import B200Circuit
+
+    g = Golden("qt8_cp_k4")
+    cc = B200Circuit(g.plan, seed=2).to(dev)
+    x = torch.randint(0, 256, (8, g.plan.num_variables))
+    x[3, 5] = 256
+    y = cc(x.to(dev))  # default: clamped, finite
+    assert torch.isfinite(y).all()
+    cc.runtime.check_evidence = True
+    with pytest.raises(IndexError, match="out of range"):
+        cc(x.to(dev))
+    x[3, 5] = -1
+    with pytest.raises(IndexError, match="out of range"):
+        cc(x.to(dev))
+    x[3, 5] = 255
+    assert torch.isfinite(cc(x.to(dev))).all()
