@@ -25,6 +25,7 @@ STEP_NO_GATHER = 32
 POP_SOFTMAX, POP_LOG_SOFTMAX_T, POP_LOG_T, POP_COPY_T, POP_SCALED_SIGMOID, POP_LOG, POP_LSE_ROWS, POP_CONJ = range(8)
 U8, I32, I64, F32, F64, I16 = range(6)
 RUN_PARAM_OPS = 1
+USE_GRAPHS = 2
 
 EXPORTS = (
     "ckb_version",

@@ -37,14 +37,37 @@ int complex_step_fwd(const ckb_step_desc_t& d, Ctx& c);
 int complex_step_bwd(const ckb_step_desc_t& d, Ctx& c);
 size_t complex_step_ws(const ckb_step_desc_t& d, int64_t B);
 int complex_conj(const float* src, float* dst, int64_t n, Ctx& c);
+int tc_flags();
+bool tc_disabled();
 
 }  // namespace ckb
 
+// A forward / backward call whose arguments (pointers, batch, range, flags, table contents) repeat
+// is the same sequence of ~20 launches every time: after it has been seen twice it is captured
+// into a CUDA graph on a private stream and replayed with one cudaGraphLaunch (CKB_USE_GRAPHS).
+// Training loops hit the cache because the caching allocator hands the arenas back at the same
+// addresses; anything else simply stays on the eager path.
+struct GraphEntry {
+  uint64_t key = 0;
+  int seen = 0;                     // eager runs with this key so far
+  bool failed = false;              // capture did not work once: stay eager
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  uint64_t last_use = 0;
+};
 struct ckb_plan {
   std::vector<ckb_step_desc_t> steps;
   std::vector<ckb_param_op_t> ops;
   int32_t n_slots = 0;
   int64_t last_launches = 0;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t capture_stream = nullptr;
+  uint64_t clock = 0;
+  ~ckb_plan() {
+    for (GraphEntry& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
 };
 
 using namespace ckb;
@@ -272,7 +295,7 @@ static int run_param_ops(ckb_plan_t* plan, int o0, int o1, bool bwd, Ctx& c) {
   return CKB_OK;
 }
 
-int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+static int plan_forward_eager(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
                      const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
                      float* const* tensors, float* arena, void* workspace, size_t workspace_bytes,
                      int32_t flags, void* stream) {
@@ -307,7 +330,7 @@ int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int
   return CKB_OK;
 }
 
-int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+static int plan_backward_eager(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
                       const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
                       float* const* tensors, float* const* grads, const float* arena,
                       float* garena, void* workspace, size_t workspace_bytes, int32_t flags,
@@ -346,6 +369,126 @@ int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, in
     if (int rc = run_param_ops(plan, 0, (int)plan->ops.size(), true, c)) return rc;
   plan->last_launches = c.launches;
   return CKB_OK;
+}
+
+
+}  // extern "C" (the helpers below are templates)
+
+namespace {
+inline uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
+}
+constexpr int kMaxGraphs = 16;
+
+// Runs `eager(stream)` through the plan's graph cache.  `key` identifies the call completely.
+template <typename Fn>
+int run_with_graphs(ckb_plan_t* plan, uint64_t key, cudaStream_t stream, Fn&& eager) {
+  GraphEntry* e = nullptr;
+  for (GraphEntry& g : plan->graphs)
+    if (g.key == key) e = &g;
+  if (e == nullptr) {
+    if ((int)plan->graphs.size() >= kMaxGraphs) {  // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < plan->graphs.size(); ++i)
+        if (plan->graphs[i].last_use < plan->graphs[lru].last_use) lru = i;
+      if (plan->graphs[lru].exec) cudaGraphExecDestroy(plan->graphs[lru].exec);
+      plan->graphs.erase(plan->graphs.begin() + lru);
+    }
+    plan->graphs.push_back(GraphEntry{});
+    e = &plan->graphs.back();
+    e->key = key;
+  }
+  e->last_use = ++plan->clock;
+  if (e->exec != nullptr) {
+    CKB_CUDA_CHECK(cudaGraphLaunch(e->exec, stream));
+    plan->last_launches = e->launches;
+    return CKB_OK;
+  }
+  if (e->failed || e->seen < 1) {  // first sight of this call (or capture is not possible): eager
+    e->seen++;
+    return eager(stream);
+  }
+  // second sight: capture on a private stream (the caller's may be the legacy default stream,
+  // which cannot be captured), instantiate, replay on the caller's stream
+  if (plan->capture_stream == nullptr)
+    CKB_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->capture_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(plan->capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    e->failed = true;
+    return eager(stream);
+  }
+  const int rc = eager(plan->capture_stream);
+  const cudaError_t ce = cudaStreamEndCapture(plan->capture_stream, &graph);
+  if (rc != CKB_OK || ce != cudaSuccess || graph == nullptr) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    e->failed = true;
+    return rc != CKB_OK ? rc : eager(stream);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || exec == nullptr) {
+    cudaGetLastError();
+    e->failed = true;
+    return eager(stream);
+  }
+  e->exec = exec;
+  e->launches = plan->last_launches;
+  CKB_CUDA_CHECK(cudaGraphLaunch(exec, stream));
+  return CKB_OK;
+}
+
+uint64_t table_hash(uint64_t h, float* const* table, int n) {
+  for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)table[i]);
+  return h;
+}
+}  // namespace
+
+extern "C" {
+
+int ckb_plan_forward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                     const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                     float* const* tensors, float* arena, void* workspace, size_t workspace_bytes,
+                     int32_t flags, void* stream) {
+  auto eager = [&](cudaStream_t st) {
+    return plan_forward_eager(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows, tensors,
+                              arena, workspace, workspace_bytes, flags, (void*)st);
+  };
+  if (!(flags & CKB_USE_GRAPHS) || plan == nullptr || tensors == nullptr) return eager((cudaStream_t)stream);
+  uint64_t key = 0xF0;
+  for (uint64_t v : {(uint64_t)step_begin, (uint64_t)step_end, (uint64_t)batch, (uint64_t)(uintptr_t)xT,
+                     (uint64_t)x_is_float, (uint64_t)(uintptr_t)maskT, (uint64_t)mask_rows,
+                     (uint64_t)(uintptr_t)arena, (uint64_t)(uintptr_t)workspace, (uint64_t)workspace_bytes,
+                     (uint64_t)flags, (uint64_t)tc_flags(), (uint64_t)pdl_enabled(), (uint64_t)tc_disabled()})
+    key = mix(key, v);
+  key = table_hash(key, tensors, plan->n_slots);
+  return run_with_graphs(plan, key, (cudaStream_t)stream, eager);
+}
+
+int ckb_plan_backward(ckb_plan_t* plan, int32_t step_begin, int32_t step_end, int64_t batch,
+                      const void* xT, int32_t x_is_float, const uint8_t* maskT, int64_t mask_rows,
+                      float* const* tensors, float* const* grads, const float* arena,
+                      float* garena, void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* stream) {
+  auto eager = [&](cudaStream_t st) {
+    return plan_backward_eager(plan, step_begin, step_end, batch, xT, x_is_float, maskT, mask_rows, tensors,
+                               grads, arena, garena, workspace, workspace_bytes, flags, (void*)st);
+  };
+  if (!(flags & CKB_USE_GRAPHS) || plan == nullptr || tensors == nullptr || grads == nullptr)
+    return eager((cudaStream_t)stream);
+  uint64_t key = 0xB0;
+  for (uint64_t v : {(uint64_t)step_begin, (uint64_t)step_end, (uint64_t)batch, (uint64_t)(uintptr_t)xT,
+                     (uint64_t)x_is_float, (uint64_t)(uintptr_t)maskT, (uint64_t)mask_rows,
+                     (uint64_t)(uintptr_t)arena, (uint64_t)(uintptr_t)garena, (uint64_t)(uintptr_t)workspace,
+                     (uint64_t)workspace_bytes, (uint64_t)flags, (uint64_t)tc_flags(), (uint64_t)pdl_enabled(),
+                     (uint64_t)tc_disabled()})
+    key = mix(key, v);
+  key = table_hash(key, tensors, plan->n_slots);
+  key = table_hash(key, grads, plan->n_slots);
+  return run_with_graphs(plan, key, (cudaStream_t)stream, eager);
 }
 
 int ckb_plan_param_ops(ckb_plan_t* plan, int32_t op_begin, int32_t op_end, int32_t backward,

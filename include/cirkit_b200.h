@@ -177,6 +177,11 @@ int ckb_transpose_mask(const uint8_t* mask, int64_t rows, int32_t num_vars, uint
                        void* stream);
 
 #define CKB_RUN_PARAM_OPS 1 /* forward: evaluate the parameter ops; backward: back-propagate them */
+#define CKB_USE_GRAPHS 2    /* a call whose arguments repeat exactly (pointers, batch, range, flags,
+                               table contents) is captured into a CUDA graph the second time it is
+                               seen and replayed from then on: one launch instead of ~20 (host time of
+                               small-batch loops).  Every external / per-call tensor must keep its
+                               address for the replay to be taken; otherwise the call runs eagerly. */
 
 /* One forward pass over steps [step_begin, step_end).  Replaces TorchDiAcyclicGraph.evaluate
  * (graph/modules.py:303-335) + LayerAddressBook.lookup (circuits.py:30-71) + every layer's
