@@ -194,6 +194,144 @@ __global__ void dense_fwd_generic(DenseArgs a, int e_stride) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Any shape, tiled (sum layers over concatenated inputs with Kred > 128: PoonDomingos at K = 128
+// has Kred up to 1792).  The warp-per-sample kernel above streams the whole weight matrix of a
+// fold (Ko * Kred * 4 bytes, ~1 MB) through L2 once PER SAMPLE; here a CTA owns a 64-sample x
+// 64-output tile and walks the reduction in steps of 32 through shared memory, so weights and
+// inputs are read once per tile (2.2 ms -> 0.2 ms for the F = 4, Kred = 1792 layer of config 4).
+//   pass 1  row shifts m[f,b] = max_i u[b,i]                       (dense_rowmax_generic)
+//   pass 2  y[b,o] = log sum_i W[o,i] exp(u[b,i] - m[b]) + m[b]     (dense_fwd_tiled_generic)
+// and for the backward, with r = g exp(m - y):
+//   du[b,i] = exp(u[b,i] - m[b]) * sum_o r[b,o] W[o,i]              (dense_du_tiled_generic)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gather_u(const DenseArgs& a, int f, int64_t b, int i) {
+  if (a.concat) {
+    const int h = i / a.Ki;
+    return in_row(a, f, h)[b * a.Ki + (i - h * a.Ki)];
+  }
+  float u = 0.f;
+  for (int h = 0; h < a.H; ++h) u += in_row(a, f, h)[b * a.Ki + i];
+  return u;
+}
+
+__global__ void dense_rowmax_generic(DenseArgs a, float* __restrict__ mrow) {
+  const int f = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int64_t b = (int64_t)blockIdx.x * nwarps + warp; b < a.B; b += (int64_t)gridDim.x * nwarps) {
+    float m = -INFINITY;
+    for (int i = lane; i < a.Kred; i += 32) m = fmaxf(m, gather_u(a, f, b, i));
+    m = clamp_max(warp_max(m));
+    if (lane == 0) mrow[(int64_t)f * a.B + b] = m;
+  }
+}
+
+constexpr int kGtB = 64, kGtN = 64, kGtK = 32, kGtLd = 68;  // tile sizes; padded row stride
+// thread (ty, tx) of 16 x 16 owns samples 4 ty .. 4 ty + 3 and columns 4 tx .. 4 tx + 3 of the tile
+__global__ void __launch_bounds__(256) dense_fwd_tiled_generic(DenseArgs a, const float* __restrict__ mrow) {
+  __shared__ __align__(16) float es[kGtK][kGtLd];  // [reduction index][sample]
+  __shared__ __align__(16) float ws[kGtK][kGtLd];  // [reduction index][output]
+  const int f = blockIdx.z;
+  const int64_t b0 = (int64_t)blockIdx.x * kGtB;
+  const int o0 = blockIdx.y * kGtN;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < a.Kred; k0 += kGtK) {
+    for (int q = tid; q < kGtB * kGtK; q += 256) {
+      const int bb = q / kGtK, k = q - bb * kGtK;  // consecutive threads: consecutive reduction indices
+      const int64_t b = b0 + bb;
+      float e = 0.f;
+      if (b < a.B && k0 + k < a.Kred) e = expf(gather_u(a, f, b, k0 + k) - mrow[(int64_t)f * a.B + b]);
+      es[k][bb] = e;
+    }
+    for (int q = tid; q < kGtN * kGtK; q += 256) {
+      const int oo = q / kGtK, k = q - oo * kGtK;
+      ws[k][oo] = (o0 + oo < a.Ko && k0 + k < a.Kred) ? __ldg(Wf + (int64_t)(o0 + oo) * a.Kred + k0 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kGtK; ++k) {
+      const float4 ev = *reinterpret_cast<const float4*>(&es[k][4 * ty]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[k][4 * tx]);
+      const float e4[4] = {ev.x, ev.y, ev.z, ev.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(e4[p], w4[q], acc[p][q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int64_t b = b0 + 4 * ty + p;
+    if (b >= a.B) continue;
+    const float m = mrow[(int64_t)f * a.B + b];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = o0 + 4 * tx + q;
+      if (o < a.Ko) a.y[((int64_t)f * a.B + b) * a.Ko + o] = logf(acc[p][q]) + m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_du_tiled_generic(DenseArgs a, const float* __restrict__ mrow) {
+  __shared__ __align__(16) float rs[kGtK][kGtLd];  // [output][sample]
+  __shared__ __align__(16) float ws[kGtK][kGtLd];  // [output][reduction index]
+  const int f = blockIdx.z;
+  const int64_t b0 = (int64_t)blockIdx.x * kGtB;
+  const int i0 = blockIdx.y * kGtN;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* Wf = a.W + (int64_t)f * a.Ko * a.Kred;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < a.Ko; k0 += kGtK) {
+    for (int q = tid; q < kGtB * kGtK; q += 256) {
+      const int bb = q / kGtK, k = q - bb * kGtK;  // consecutive threads: consecutive outputs of a sample
+      const int64_t b = b0 + bb;
+      float r = 0.f;
+      if (b < a.B && k0 + k < a.Ko) {
+        const float g = pull_grad(a.gs, f, b, a.Ko, k0 + k);
+        if (g != 0.f) r = g * expf(mrow[(int64_t)f * a.B + b] - a.y[((int64_t)f * a.B + b) * a.Ko + k0 + k]);
+      }
+      rs[k][bb] = r;
+    }
+    for (int q = tid; q < kGtK * kGtN; q += 256) {
+      const int k = q / kGtN, ii = q - k * kGtN;  // consecutive threads: consecutive reduction indices
+      ws[k][ii] = (k0 + k < a.Ko && i0 + ii < a.Kred) ? __ldg(Wf + (int64_t)(k0 + k) * a.Kred + i0 + ii) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kGtK; ++k) {
+      const float4 rv = *reinterpret_cast<const float4*>(&rs[k][4 * ty]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[k][4 * tx]);
+      const float r4[4] = {rv.x, rv.y, rv.z, rv.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(r4[p], w4[q], acc[p][q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int64_t b = b0 + 4 * ty + p;
+    if (b >= a.B) continue;
+    const float m = mrow[(int64_t)f * a.B + b];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + 4 * tx + q;
+      if (i >= a.Kred) continue;
+      const float du = expf(gather_u(a, f, b, i) - m) * acc[p][q];
+      if (!a.concat) {
+        a.gin[((int64_t)f * a.B + b) * a.Ki + i] = du;
+      } else {
+        const int h = i / a.Ki;
+        a.gin[(((int64_t)f * a.H + h) * a.B + b) * a.Ki + (i - h * a.Ki)] = du;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Single-output layers (Ko = 1: the root sum of a circuit).  One warp per sample, the weight
 // row in registers; the batch reduction of dW goes through per-block partials.
 // ------------------------------------------------------------------------------------------
@@ -308,6 +446,17 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
     if (kmax <= 32) return launch_dense_fwd_small<1, 16>(a, F, c);
     if (kmax <= 64) return launch_dense_fwd_small<2, 16>(a, F, c);
     return launch_dense_fwd_small<4, 8>(a, F, c);
+  }
+  if (c.ws != nullptr && c.ws_bytes >= (size_t)F * a.B * 4) {  // tiled: row shifts, then 64 x 64 tiles
+    float* mrow = (float*)c.ws;
+    dim3 g1((int)min64(ceil_div(a.B, 8), 8 * kNumSMs), F);
+    dense_rowmax_generic<<<g1, 256, 0, c.stream>>>(a, mrow);
+    CKB_LAUNCH_CHECK();
+    dim3 g2(ceil_div(a.B, kGtB), ceil_div(a.Ko, kGtN), F);
+    dense_fwd_tiled_generic<<<g2, 256, 0, c.stream>>>(a, mrow);
+    CKB_LAUNCH_CHECK();
+    c.launches += 2;
+    return CKB_OK;
   }
   const int e_stride = (a.Kred + 3) & ~3;
   int nwarps = 8;
@@ -746,17 +895,27 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   float* mrow = nullptr;
-  if (dW) {
+  if (dW || ws_bytes >= (size_t)F * a.B * 4) {
     if (ws_bytes < (size_t)F * a.B * 4) {
       set_error("dense_bwd: workspace too small (%zu < %zu)", ws_bytes, (size_t)F * a.B * 4);
       return CKB_ERR_WORKSPACE;
     }
     mrow = (float*)ws;
   }
-  dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
-  dense_bwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride, r_stride, mrow);
-  CKB_LAUNCH_CHECK();
-  c.launches++;
+  if (mrow != nullptr) {  // tiled du (see dense_fwd_tiled_generic)
+    dim3 g1((int)min64(ceil_div(a.B, 8), 8 * kNumSMs), F);
+    dense_rowmax_generic<<<g1, 256, 0, c.stream>>>(a, mrow);
+    CKB_LAUNCH_CHECK();
+    dim3 g2(ceil_div(a.B, kGtB), ceil_div(a.Kred, kGtN), F);
+    dense_du_tiled_generic<<<g2, 256, 0, c.stream>>>(a, mrow);
+    CKB_LAUNCH_CHECK();
+    c.launches += 2;
+  } else {
+    dim3 grid((int)min64(ceil_div(a.B, nwarps), 8 * kNumSMs), F);
+    dense_bwd_generic<<<grid, nwarps * 32, smem, c.stream>>>(a, e_stride, r_stride, mrow);
+    CKB_LAUNCH_CHECK();
+    c.launches++;
+  }
   if (dW) {
     dim3 g2(ceil_div(a.Kred, kDwTi), ceil_div(a.Ko, kDwTo), F);
     dense_dw_generic<<<g2, 256, 0, c.stream>>>(a, mrow, dW);
@@ -877,7 +1036,14 @@ int tucker_fwd(const ckb_step_desc_t& d, Ctx& c) {
   }
   float* kron = (float*)c.ws;
   if (int rc = kronecker_into(d, c, kron)) return rc;
-  return run_dense_fwd(tucker_args(d, c, kron), d.num_folds, c);
+  // the dense block may use scratch of its own (row shifts of the tiled generic kernels): behind kron
+  const size_t used = (kron_bytes + 255) & ~(size_t)255;
+  Ctx c2 = c;
+  c2.ws = c.ws_bytes > used ? c.ws + used : nullptr;
+  c2.ws_bytes = c.ws_bytes > used ? c.ws_bytes - used : 0;
+  const int rc = run_dense_fwd(tucker_args(d, c, kron), d.num_folds, c2);
+  c.launches = c2.launches;
+  return rc;
 }
 
 int tucker_bwd(const ckb_step_desc_t& d, Ctx& c) {
