@@ -505,6 +505,10 @@ def run_b200(args):
         "kernel_ms": t, "kernel_share_of_step": t / step_ms_sum,
         "algorithmic_bytes": nbytes, "whole_step": whole,
     }
+    if f"{d}_bytes_moved" in r:
+        # this launch reads a fused (pre-summed) input block: fewer bytes than the formula charges it
+        common["bytes_moved"] = r[f"{d}_bytes_moved"]
+        common["achieved_on_bytes_moved_gbs"] = r[f"{d}_bytes_moved"] / (t * 1e-3) / 1e9
     if r["kind"] == "tucker":
         # the Tucker contraction is tensor-pipe bound: 2*Ko*Ki^2 flop per (fold, sample) forward,
         # twice that backward; the kernels run it as 3xTF32 (three tf32 MMAs per product)

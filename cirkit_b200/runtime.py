@@ -1394,6 +1394,14 @@ def profile_steps(rt: PlanRuntime, x: Tensor, leaves: Sequence[Tensor], iters: i
             res.append({"step": es.label, "kind": es.label.split(":")[1], "F": plan.steps[es.out_sid].num_folds,
                         "fwd_ms": t, "fwd_launches": n, "fwd_bytes": fb, "bwd_bytes": bb,
                         "fwd_flops": ff, "bwd_flops": bf})
+            if es.table_input is not None:
+                # The SURVEY formula charges the layer its H input rows; since the gather fusion the
+                # launches move the gathered block u instead (forward: table slices + x in, u out and in
+                # again, y out; backward: u, y, g in, du out).  Reported next to the formula's bytes.
+                s_ = plan.steps[es.out_sid]
+                blk = s_.num_folds * B * s_.num_input_units * 4
+                res[-1]["fwd_bytes_moved"] = fb - s_.arity * blk + 2 * blk
+                res[-1]["bwd_bytes_moved"] = bb - (s_.arity - 1) * blk
         for i in reversed(range(S)):
             t, n = timed(bwd, i, i + 1, 0)
             res[i + 1]["bwd_ms"] = t
