@@ -319,9 +319,30 @@ class BatchShardedCircuit(nn.Module):
         if rt is None or not hasattr(rt, "grad_sync") or rt.needs_batch or rt.is_complex:
             return False
         dev = next(self.circuit.parameters()).device
-        if dev.type != "cuda" or not NvlsGradientReducer.available(dev):
+        ok = dev.type == "cuda" and NvlsGradientReducer.available(dev)
+        red = None
+        if ok:
+            # Dry run on a small buffer: the symmetric-memory rendezvous and the multicast mapping are
+            # the parts that can fail on a given box (driver, fabric manager, container limits).
+            try:
+                red = NvlsGradientReducer(self.group, average, num_ctas, fused)
+                n = 4096
+                buf = red.alloc(n, dev)
+                if buf is not None:
+                    buf.fill_(1.0)
+                    out = torch.empty(n, dtype=torch.float32, device=dev)
+                    red.finish(buf, out)
+                    ok = bool((out == (1.0 if average else float(self.world_size))).all())
+            except Exception:  # pragma: no cover - depends on the box
+                ok = False
+        # every rank must take the same path (the collectives differ)
+        if self.world_size > 1 and dev.type == "cuda":
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = bool(flag.item())
+        if not ok:
             return False
-        rt.grad_sync = NvlsGradientReducer(self.group, average, num_ctas, fused)
+        rt.grad_sync = red
         return True
 
     def overlap_gradient_sync(self, chunks: int = 4, *, average: bool = False,
