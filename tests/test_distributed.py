@@ -262,3 +262,29 @@ def test_gradient_stages_of_other_plans(name, which):
     assert torch.equal(flat, torch.ones_like(flat))
     if name == "pd32_cp_k4":
         assert len(stages) > 5 and any(es.folds is not None for es in sync)
+
+
+def test_nvls_reducer_is_a_no_op_in_a_single_process():
+    """World size 1: the in-switch reducer owns no buffer (the runtime keeps writing into its own
+    flat tensor) and `finish` only reports the bytes it was told about."""
+    from cirkit_b200.distributed import NvlsGradientReducer
+
+    red = NvlsGradientReducer()
+    assert red.alloc(1000, torch.device("cpu")) is None
+    red([torch.zeros(10), torch.zeros(6)])
+    assert red.finish() == 64
+    assert red.finish() == 0
+
+
+def test_graph_policy_follows_the_arena_size():
+    """CUDA-graph replay is on where the host is the bottleneck (activation arenas up to 256 MB)
+    and off for plans with per-call PyTorch inputs (host logic only, no device)."""
+    from cirkit_b200.runtime import PlanRuntime
+
+    rt = PlanRuntime(Golden("qt28_cp_k64").plan)
+    assert rt.use_graphs == "auto"
+    assert rt.graphs_for(256) and not rt.graphs_for(2048)  # 154 MB / 1.23 GB of activations
+    rt.use_graphs = False
+    assert not rt.graphs_for(8)
+    rt.use_graphs = True
+    assert rt.graphs_for(8192)
