@@ -85,3 +85,28 @@ def test_complex_plans():
     real.semiring = "tropical"
     with pytest.raises(ValueError, match="semiring"):
         real.validate()
+
+
+def test_gather_fusion_marks_only_the_fused_plan():
+    """`PlanRuntime._fuse_table_inputs` (host logic, no device): the first CP-T layer of a QuadTree
+    circuit gathers its inputs from the fused table pair (CKB_STEP_TABLE_INPUT) and the pair skips
+    its own gather (CKB_STEP_NO_GATHER) -- in the FUSED execution plan only.  The plain plan
+    shares step objects with it and must stay untouched (it serves small batches and masks)."""
+    from cirkit_b200 import _lib
+    from cirkit_b200.runtime import STEP_TABLE_DENSE, PlanRuntime
+    from helpers import Golden
+
+    for name in ("qt28_cp_k64", "qt8_cp_k4", "qt28_cp_k32"):
+        rt = PlanRuntime(Golden(name).plan)
+        fused, plain = rt.exec_plans["fused"], rt.exec_plans["plain"]
+        assert fused[0].kind == STEP_TABLE_DENSE and fused[0].flags & _lib.STEP_NO_GATHER
+        assert fused[1].flags & _lib.STEP_TABLE_INPUT and fused[1].table_input == (0, 1, fused[0].scratch[0])
+        assert all(es.flags == 0 and es.table_input is None for es in plain)
+        assert all(es.flags == 0 for es in fused[2:])
+        assert rt.exec_plans["masked"] is plain
+    # no fusion: the pair's output has other readers / the reader is not a CP-T layer over it
+    for name in ("qg8_cp_k4", "pd32_cp_k4", "qt8_tucker_k4", "qt8_cp_k6_embedding"):
+        rt = PlanRuntime(Golden(name).plan)
+        assert all(es.table_input is None for es in rt.exec_plans["fused"])
+    off = PlanRuntime(Golden("qt8_cp_k4").plan, fuse_table_inputs=False)
+    assert all(es.flags == 0 for es in off.exec_plans["fused"])
