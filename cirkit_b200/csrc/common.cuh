@@ -41,11 +41,15 @@ struct PerDeviceOnce {
 // ------------------------------------------------------------------ programmatic dependent launch
 // The step is a chain of ~40 dependent launches, many of them 10-20 us long: with plain stream
 // order every boundary costs the drain of one grid plus the launch latency and prologue of the
-// next.  Kernels that opt in call pdl_launch_dependents() first (the next grid of the stream may
-// be scheduled as soon as every CTA of this one has started), do the part of their prologue that
-// touches no global memory written by earlier kernels of the step (barrier set-up, TMEM
-// allocation, weight staging), and call pdl_wait() before anything else: it returns when the
-// preceding grid has completed and its writes are visible.  Launch them with launch_pdl().
+// next.  Kernels that opt in do the part of their prologue that touches no global memory written
+// by kernels of the same step first (barrier set-up, TMEM allocation, weight staging), then
+// pdl_wait() -- it returns when the preceding grid has completed and its writes are visible --
+// and only THEN pdl_launch_dependents(): the next grid of the stream may be scheduled as soon as
+// every CTA of this one has passed its own wait (or exited).  The order matters: a grid that
+// triggers before it has waited lets its successor start while its PREDECESSOR is still running,
+// and the successor's prologue (which reads effective weights) would then race with a parameter-op
+// kernel two launches back.  With wait-then-trigger, "grid N+1 is running" implies "grid N-1 is
+// complete" for every N.  Launch them with launch_pdl().
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }

@@ -359,8 +359,8 @@ __device__ __forceinline__ float ko1_load(const DenseArgs& a, int f, int64_t b, 
 }
 
 __global__ void dense_ko1_fwd_kernel(DenseArgs a) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float w[kKo1MaxPerLane];
@@ -380,8 +380,8 @@ __global__ void dense_ko1_fwd_kernel(DenseArgs a) {
 }
 
 __global__ void dense_ko1_bwd_kernel(DenseArgs a) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[8][32 * kKo1MaxPerLane];
   const int f = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;

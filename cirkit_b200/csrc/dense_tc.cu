@@ -104,7 +104,6 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   const int n_tiles_total = (int)((a.B + TM - 1) / TM);
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
-  pdl_launch_dependents();
   if (n_tiles <= 0) return;
 
   // input row pointers first: their (dependent) index loads overlap the rest of the setup
@@ -130,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 2) dense_tc_fwd_kernel(DenseArgs a, 
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
   pdl_wait();
+  pdl_launch_dependents();  // (after the wait: see common.cuh)
 
   if (warp == kMmaWarp) {
     // ================= MMA issuer =================

@@ -139,7 +139,6 @@ dense_tc_bwd3_kernel(DenseArgs a, const __grid_constant__ CUtensorMap tmX,
   const int n_tiles_total = (int)(a.B / TM3);
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int n_tiles = min(n_tiles_total, t_begin + tiles_per_cta) - t_begin;
-  pdl_launch_dependents();
   if (n_tiles <= 0) return;
 
   // The producer lane sets up its own ring barriers and puts the first kStages slots in flight
@@ -193,6 +192,7 @@ dense_tc_bwd3_kernel(DenseArgs a, const __grid_constant__ CUtensorMap tmX,
   tc_fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
   pdl_wait();  // everything below may touch global memory the preceding grid wrote (du, dW slabs)
+  pdl_launch_dependents();  // (after the wait: see common.cuh)
   // TMEM columns: D1 [0,128) (main | correction), D2 [128,256), r_hi [256,320), r_lo [320,384)
   constexpr uint32_t kD2Col = 128, kRhiCol = 256, kRloCol = 320;
 

@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(256) table_pair_gather_smem_kernel(
     const float* __restrict__ T2, const int32_t* __restrict__ scope_var, const int64_t* __restrict__ folds,
     const void* __restrict__ xT, int x_is_float, float* __restrict__ u, int64_t B, int K, int V, int H,
     int KT) {
-  pdl_launch_dependents();
   extern __shared__ __align__(16) float tab[];                     // [H][V][KT]
   int* st = reinterpret_cast<int*>(tab + (size_t)H * V * KT);      // [2][H][kStageRows] row offsets
   const int f = blockIdx.y, k0 = blockIdx.x * KT;
@@ -212,6 +211,7 @@ __global__ void __launch_bounds__(256) table_pair_gather_smem_kernel(
     var[h] = h < H ? scope_var[tfs[h]] : 0;
   }
   pdl_wait();
+  pdl_launch_dependents();
 #pragma unroll
   for (int h = 0; h < kPairMaxH; ++h) {
     const int64_t tf = tfs[h];
@@ -324,8 +324,8 @@ table_bwd_kernel(GradSrc gs, const int32_t* __restrict__ scope_var, const void* 
   uint16_t* list = xs + chunk;                           // [chunk] sample ids grouped by state
   __shared__ const float* grows[kTableMaxCons];
   __shared__ int n_cons_s;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.y;
   const int k0 = blockIdx.z * (32 * NT);
   const int var = scope_var[f];
@@ -791,8 +791,8 @@ int external_bwd(const ckb_step_desc_t& d, Ctx& c) {
 // ------------------------------------------------------------------------------------------
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                        int64_t n, int splits) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     // fixed left-to-right order (deterministic), but 16 independent loads in flight at a time
@@ -814,8 +814,8 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
 // sum is ~8 dependent loads deep instead of 256.
 __global__ void reduce_partials_wide_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                             int64_t n, int splits) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;

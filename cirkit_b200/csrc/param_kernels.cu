@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) table_fwd_t_smem_kernel(const float* __re
                                                                float* __restrict__ dst, int K, int V) {
   extern __shared__ float tile[];  // [32][V + 1]
   __shared__ float lse[32];
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.y, k0 = blockIdx.x * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = min(32, K - k0), ld = V + 1;
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(256) table_bwd_t_smem_kernel(const float* __re
                                                                float* __restrict__ dsrc, int K, int V) {
   extern __shared__ float tile[];  // g [32][V + 1], then (MODE 0) exp(T) [32][V + 1]
   __shared__ float colsum[32];
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.y, k0 = blockIdx.x * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = min(32, K - k0), ld = V + 1;
@@ -342,8 +342,8 @@ struct MultiSoftmax {
 constexpr int kMsRows = 4;
 template <bool BWD>
 __global__ void multi_softmax_kernel(const __grid_constant__ MultiSoftmax m) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int64_t total = m.row_end[m.n - 1];
   if (m.all64) {
