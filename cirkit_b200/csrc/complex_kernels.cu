@@ -1,11 +1,10 @@
 // 'complex-lse-sum' building blocks, FP32 SIMT (first correct version: one warp per (fold, sample)).
 //
-// EXPERIMENTAL -- written at the end of round 1 without GPU time left: compiled for sm_100a, NOT
-// yet run.  Nothing in the plan executor dispatches here (PlanRuntime refuses complex plans); the
-// entry points exist so that the kernels can be checked against the oracle's complex path
-// (oracle/reference_eval.py, fixtures tests/golden/*_complex*.npz) layer by layer before the
-// runtime learns about complex arenas.  tests/test_gpu_zzz_complex_kernels.py is that check and
-// only runs with CKB_EXPERIMENTAL=1.
+// Per-layer entry points (ckb_complex_*), validated on the B200 in round 2 against the oracle's
+// complex path (oracle/reference_eval.py, fixtures tests/golden/*_complex*.npz):
+// tests/test_gpu_zzz_complex_kernels.py.  The plan executor runs complex plans through its own
+// step kernels (complex_plan.cu, deterministic weight gradients); these stay as unit-testable
+// building blocks (their weight gradients use atomics).
 //
 // Reference semantics (cirkit/backend/torch):
 //   * activations are complex logarithms, stored interleaved (re, im) as float2, layout

@@ -57,7 +57,7 @@ bool dense_tc_bwd3_ok(const DenseArgs& a, int rows64);
 size_t dense_tc_bwd3_ws(int F, int64_t B);
 int dense_tc_bwd3(const DenseArgs& a, int F, float* dW, Ctx& c, char* ws, size_t ws_bytes);
 
-// Ki = Ko = 128 forward on tcgen05 (dense128_tc.cu): EXPERIMENTAL, opt-in (CKB_OPT_TC_FAST_MATH bit 9)
+// Ki = Ko = 128 on tcgen05 (dense128_tc.cu), bit 9 of CKB_OPT_TC_FAST_MATH (set in the default value)
 int tc_flags();  // CKB_OPT_TC_FAST_MATH bits (dense_tc.cu)
 bool dense128_tc_ok(const DenseArgs& a);
 int dense128_tc_fwd(const DenseArgs& a, int F, Ctx& c);

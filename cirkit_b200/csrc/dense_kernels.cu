@@ -434,7 +434,7 @@ static int run_dense_fwd(const DenseArgs& a, int F, Ctx& c) {
     if (rc <= 0) return rc;
   }
   if (dense32_ok(a)) return dense32_fwd(a, F, c);
-  if (dense128_tc_ok(a)) return dense128_tc_fwd(a, F, c);  // experimental, off by default
+  if (dense128_tc_ok(a)) return dense128_tc_fwd(a, F, c);  // Ki = Ko = 128 on tcgen05
   if (dense_ko1_ok(a)) {
     dim3 grid(dense_ko1_blocks(F, a.B), F);
     CKB_CUDA_CHECK(launch_pdl(dense_ko1_fwd_kernel, grid, dim3(256), 0, c.stream, a));
@@ -839,7 +839,7 @@ static int run_dense_bwd(DenseArgs a, int F, float* dW, Ctx& c, char* ws, size_t
   }
   const size_t n = (size_t)F * a.Ko * a.Kred;
   if (dense32_ok(a)) return dense32_bwd(a, F, dW, c, ws, ws_bytes);
-  if (dense128_tc_ok(a)) {  // experimental, off by default
+  if (dense128_tc_ok(a)) {  // Ki = Ko = 128 on tcgen05
     const int rc = dense128_tc_bwd(a, F, dW, c, ws, ws_bytes);
     if (rc <= 0) return rc;
   }

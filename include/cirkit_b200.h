@@ -280,8 +280,9 @@ int ckb_set_option(int32_t option, int32_t value);
 /* Copies the device-side debug timeline (clock64 stamps of the tcgen05 kernels) to host memory. */
 int ckb_debug_read(void* dst, size_t bytes);
 
-/* ---- 'complex-lse-sum' building blocks (EXPERIMENTAL: compiled, not yet validated on a GPU; the
- * plan executor does not use them and refuses complex plans).  Complex tensors are interleaved
+/* ---- 'complex-lse-sum' per-layer building blocks (validated on the B200 in round 2,
+ * tests/test_gpu_zzz_complex_kernels.py; the plan executor runs complex plans through its own step
+ * kernels, csrc/complex_plan.cu, and does not call these).  Complex tensors are interleaved
  * (re, im) float pairs in the (fold, batch, unit) layout.  Replaces, per layer:
  * ComplexLSESumSemiring.apply_reduce semiring.py:440-476 under TorchCPTLayer.forward
  * layers/optimized.py:171-178 (x1 == NULL: an arity-1 TorchSumLayer, layers/inner.py:266-273),
